@@ -1,0 +1,246 @@
+/*
+ * lzfear_b200.h — C ABI of the B200-native LZ4 block codec that drops in for the
+ * hot path of the pure-Rust `lz-fear` crate.
+ *
+ * The reference has no FFI of its own (`#![forbid(unsafe_code)]`, src/lib.rs:1); the seam this
+ * ABI replaces is the pair of generic Rust calls
+ *     compress2(&in_buffer, window_offset, &mut table, &mut NoPartialWrites(&mut out[..n]))
+ *                                                        src/framed/compress.rs:242-243
+ *     raw::decompress_raw(buf, dec_prefix, output, self.block_maxsize)
+ *                                                        src/framed/decompress.rs:247-248
+ * batched over many independent blocks, plus the per-block loop around them
+ * (src/framed/compress.rs:221-276, src/framed/decompress.rs:197-279) and the XXH32 call
+ * sites (twox-hash; src/framed/compress.rs:172,197-199,233-235,260-262,279-281).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary
+ *   - `d_` pointers are device memory on the ctx's GPU, everything else is host memory
+ *   - functions return a call-level code (LZF_SUCCESS or < 0); codec results are reported
+ *     PER BLOCK in `status[]` so one bad block never poisons a batch
+ *   - there is NO CPU fallback: without a CUDA device every entry point fails with
+ *     LZF_ERR_NO_DEVICE / LZF_ERR_CUDA
+ *   - batched device calls are asynchronous on `stream` (a cudaStream_t passed as void*);
+ *     host-buffer calls synchronise before returning
+ *   - nothing here throws or aborts across the ABI
+ */
+#ifndef LZFEAR_B200_H
+#define LZFEAR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LZF_ABI_VERSION 1
+
+/* ---- call-level return codes ---- */
+enum {
+    LZF_SUCCESS = 0,
+    LZF_ERR_INVALID_ARG = -1,
+    LZF_ERR_CUDA = -2,
+    LZF_ERR_NO_DEVICE = -3,
+    LZF_ERR_OOM = -4,
+    LZF_ERR_UNSUPPORTED = -5
+};
+
+/* ---- per-block codec status ----
+ * 1..4 = raw::DecodeError variants in declaration order (src/raw/decompress.rs:7-17);
+ * 5    = the bounded writer refused a write (io::ErrorKind::ConnectionAborted from
+ *        NoPartialWrites, src/framed/compress.rs:298-301) => the frame layer stores the block raw;
+ * 6    = the physical output buffer was too small (reference Vec would simply have grown);
+ * 7    = a reference assert!/expect() would have fired (e.g. U16Table with > 65535 bytes,
+ *        src/raw/compress/mod.rs:167). */
+enum {
+    LZF_OK = 0,
+    LZF_UNEXPECTED_END = 1,
+    LZF_MEMORY_LIMIT_EXCEEDED = 2,
+    LZF_ZERO_DEDUP_OFFSET = 3,
+    LZF_INVALID_DEDUP_OFFSET = 4,
+    LZF_WRITER_FULL = 5,
+    LZF_OUTPUT_CAP = 6,
+    LZF_PANIC = 7
+};
+
+/* ---- frame-level status (DecompressionError src/framed/decompress.rs:16-36,
+ *      CompressionError src/framed/compress.rs:15-23) ---- */
+enum {
+    LZF_F_OK = 0,
+    LZF_F_INPUT_ERROR = 10,
+    LZF_F_CODEC_ERROR = 11,           /* detail = per-block codec status 1..4 */
+    LZF_F_HEADER_PARSE_ERROR = 12,    /* detail = LZF_P_* */
+    LZF_F_WRONG_MAGIC = 13,
+    LZF_F_HEADER_CHECKSUM_FAIL = 14,
+    LZF_F_BLOCK_CHECKSUM_FAIL = 15,
+    LZF_F_FRAME_CHECKSUM_FAIL = 16,
+    LZF_F_BLOCK_LENGTH_OVERFLOW = 17,
+    LZF_F_BLOCK_SIZE_OVERFLOW = 18,
+    LZF_F_INVALID_BLOCK_SIZE = 20,
+    LZF_F_WRITE_ERROR = 21,           /* caller's output buffer too small */
+    LZF_F_PANIC = 22                  /* reference would panic (e.g. header.rs:55 unwrap) */
+};
+enum {                                /* header::ParseError, src/framed/header.rs:18-28 */
+    LZF_P_UNIMPLEMENTED_BLOCKSIZE = 1,
+    LZF_P_UNSUPPORTED_VERSION = 2,
+    LZF_P_RESERVED_FLAG_BITS = 3,
+    LZF_P_RESERVED_BD_BITS = 4
+};
+
+/* EncoderTable implementations, src/raw/compress/mod.rs:27-36 (U32Table), :78-101 (U16Table) */
+enum { LZF_TABLE_U32 = 0, LZF_TABLE_U16 = 1 };
+
+/* high bit of a block length word: "stored, not compressed" (src/framed/mod.rs:18) */
+#define LZF_INCOMPRESSIBLE 0x80000000u
+#define LZF_MAGIC 0x184D2204u          /* src/framed/mod.rs:16 */
+#define LZF_WINDOW_SIZE 65536u         /* src/framed/mod.rs:20 */
+
+typedef struct lzf_ctx lzf_ctx;
+
+int lzf_abi_version(void);
+/* Creates a context bound to CUDA device `device`.  Fails (LZF_ERR_NO_DEVICE) without a GPU. */
+int lzf_create(int device, lzf_ctx** ctx);
+void lzf_destroy(lzf_ctx* ctx);
+/* Human-readable text for the last failing call on this ctx (valid until the next call). */
+const char* lzf_last_error(const lzf_ctx* ctx);
+/* Number of kernels this ctx has launched so far (bench.py's gpu_launches). */
+uint64_t lzf_launch_count(const lzf_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------
+ * Batched block compress — replaces the per-block `compress2` call of
+ * src/framed/compress.rs:242-243 (body: src/raw/compress/mod.rs:165-238), each block from a fresh
+ * zeroed table with cursor 0 (independent blocks, src/framed/compress.rs:265-270).
+ *
+ *   block b reads  d_in[d_in_off[b] .. + d_in_len[b]]
+ *   and writes     d_out[d_out_off[b] .. + cap_b], cap_b = d_out_cap ? d_out_cap[b] : d_in_len[b]
+ *                  (cap = own plaintext length is the NoPartialWrites bound of compress.rs:242)
+ *   d_out_len[b]   bytes written when d_status[b] == LZF_OK
+ *   d_status[b]    LZF_OK | LZF_WRITER_FULL (store raw; compress.rs:250-255) | LZF_PANIC
+ *   d_xxh_plain    nullable: XXH32(seed 0) of the block's plaintext
+ *   d_xxh_stored   nullable: XXH32 of the bytes the frame stores for this block — the compressed
+ *                  bytes if LZF_OK, else the plaintext (block checksum, compress.rs:259-263)
+ *   hashlog        0 or 12 = reference (src/raw/compress/mod.rs:15); 13..16 = larger-table extension
+ *   table_kind     LZF_TABLE_U32 (framed path, compress.rs:202) or LZF_TABLE_U16 (src/lib.rs:26-27)
+ * Output bytes are identical to the reference's for the same input.
+ * ------------------------------------------------------------------------------------------ */
+int lzf_compress_blocks(lzf_ctx* ctx,
+                        const uint8_t* d_in, const uint64_t* d_in_off, const uint32_t* d_in_len,
+                        uint32_t nblocks, uint32_t hashlog, uint32_t table_kind,
+                        uint8_t* d_out, const uint64_t* d_out_off, const uint32_t* d_out_cap,
+                        uint32_t* d_out_len, int32_t* d_status,
+                        uint32_t* d_xxh_plain, uint32_t* d_xxh_stored, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Batched block decompress — replaces `raw::decompress_raw` at src/framed/decompress.rs:247-248
+ * (body: src/raw/decompress.rs:58-138) and the stored-block copy at :249-251.
+ *
+ *   block b reads  d_in[d_in_off[b] .. + (d_in_len[b] & 0x7fffffff)]; if bit 31 of d_in_len[b]
+ *                  is set the block is stored and is copied verbatim
+ *   prefix         nullable triple: history behind the output (dictionary / carry-over window,
+ *                  src/raw/decompress.rs:84-99); block b uses d_prefix[d_prefix_off[b] .. + d_prefix_len[b]]
+ *   output         starts empty at d_out[d_out_off[b]], physical capacity d_out_cap[b]
+ *   d_out_limit[b] the reference's soft `output_limit` (decompress.rs:55-57,72-74)
+ *   d_out_len[b]   decoded length (may exceed d_out_cap[b] with status LZF_OUTPUT_CAP: the
+ *                  length the reference's growing Vec would have reached)
+ *   d_status[b]    LZF_OK or 1..4 with the reference's check precedence, or LZF_OUTPUT_CAP
+ *   d_xxh_plain    nullable: XXH32(seed 0) of the decoded bytes (valid when status == LZF_OK)
+ * ------------------------------------------------------------------------------------------ */
+int lzf_decompress_blocks(lzf_ctx* ctx,
+                          const uint8_t* d_in, const uint64_t* d_in_off, const uint32_t* d_in_len,
+                          uint32_t nblocks,
+                          const uint8_t* d_prefix, const uint64_t* d_prefix_off, const uint32_t* d_prefix_len,
+                          uint8_t* d_out, const uint64_t* d_out_off, const uint32_t* d_out_cap,
+                          const uint32_t* d_out_limit, uint32_t* d_out_len, int32_t* d_status,
+                          uint32_t* d_xxh_plain, void* stream);
+
+/* Batched XXH32 (seed 0) of device byte ranges, one hash per range (content checksums of whole
+ * frames: src/framed/compress.rs:233-235,279-281; src/framed/decompress.rs:276-278,207-211). */
+int lzf_xxh32_ranges(lzf_ctx* ctx, const uint8_t* d_data, const uint64_t* d_off, const uint64_t* d_len,
+                     uint32_t nranges, uint32_t* d_hash, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Single-block host-pointer conveniences mirroring the Rust raw API.
+ *   lzf_raw_compress_into  = compress2(input, 0, &mut fresh table, NoPartialWrites(out[..cap]))
+ *                            (the crate has no `compress_into`; see SURVEY.md "Facts")
+ *   lzf_raw_decompress     = decompress_raw(input, prefix, &mut Vec (empty), output_limit)
+ * Return value: call-level code; *status gets the per-block codec status.
+ * ------------------------------------------------------------------------------------------ */
+int lzf_raw_compress_into(lzf_ctx* ctx, const uint8_t* in, size_t n, uint32_t table_kind, uint32_t hashlog,
+                          uint8_t* out, size_t cap, size_t* written, int32_t* status);
+int lzf_raw_decompress(lzf_ctx* ctx, const uint8_t* in, size_t n, const uint8_t* prefix, size_t plen,
+                       uint8_t* out, size_t out_cap, size_t out_limit, size_t* out_len, int32_t* status);
+/* worst-case compress2 output for n input bytes into an unbounded writer */
+size_t lzf_compress_bound(size_t n);
+
+/* ------------------------------------------------------------------------------------------
+ * Frame layer — CompressionSettings (src/framed/compress.rs:36-157) as a POD.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t independent_blocks;     /* default 1  compress.rs:47 */
+    int32_t block_checksums;        /* default 0  compress.rs:48 */
+    int32_t content_checksum;       /* default 1  compress.rs:49 */
+    uint64_t block_size;            /* default 4 MiB; 64 KiB/256 KiB/1 MiB/4 MiB  compress.rs:50, header.rs:73-80 */
+    const uint8_t* dictionary;      /* nullable   compress.rs:113-117 */
+    uint64_t dictionary_len;
+    int32_t has_dictionary_id;      /* dictionary() sets both; dictionary_id_nonsense_override() only this */
+    uint32_t dictionary_id;
+    int32_t has_content_size;       /* compress_with_size / compress_with_size_unchecked  compress.rs:142-157 */
+    uint64_t content_size;
+    uint32_t hashlog;               /* 0/12 = reference */
+} lzf_settings;
+
+void lzf_settings_default(lzf_settings* s);
+/* upper bound of a frame's size for n plaintext bytes under `s` */
+size_t lzf_frame_bound(const lzf_settings* s, size_t n);
+
+/* CompressionSettings::compress / compress_with_size* over host buffers
+ * (compress_internal, src/framed/compress.rs:159-282).  *status gets an LZF_F_* code. */
+int lzf_frame_compress(lzf_ctx* ctx, const lzf_settings* s, const uint8_t* in, size_t n,
+                       uint8_t* out, size_t cap, size_t* written, int32_t* status);
+
+/* Many frames in one call (host buffers): frame f = in[in_off[f] .. + in_len[f]] is written to
+ * out[out_off[f] ..] (capacity out_cap[f]); out_len[f]/status[f] per frame.  All blocks of all
+ * frames go through ONE compress launch. */
+int lzf_frames_compress(lzf_ctx* ctx, const lzf_settings* s, const uint8_t* in, const uint64_t* in_off,
+                        const uint64_t* in_len, uint32_t nframes, uint8_t* out, const uint64_t* out_off,
+                        const uint64_t* out_cap, uint64_t* out_len, int32_t* status);
+
+/* Same, device-resident plaintext and frames; offsets/lengths/status are HOST arrays. Synchronises. */
+int lzf_frames_compress_device(lzf_ctx* ctx, const lzf_settings* s, const uint8_t* d_in, const uint64_t* in_off,
+                               const uint64_t* in_len, uint32_t nframes, uint8_t* d_out, const uint64_t* out_off,
+                               const uint64_t* out_cap, uint64_t* out_len, int32_t* status);
+
+/* LZ4FrameReader::new (src/framed/decompress.rs:101-161) */
+typedef struct {
+    uint8_t flags;                  /* Flags bits, header.rs:8-16 */
+    uint64_t block_maxsize;         /* LZ4FrameReader::block_size() */
+    int32_t has_content_size;
+    uint64_t content_size;          /* LZ4FrameReader::frame_size() */
+    int32_t has_dictionary_id;
+    uint32_t dictionary_id;         /* LZ4FrameReader::dictionary_id() */
+    size_t header_len;
+} lzf_frame_info;
+int lzf_frame_parse_header(const uint8_t* in, size_t n, lzf_frame_info* info, int32_t* detail);
+
+/* decompress_frame / into_read_with_dictionary(..).read_to_end (src/framed/decompress.rs:180-288)
+ * over host buffers.  *status = LZF_F_*, *detail = codec status / ParseError kind, *written =
+ * plaintext bytes of the blocks decoded before a failure (what read_to_end had appended),
+ * *consumed = bytes of `in` the reader consumed. */
+int lzf_frame_decompress(lzf_ctx* ctx, const uint8_t* in, size_t n, const uint8_t* dict, size_t dlen,
+                         uint8_t* out, size_t cap, size_t* written, size_t* consumed,
+                         int32_t* status, int32_t* detail);
+
+/* Many frames in one call (host buffers); all blocks of all frames go through ONE decompress launch. */
+int lzf_frames_decompress(lzf_ctx* ctx, const uint8_t* in, const uint64_t* in_off, const uint64_t* in_len,
+                          uint32_t nframes, uint8_t* out, const uint64_t* out_off, const uint64_t* out_cap,
+                          uint64_t* out_len, int32_t* status, int32_t* detail);
+
+/* Same, device-resident frames and plaintext; offsets/lengths/status are HOST arrays. Synchronises. */
+int lzf_frames_decompress_device(lzf_ctx* ctx, const uint8_t* d_in, const uint64_t* in_off, const uint64_t* in_len,
+                                 uint32_t nframes, uint8_t* d_out, const uint64_t* out_off, const uint64_t* out_cap,
+                                 uint64_t* out_len, int32_t* status, int32_t* detail);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,158 @@
+// lzf_common.cuh — device helpers shared by the sm_100a kernels.
+//
+// All helpers are warp-synchronous: every lane of a full 32-lane warp calls them with the same
+// (warp-uniform) arguments unless stated otherwise.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/lzfear_b200.h"
+
+#define LZF_FULL_MASK 0xffffffffu
+
+namespace lzf {
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+
+// ---- unaligned little-endian loads built from aligned 32-bit loads -------------------------
+// An aligned word that contains at least one byte of an allocation lies entirely inside it
+// (cudaMalloc / caching-allocator granularity >= 256 B), so the only over-read these helpers can
+// perform is within the first/last word of the range, never past the allocation.
+
+// 32 bits at byte address p (any alignment). Reads the word holding p and, if needed, the next.
+__device__ __forceinline__ uint32_t ld_u32_unaligned(const uint8_t* p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+    const unsigned sh = (unsigned)(a & 3u) * 8u;
+    const uint32_t lo = w[0];
+    if (sh == 0) return lo;
+    return __funnelshift_r(lo, w[1], sh);
+}
+
+// 64 bits at byte address p (any alignment). `end` = one past the last readable byte of the
+// range; the third word is only touched when it still holds a byte below `end`.
+__device__ __forceinline__ uint64_t ld_u64_unaligned(const uint8_t* p, const uint8_t* end) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+    const unsigned sh = (unsigned)(a & 3u) * 8u;
+    const uint32_t w0 = w[0];
+    const uint32_t w1 = w[1];
+    uint32_t w2 = 0;
+    if (sh != 0 && reinterpret_cast<const uint8_t*>(w + 2) < end) w2 = w[2];
+    const uint32_t lo = __funnelshift_r(w0, w1, sh);
+    const uint32_t hi = __funnelshift_r(w1, w2, sh);
+    return (uint64_t(hi) << 32) | lo;
+}
+
+// ---- XXH32 (public algorithm; twox-hash XxHash32 in the reference) --------------------------
+constexpr uint32_t XP1 = 2654435761u, XP2 = 2246822519u, XP3 = 3266489917u, XP4 = 668265263u, XP5 = 374761393u;
+
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, unsigned r) { return __funnelshift_l(x, x, r); }
+__device__ __forceinline__ uint32_t xxh_round(uint32_t acc, uint32_t x) { return rotl32(acc + x * XP2, 13) * XP1; }
+
+// XXH32(seed 0) of p[0..n) computed by one warp.  Lanes 0..3 each own one accumulator lane of
+// the 16-byte stripes; the tail and avalanche run on lane 0.  Returns the hash in every lane.
+__device__ __forceinline__ uint32_t warp_xxh32(const uint8_t* p, size_t n) {
+    const unsigned lane = lane_id();
+    uint32_t acc = 0;
+    if (lane == 0) acc = XP1 + XP2;
+    else if (lane == 1) acc = XP2;
+    else if (lane == 2) acc = 0;
+    else if (lane == 3) acc = 0u - XP1;
+    const size_t nstripes = n >> 4;
+    if (lane < 4) {
+        const uint8_t* q = p + 4 * lane;
+        const bool aligned = (reinterpret_cast<uintptr_t>(p) & 3u) == 0;
+        size_t s = 0;
+        if (aligned) {
+            const uint32_t* qw = reinterpret_cast<const uint32_t*>(q);
+            for (; s + 8 <= nstripes; s += 8) {
+                uint32_t x[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) x[i] = qw[(s + i) * 4];
+#pragma unroll
+                for (int i = 0; i < 8; i++) acc = xxh_round(acc, x[i]);
+            }
+            for (; s < nstripes; s++) acc = xxh_round(acc, qw[s * 4]);
+        } else {
+            for (; s + 4 <= nstripes; s += 4) {
+                uint32_t x[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) x[i] = ld_u32_unaligned(q + (s + i) * 16);
+#pragma unroll
+                for (int i = 0; i < 4; i++) acc = xxh_round(acc, x[i]);
+            }
+            for (; s < nstripes; s++) acc = xxh_round(acc, ld_u32_unaligned(q + s * 16));
+        }
+    }
+    const uint32_t a0 = __shfl_sync(LZF_FULL_MASK, acc, 0);
+    const uint32_t a1 = __shfl_sync(LZF_FULL_MASK, acc, 1);
+    const uint32_t a2 = __shfl_sync(LZF_FULL_MASK, acc, 2);
+    const uint32_t a3 = __shfl_sync(LZF_FULL_MASK, acc, 3);
+    uint32_t h = 0;
+    if (lane == 0) {
+        if (n >= 16) h = rotl32(a0, 1) + rotl32(a1, 7) + rotl32(a2, 12) + rotl32(a3, 18);
+        else h = XP5;
+        h += (uint32_t)n;
+        const uint8_t* t = p + (nstripes << 4);
+        unsigned rem = (unsigned)(n & 15);
+        while (rem >= 4) {
+            // byte-wise gather keeps us inside [p, p+n)
+            uint32_t x = uint32_t(t[0]) | (uint32_t(t[1]) << 8) | (uint32_t(t[2]) << 16) | (uint32_t(t[3]) << 24);
+            h = rotl32(h + x * XP3, 17) * XP4;
+            t += 4; rem -= 4;
+        }
+        while (rem) { h = rotl32(h + uint32_t(*t) * XP5, 11) * XP1; t++; rem--; }
+        h ^= h >> 15; h *= XP2;
+        h ^= h >> 13; h *= XP3;
+        h ^= h >> 16;
+    }
+    return __shfl_sync(LZF_FULL_MASK, h, 0);
+}
+
+// ---- warp-wide byte copy, non-overlapping, any alignment -----------------------------------
+// Copies n bytes src -> dst.  Short runs go byte-per-lane; long runs align the destination to
+// 16 bytes and move one uint4 per lane per step, re-aligning the source with funnel shifts.
+__device__ __forceinline__ void warp_copy(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, size_t n) {
+    const unsigned lane = lane_id();
+    if (n < 128) {
+        for (size_t i = lane; i < n; i += 32) dst[i] = src[i];
+        return;
+    }
+    // head: bring dst to 16-byte alignment
+    const unsigned head = (unsigned)((16u - (reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u);
+    if (lane < head) dst[lane] = src[lane];
+    dst += head; src += head; n -= head;
+    const size_t nvec = n >> 4;
+    const uintptr_t sa = reinterpret_cast<uintptr_t>(src);
+    const unsigned sh = (unsigned)(sa & 3u) * 8u;
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(sa & ~uintptr_t(3));
+    uint4* dv = reinterpret_cast<uint4*>(dst);
+    if (sh == 0 && (sa & 15u) == 0) {
+        const uint4* sv = reinterpret_cast<const uint4*>(src);
+        for (size_t v = lane; v < nvec; v += 32) dv[v] = sv[v];
+    } else if (sh == 0) {
+        for (size_t v = lane; v < nvec; v += 32) {
+            const uint32_t* s4 = sw + v * 4;
+            dv[v] = make_uint4(s4[0], s4[1], s4[2], s4[3]);
+        }
+    } else {
+        // the 5th word of the last vector holds at least one byte < src+n only if a tail exists;
+        // guard it so we never touch a word fully past the range
+        const uint8_t* send = src + n;
+        for (size_t v = lane; v < nvec; v += 32) {
+            const uint32_t* s4 = sw + v * 4;
+            const uint32_t w0 = s4[0], w1 = s4[1], w2 = s4[2], w3 = s4[3];
+            uint32_t w4 = 0;
+            if (reinterpret_cast<const uint8_t*>(s4 + 4) < send) w4 = s4[4];
+            dv[v] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh),
+                               __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+        }
+    }
+    const size_t done = nvec << 4;
+    const unsigned tail = (unsigned)(n - done);
+    if (lane < tail) dst[done + lane] = src[done + lane];
+}
+
+}  // namespace lzf

@@ -1,0 +1,284 @@
+// lzf_frame.cu — device side of the frame glue around the block kernels:
+//   * XXH32 over byte ranges (block checksums of stored payloads, content checksums of frames)
+//   * compress: per-frame layout scan + parallel assembly of `u32 len | payload | [u32 xxh]`
+//     (src/framed/compress.rs:244-263,277-281)
+//   * decompress: walking the block-length words of device-resident frames
+//     (src/framed/decompress.rs:205-235) and compaction of short non-final blocks
+#include "lzf_common.cuh"
+#include "lzf_frame.cuh"
+
+namespace lzf {
+
+// ------------------------------------------------------------------------------------------
+// XXH32 of ranges: one warp per range
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+xxh32_ranges_kernel(const uint8_t* data, const uint64_t* off, const uint64_t* len, uint32_t nranges, uint32_t* hash) {
+    const uint32_t r = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (r >= nranges) return;
+    const uint32_t h = warp_xxh32(data + off[r], len[r]);
+    if (lane_id() == 0) hash[r] = h;
+}
+
+// ------------------------------------------------------------------------------------------
+// compress: layout.  One warp per frame scans its blocks' stored sizes, decides the position of
+// every block inside the frame, and writes header, EndMark and content checksum.
+// ------------------------------------------------------------------------------------------
+struct LayoutArgs {
+    uint32_t nframes;
+    const uint32_t* first_block; const uint32_t* nblocks;
+    const uint32_t* blk_in_len; const uint32_t* blk_comp_len; const int32_t* blk_status;
+    int block_checksums; int content_checksum;
+    const uint8_t* headers;          // nframes x 20: [0] = header length, [1..] = header bytes
+    uint8_t* out; const uint64_t* out_off; const uint64_t* out_cap;
+    const uint32_t* content_hash;    // per frame (valid when content_checksum)
+    uint64_t* blk_dst;               // out: absolute offset in `out` of each block's length word (~0 = skip)
+    uint64_t* frame_len; int32_t* frame_status;
+};
+
+__global__ void __launch_bounds__(128) frame_layout_kernel(LayoutArgs a) {
+    const unsigned lane = lane_id();
+    const uint32_t f = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (f >= a.nframes) return;
+    const uint32_t b0 = a.first_block[f], nb = a.nblocks[f];
+    const uint32_t hlen = a.headers[(size_t)f * 20];
+    const uint64_t per_block_extra = 4 + (a.block_checksums ? 4 : 0);
+
+    // pass 1: total size + panic detection
+    uint64_t total = 0;
+    int bad = 0;
+    for (uint32_t i = lane; i < nb; i += 32) {
+        const int st = a.blk_status[b0 + i];
+        const uint64_t stored = (st == LZF_OK) ? a.blk_comp_len[b0 + i] : a.blk_in_len[b0 + i];
+        if (st != LZF_OK && st != LZF_WRITER_FULL) bad = 1;
+        total += stored + per_block_extra;
+    }
+    for (int s = 16; s; s >>= 1) total += __shfl_xor_sync(LZF_FULL_MASK, total, s);
+    bad = __any_sync(LZF_FULL_MASK, bad);
+    const uint64_t flen = hlen + total + 4 + (a.content_checksum ? 4 : 0);
+    int status = LZF_F_OK;
+    if (bad) status = LZF_F_PANIC;
+    else if (flen > a.out_cap[f]) status = LZF_F_WRITE_ERROR;
+
+    // pass 2: exclusive scan -> block positions
+    uint64_t run = a.out_off[f] + hlen;
+    for (uint32_t i0 = 0; i0 < nb; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        uint64_t sz = 0;
+        if (i < nb) {
+            const int st = a.blk_status[b0 + i];
+            sz = ((st == LZF_OK) ? a.blk_comp_len[b0 + i] : a.blk_in_len[b0 + i]) + per_block_extra;
+        }
+        uint64_t inc = sz;
+        for (int s = 1; s < 32; s <<= 1) {
+            const uint64_t t = __shfl_up_sync(LZF_FULL_MASK, inc, s);
+            if (lane >= (unsigned)s) inc += t;
+        }
+        if (i < nb) a.blk_dst[b0 + i] = (status == LZF_F_OK) ? run + inc - sz : ~0ull;
+        run += __shfl_sync(LZF_FULL_MASK, inc, 31);
+    }
+    if (status == LZF_F_OK) {
+        uint8_t* o = a.out + a.out_off[f];
+        if (lane < hlen) o[lane] = a.headers[(size_t)f * 20 + 1 + lane];        // compress.rs:200
+        uint8_t* t = a.out + run;
+        if (lane < 4) t[lane] = 0;                                              // EndMark compress.rs:277
+        if (a.content_checksum && lane < 4) t[4 + lane] = (uint8_t)(a.content_hash[f] >> (8 * lane));   // :279-281
+    }
+    if (lane == 0) {
+        a.frame_len[f] = (status == LZF_F_OK) ? flen : 0;
+        a.frame_status[f] = status;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// compress: assembly.  grid = (blocks, slices); every CTA moves one 64 KiB slice of one block's
+// stored payload into the frame; slice 0 also writes the length word and the block checksum.
+// ------------------------------------------------------------------------------------------
+struct AssembleArgs {
+    uint32_t nblocks;
+    const uint8_t* in; const uint64_t* blk_in_off; const uint32_t* blk_in_len;
+    const uint8_t* comp; const uint64_t* blk_comp_off; const uint32_t* blk_comp_len; const int32_t* blk_status;
+    const uint32_t* blk_xxh_stored;  // nullable
+    const uint64_t* blk_dst; uint8_t* out;
+};
+constexpr uint32_t kSliceBytes = 64 * 1024;
+
+__global__ void __launch_bounds__(256) frame_assemble_kernel(AssembleArgs a) {
+    const uint32_t b = blockIdx.x;
+    const uint64_t dst = a.blk_dst[b];
+    if (dst == ~0ull) return;
+    const int st = a.blk_status[b];
+    const bool compressed = st == LZF_OK;
+    const uint32_t stored = compressed ? a.blk_comp_len[b] : a.blk_in_len[b];
+    const uint8_t* src = compressed ? a.comp + a.blk_comp_off[b] : a.in + a.blk_in_off[b];
+    uint8_t* o = a.out + dst;
+    const uint64_t s0 = (uint64_t)blockIdx.y * kSliceBytes;
+    if (blockIdx.y == 0 && threadIdx.x < 4) {
+        const uint32_t word = compressed ? stored : (stored | LZF_INCOMPRESSIBLE);   // compress.rs:247,253
+        o[threadIdx.x] = (uint8_t)(word >> (8 * threadIdx.x));
+        if (a.blk_xxh_stored) o[4 + (uint64_t)stored + threadIdx.x] = (uint8_t)(a.blk_xxh_stored[b] >> (8 * threadIdx.x));   // :259-263
+    }
+    if (s0 >= stored) return;
+    const uint64_t slice = min((uint64_t)kSliceBytes, (uint64_t)stored - s0);
+    // 8 warps x 8 KiB
+    const unsigned warp = threadIdx.x >> 5;
+    const uint64_t w0 = (uint64_t)warp * 8192;
+    if (w0 < slice) warp_copy(o + 4 + s0 + w0, src + s0 + w0, min((uint64_t)8192, slice - w0));
+}
+
+// ------------------------------------------------------------------------------------------
+// decompress: frame walk.  One thread per frame parses the header and chases the block-length
+// words (decompress.rs:205-235).  mode 0 = count blocks, mode 1 = also fill block descriptors.
+// ------------------------------------------------------------------------------------------
+struct WalkFrame {                 // per-frame result
+    int32_t header_status; int32_t header_detail;
+    uint32_t flags; uint32_t nblocks;          // blocks whose payload (and checksum) are fully present
+    uint64_t block_maxsize;
+    int32_t term_status;                       // LZF_F_OK if the EndMark (and content checksum) was read
+    uint32_t content_checksum;
+    uint64_t consumed;
+    uint64_t content_size; uint32_t dictionary_id; uint32_t has_fields;   // bit0 content size, bit1 dict id
+};
+struct WalkArgs {
+    uint32_t nframes; int mode;
+    const uint8_t* in; const uint64_t* in_off; const uint64_t* in_len;
+    WalkFrame* frames;
+    // mode 1
+    const uint32_t* first_block;
+    const uint64_t* out_off; const uint64_t* out_cap;
+    uint64_t* blk_in_off; uint32_t* blk_len_word; uint32_t* blk_checksum;
+    uint64_t* blk_out_off; uint32_t* blk_out_cap; uint32_t* blk_out_limit;
+    uint64_t* blk_payload_len;     // u64 copy of the payload length (for xxh32_ranges)
+};
+
+__device__ __forceinline__ uint32_t rd32_bytes(const uint8_t* p) {
+    return uint32_t(p[0]) | (uint32_t(p[1]) << 8) | (uint32_t(p[2]) << 16) | (uint32_t(p[3]) << 24);
+}
+
+__global__ void __launch_bounds__(64) frame_walk_kernel(WalkArgs a) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= a.nframes) return;
+    const uint8_t* in = a.in + a.in_off[f];
+    const uint64_t n = a.in_len[f];
+    WalkFrame w;
+    lzf_frame_info info;
+    int32_t detail = 0;
+    w.header_status = parse_frame_header(in, n, &info, &detail);
+    w.header_detail = detail;
+    w.flags = info.flags; w.block_maxsize = info.block_maxsize; w.nblocks = 0;
+    w.term_status = LZF_F_INPUT_ERROR; w.content_checksum = 0; w.consumed = 0;
+    w.content_size = info.content_size; w.dictionary_id = info.dictionary_id;
+    w.has_fields = (info.has_content_size ? 1u : 0u) | (info.has_dictionary_id ? 2u : 0u);
+    if (w.header_status == LZF_F_OK) {
+        uint64_t p = info.header_len;
+        const uint64_t bms = info.block_maxsize;
+        const bool bc = (info.flags & kFlagBlockChecksums) != 0;
+        const uint32_t b0 = a.mode ? a.first_block[f] : 0;
+        uint32_t i = 0;
+        for (;;) {
+            if (n - p < 4) { w.term_status = LZF_F_INPUT_ERROR; break; }             // :205
+            const uint32_t word = rd32_bytes(in + p);
+            p += 4;
+            if (word == 0) {                                                         // :206-215
+                if (info.flags & kFlagContentChecksum) {
+                    if (n - p < 4) { w.term_status = LZF_F_INPUT_ERROR; break; }
+                    w.content_checksum = rd32_bytes(in + p);
+                    p += 4;
+                }
+                w.term_status = LZF_F_OK;
+                break;
+            }
+            const uint32_t blen = word & ~LZF_INCOMPRESSIBLE;                        // :217-218
+            if (blen > (uint32_t)bms) { w.term_status = LZF_F_BLOCK_SIZE_OVERFLOW; break; }   // :220-222
+            if (n - p < blen) { w.term_status = LZF_F_INPUT_ERROR; break; }          // :226
+            const uint64_t payload = p;
+            p += blen;
+            uint32_t cks = 0;
+            if (bc) {                                                                // :228-229
+                if (n - p < 4) { w.term_status = LZF_F_INPUT_ERROR; break; }
+                cks = rd32_bytes(in + p);
+                p += 4;
+            }
+            if (a.mode) {
+                const uint32_t b = b0 + i;
+                a.blk_in_off[b] = a.in_off[f] + payload;
+                a.blk_len_word[b] = word;
+                a.blk_payload_len[b] = blen;
+                a.blk_checksum[b] = cks;
+                const uint64_t rel = (uint64_t)i * bms;
+                const uint64_t capf = a.out_cap[f];
+                a.blk_out_off[b] = a.out_off[f] + (rel < capf ? rel : capf);
+                a.blk_out_cap[b] = (uint32_t)(rel < capf ? min(bms, capf - rel) : 0);
+                a.blk_out_limit[b] = (uint32_t)bms;                                  // :248 output_limit = block_maxsize
+            }
+            i++;
+        }
+        w.nblocks = i;
+        w.consumed = p;
+    }
+    if (a.mode == 0) a.frames[f] = w;
+}
+
+// ------------------------------------------------------------------------------------------
+// decompress: compaction (rare).  When a non-final block decodes to fewer than block_maxsize
+// bytes (hand-crafted frames, decompress.rs:165-166), later blocks are moved left so the frame's
+// plaintext is contiguous.  One warp per frame, blocks in order, forward copy (dst < src).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+frame_compact_kernel(uint32_t nframes, const uint32_t* first_block, const uint32_t* nblocks, const uint8_t* needs,
+                     const uint64_t* blk_out_off, const uint32_t* blk_out_len, const uint64_t* out_off, uint8_t* out) {
+    const uint32_t f = blockIdx.x;
+    if (f >= nframes || !needs[f]) return;
+    const unsigned lane = lane_id();
+    uint64_t dst = out_off[f];
+    for (uint32_t i = 0; i < nblocks[f]; i++) {
+        const uint32_t b = first_block[f] + i;
+        const uint64_t src = blk_out_off[b];
+        const uint64_t len = blk_out_len[b];
+        if (src != dst) {
+            for (uint64_t k0 = 0; k0 < len; k0 += 32) {
+                const uint64_t k = k0 + lane;
+                uint8_t v = 0;
+                if (k < len) v = out[src + k];
+                __syncwarp();
+                if (k < len) out[dst + k] = v;
+                __syncwarp();
+            }
+        }
+        dst += len;
+    }
+}
+
+}  // namespace lzf
+
+extern "C" int lzf_launch_xxh32_ranges(const uint8_t* data, const uint64_t* off, const uint64_t* len,
+                                       uint32_t nranges, uint32_t* hash, cudaStream_t s) {
+    if (!nranges) return 0;
+    lzf::xxh32_ranges_kernel<<<(nranges + 3) / 4, 128, 0, s>>>(data, off, len, nranges, hash);
+    return (int)cudaGetLastError();
+}
+extern "C" int lzf_launch_layout(const lzf::LayoutArgs* a, cudaStream_t s) {
+    if (!a->nframes) return 0;
+    lzf::frame_layout_kernel<<<(a->nframes + 3) / 4, 128, 0, s>>>(*a);
+    return (int)cudaGetLastError();
+}
+extern "C" int lzf_launch_assemble(const lzf::AssembleArgs* a, uint32_t max_block_len, cudaStream_t s) {
+    if (!a->nblocks) return 0;
+    uint32_t slices = (max_block_len + lzf::kSliceBytes - 1) / lzf::kSliceBytes;
+    if (slices == 0) slices = 1;
+    dim3 grid(a->nblocks, slices);
+    lzf::frame_assemble_kernel<<<grid, 256, 0, s>>>(*a);
+    return (int)cudaGetLastError();
+}
+extern "C" int lzf_launch_walk(const lzf::WalkArgs* a, cudaStream_t s) {
+    if (!a->nframes) return 0;
+    lzf::frame_walk_kernel<<<(a->nframes + 63) / 64, 64, 0, s>>>(*a);
+    return (int)cudaGetLastError();
+}
+extern "C" int lzf_launch_compact(uint32_t nframes, const uint32_t* first_block, const uint32_t* nblocks,
+                                  const uint8_t* needs, const uint64_t* blk_out_off, const uint32_t* blk_out_len,
+                                  const uint64_t* out_off, uint8_t* out, cudaStream_t s) {
+    if (!nframes) return 0;
+    lzf::frame_compact_kernel<<<nframes, 32, 0, s>>>(nframes, first_block, nblocks, needs, blk_out_off, blk_out_len, out_off, out);
+    return (int)cudaGetLastError();
+}
