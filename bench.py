@@ -1,0 +1,480 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 LZ4 block codec (BASELINE.json / SURVEY.md §8(d)).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch of synthetic input.  Per GPU (weak scaling):
+
+  headline  config 2 — DEcompress 4 GiB of independent 64 KiB blocks ("seq50": ~50 % literal bytes,
+            ~50 % short matches).  `value` = plaintext GiB/s of the batched block call
+            (lzf_decompress_blocks, XXH32 fused) with inputs resident in HBM, CUDA events.
+            `e2e` = the same blocks wrapped in LZ4 frames (16 blocks each, content checksum on),
+            decoded through the host-buffer frame call (lzf_frames_decompress): pinned host frames
+            -> H2D -> walk + decode + checksum kernels -> D2H plaintext, all inside the timed region.
+  also      config 3 — compress 4 MiB text-like blocks with default CompressionSettings (frames of
+            16 blocks), reported under "compress" with its own value / e2e / roofline.
+
+`--impl reference` times the reference's algorithm on the host cores (the CPU oracle port — the
+crate is Rust and cannot be built here) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GiB = float(1 << 30)
+BLOCK2 = 65536                 # config 2 block size
+BLOCKS_PER_FRAME2 = 16
+BLOCK3 = 4 << 20               # config 3 block size (CompressionSettings::default)
+BLOCKS_PER_FRAME3 = 16
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--decomp-gib", type=float, default=4.0, help="config-2 plaintext GiB per GPU")
+    ap.add_argument("--comp-gib", type=float, default=16.0, help="config-3 plaintext GiB per GPU")
+    ap.add_argument("--no-compress", action="store_true", help="skip the config-3 compress section")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); smax = float(p[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU reference legs (oracle port; test/bench infrastructure)
+# ---------------------------------------------------------------------------------------------
+def cpu_decompress_sample(comp_h, off_h, len_h, nblocks, nthreads, reps=3):
+    import oracle
+    out = np.empty(nblocks * BLOCK2, dtype=np.uint8)
+    out_off = np.arange(nblocks, dtype=np.uint64) * BLOCK2
+    cap = np.full(nblocks, BLOCK2, dtype=np.uint32)
+    best = None
+    for _ in range(reps):
+        t = time.perf_counter()
+        olen, st = oracle.decompress_blocks_mt(comp_h, off_h, len_h, out, out_off, cap, cap, nthreads=nthreads)
+        dt = time.perf_counter() - t
+        best = dt if best is None else min(best, dt)
+        assert not st.any() and (olen == BLOCK2).all()
+    return nblocks * BLOCK2 / GiB / best, out
+
+
+def cpu_compress_sample(plain_h, nblocks, nthreads, reps=2):
+    import oracle
+    off = np.arange(nblocks, dtype=np.uint64) * BLOCK3
+    ln = np.full(nblocks, BLOCK3, dtype=np.uint32)
+    out = np.empty(nblocks * BLOCK3, dtype=np.uint8)
+    best = None
+    for _ in range(reps):
+        t = time.perf_counter()
+        olen, st = oracle.compress_blocks_mt(plain_h, off, ln, out, off, nthreads=nthreads)
+        dt = time.perf_counter() - t
+        best = dt if best is None else min(best, dt)
+    return nblocks * BLOCK3 / GiB / best, olen, out
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm (CPU oracle port) on all host cores, bounded sample."""
+    import torch
+    from lz_fear_b200 import workloads as W
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    nb = 8192                                     # 512 MiB of config-2 plaintext per step
+    comp, off, ln = W.seq50_blocks(nb, device="cpu")
+    comp_h = comp.numpy(); off_h = off.numpy().astype(np.uint64); len_h = ln.numpy().astype(np.uint32)
+    for _ in range(max(args.warmup, 1)):
+        cpu_decompress_sample(comp_h, off_h, len_h, nb, cores, reps=1)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        v, _o = cpu_decompress_sample(comp_h, off_h, len_h, nb, cores, reps=1)
+    dt = time.perf_counter() - t
+    value = args.steps * nb * BLOCK2 / GiB / dt
+    line = {
+        "impl": "reference", "metric": "LZ4 block decompress throughput (config 2: 64 KiB independent blocks, seq50)",
+        "value": value, "unit": "GiB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "config2: decompress independent 64 KiB seq50 blocks (bounded sample of %d blocks = %d MiB per step)"
+                               % (nb, nb * BLOCK2 >> 20)},
+        "cpu_baseline": {"value": value, "unit": "GiB/s", "cores": cores, "kind": "port",
+                         "sample": "%d config-2 blocks (%d MiB plaintext) per step, C port of the lz-fear decode loop, one block per task"
+                                   % (nb, nb * BLOCK2 >> 20)},
+        "e2e": {"value": value, "unit": "GiB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from lz_fear_b200 import _native as N
+    from lz_fear_b200 import workloads as W
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the codec has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    ctx = N.Context(local_rank)
+    peak_gbs, peak_src = measured_peak()
+    K, Wm = args.steps, max(args.warmup, 3)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # =========================================================================================
+    # config 2: decompress
+    # =========================================================================================
+    nb = max(BLOCKS_PER_FRAME2, int(args.decomp_gib * GiB) // BLOCK2 // BLOCKS_PER_FRAME2 * BLOCKS_PER_FRAME2)
+    chunk = 4096
+    comp = torch.empty(nb * BLOCK2, dtype=torch.uint8, device=dev)
+    in_len = torch.empty(nb, dtype=torch.int32, device=dev)
+    for b0 in range(0, nb, chunk):
+        n = min(chunk, nb - b0)
+        c, _o, l = W.seq50_blocks(n, seed=0x4C5A0002 + 7919 * (rank * 1000003 + b0), device=dev)
+        comp[b0 * BLOCK2:(b0 + n) * BLOCK2] = c
+        in_len[b0:b0 + n] = l
+        del c, l
+    in_off = torch.arange(nb, device=dev, dtype=torch.int64) * BLOCK2
+    plain = torch.empty(nb * BLOCK2, dtype=torch.uint8, device=dev)
+    cap = torch.full((nb,), BLOCK2, dtype=torch.int32, device=dev)
+    olen = torch.zeros(nb, dtype=torch.int32, device=dev)
+    st = torch.zeros(nb, dtype=torch.int32, device=dev)
+    xx = torch.zeros(nb, dtype=torch.int32, device=dev)
+    comp_bytes = int(in_len.sum().item())
+    plain_bytes = nb * BLOCK2
+
+    def step_decompress():
+        ctx.decompress_blocks(comp, in_off, in_len, nb, plain, in_off, cap, cap, olen, st, xx, stream=stream)
+
+    for _ in range(Wm):
+        step_decompress()
+    torch.cuda.synchronize()
+    assert int(st.abs().sum().item()) == 0 and bool((olen == BLOCK2).all()), "decode failed"
+    launches0 = ctx.launch_count
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        step_decompress()
+    e1.record()
+    barrier()
+    dec_ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+    dec_launches = ctx.launch_count - launches0
+    total_plain = sum_over_ranks(plain_bytes)
+    dec_value = total_plain * K / GiB / (dec_ms / 1e3)
+    local_ms = e0.elapsed_time(e1) / K
+    dec_roof = {"bound": "hbm", "achieved": (comp_bytes + plain_bytes) / 1e9 / (local_ms / 1e3), "peak": peak_gbs,
+                "unit": "GB/s", "kernel": "decode_blocks_kernel", "peak_source": peak_src, "traffic": None,
+                "algorithmic_bytes_per_launch": comp_bytes + plain_bytes}
+    dec_roof["frac"] = dec_roof["achieved"] / peak_gbs
+
+    # ---- e2e: frames in pinned host memory through lzf_frames_decompress
+    dec_e2e = None
+    nframes = nb // BLOCKS_PER_FRAME2
+    frame_plain = BLOCKS_PER_FRAME2 * BLOCK2
+    if not args.no_e2e:
+        # content checksum of every frame's plaintext, computed on the device from the decoded blocks
+        f_off = torch.arange(nframes, device=dev, dtype=torch.int64) * frame_plain
+        f_len = torch.full((nframes,), frame_plain, dtype=torch.int64, device=dev)
+        f_hash = torch.zeros(nframes, dtype=torch.int32, device=dev)
+        ctx.xxh32_ranges(plain, f_off, f_len, nframes, f_hash, stream=stream)
+        torch.cuda.synchronize()
+        comp_h = comp.cpu().numpy()
+        len_h = in_len.cpu().numpy().astype(np.int64)
+        hash_h = f_hash.cpu().numpy().view(np.uint32)
+        hdr = np.frombuffer(bytes([0x04, 0x22, 0x4D, 0x18, 0x64, 0x40, 0xA7]), dtype=np.uint8)   # independent, content checksum, 64 KiB
+        fr_len = np.array([7 + int(len_h[f * BLOCKS_PER_FRAME2:(f + 1) * BLOCKS_PER_FRAME2].sum()) + 4 * BLOCKS_PER_FRAME2 + 8
+                           for f in range(nframes)], dtype=np.uint64)
+        fr_off = np.zeros(nframes, dtype=np.uint64)
+        fr_off[1:] = np.cumsum(fr_len)[:-1]
+        frames_t = torch.empty(int(fr_len.sum()), dtype=torch.uint8).pin_memory()
+        frames_h = frames_t.numpy()
+        for f in range(nframes):
+            p = int(fr_off[f])
+            frames_h[p:p + 7] = hdr
+            p += 7
+            for b in range(f * BLOCKS_PER_FRAME2, (f + 1) * BLOCKS_PER_FRAME2):
+                l = int(len_h[b])
+                frames_h[p:p + 4] = np.frombuffer(int(l).to_bytes(4, "little"), dtype=np.uint8)
+                frames_h[p + 4:p + 4 + l] = comp_h[b * BLOCK2:b * BLOCK2 + l]
+                p += 4 + l
+            frames_h[p:p + 4] = 0
+            frames_h[p + 4:p + 8] = np.frombuffer(int(hash_h[f]).to_bytes(4, "little"), dtype=np.uint8)
+        out_t = torch.empty(nb * BLOCK2, dtype=torch.uint8).pin_memory()
+        out_h = out_t.numpy()
+        o_off = np.arange(nframes, dtype=np.uint64) * frame_plain
+        o_cap = np.full(nframes, frame_plain, dtype=np.uint64)
+
+        def step_e2e():
+            return ctx.frames_decompress(frames_h, fr_off, fr_len, out_h, o_off, o_cap)
+
+        for _ in range(Wm):
+            ol, fs, det = step_e2e()
+        assert not fs.any() and (ol == frame_plain).all(), "frame decode failed: %s" % fs[fs != 0][:4]
+        check = plain[:frame_plain * 4].cpu().numpy()
+        assert np.array_equal(out_h[:frame_plain * 4], check)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            step_e2e()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        barrier()
+        dt = max_over_ranks(dt)
+        dec_e2e = {"value": total_plain * K / GiB / dt, "unit": "GiB/s", "h2d_bytes_per_step": int(fr_len.sum()),
+                   "d2h_bytes_per_step": int(nb * BLOCK2), "ms_per_step": dt / K * 1e3,
+                   "api": "lzf_frames_decompress (host buffers, %d frames of %d blocks, content checksum verified)"
+                          % (nframes, BLOCKS_PER_FRAME2)}
+        del frames_t, out_t
+
+    # ---- CPU baseline (rank 0, bounded sample)
+    cpu_dec = None
+    if rank == 0 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        ns = min(nb, 8192)
+        comp_s = comp[:ns * BLOCK2].cpu().numpy()
+        v, ref = cpu_decompress_sample(comp_s, np.arange(ns, dtype=np.uint64) * BLOCK2,
+                                       in_len[:ns].cpu().numpy().astype(np.uint32), ns, cores)
+        assert np.array_equal(ref, plain[:ns * BLOCK2].cpu().numpy()), "GPU decode differs from the oracle"
+        cpu_dec = {"value": v, "unit": "GiB/s", "cores": cores, "kind": "port",
+                   "sample": "first %d of the config-2 blocks (%d MiB plaintext), best of 3, C port of the lz-fear decode loop, "
+                             "one block per task over all host threads; GPU output verified equal on this sample" % (ns, ns * BLOCK2 >> 20)}
+    del comp, plain
+    torch.cuda.empty_cache()
+
+    # =========================================================================================
+    # config 3: compress
+    # =========================================================================================
+    comp_section = None
+    if not args.no_compress:
+        nb3 = max(BLOCKS_PER_FRAME3, int(args.comp_gib * GiB) // BLOCK3 // BLOCKS_PER_FRAME3 * BLOCKS_PER_FRAME3)
+        src = W.TextSource(seed=0x4C5A0003 + rank, device=dev)
+        data = torch.empty(nb3 * BLOCK3, dtype=torch.uint8, device=dev)
+        for b0 in range(0, nb3, 16):
+            n = min(16, nb3 - b0)
+            data[b0 * BLOCK3:(b0 + n) * BLOCK3] = src.make(n * BLOCK3)
+        off3 = torch.arange(nb3, device=dev, dtype=torch.int64) * BLOCK3
+        len3 = torch.full((nb3,), BLOCK3, dtype=torch.int32, device=dev)
+        cbuf = torch.empty(nb3 * BLOCK3, dtype=torch.uint8, device=dev)
+        clen = torch.zeros(nb3, dtype=torch.int32, device=dev)
+        cst = torch.zeros(nb3, dtype=torch.int32, device=dev)
+        cxx = torch.zeros(nb3, dtype=torch.int32, device=dev)
+
+        def step_compress():
+            ctx.compress_blocks(data, off3, len3, nb3, cbuf, off3, None, clen, cst, cxx, None, stream=stream)
+
+        for _ in range(Wm):
+            step_compress()
+        torch.cuda.synchronize()
+        assert int(cst.abs().sum().item()) == 0
+        c_bytes = int(clen.to(torch.int64).sum().item())
+        l0 = ctx.launch_count
+        barrier()
+        e0.record()
+        for _ in range(K):
+            step_compress()
+        e1.record()
+        barrier()
+        c_ms = max_over_ranks(e0.elapsed_time(e1))
+        c_launches = ctx.launch_count - l0
+        total3 = sum_over_ranks(nb3 * BLOCK3)
+        c_local_ms = e0.elapsed_time(e1) / K
+        c_roof = {"bound": "hbm", "achieved": (nb3 * BLOCK3 + c_bytes) / 1e9 / (c_local_ms / 1e3), "peak": peak_gbs,
+                  "unit": "GB/s", "kernel": "encode_blocks_kernel", "peak_source": peak_src, "traffic": None,
+                  "algorithmic_bytes_per_launch": nb3 * BLOCK3 + c_bytes}
+        c_roof["frac"] = c_roof["achieved"] / peak_gbs
+        comp_section = {"metric": "LZ4 block compress throughput (config 3: 4 MiB text-like blocks, default CompressionSettings)",
+                        "value": total3 * K / GiB / (c_ms / 1e3), "unit": "GiB/s", "ms_per_step": c_ms / K,
+                        "ratio": nb3 * BLOCK3 / max(c_bytes, 1), "plaintext_gib_per_gpu": nb3 * BLOCK3 / GiB,
+                        "roofline": c_roof, "gpu_launches": c_launches}
+        # round trip property at full size: decode what we just wrote and compare on the device
+        back = torch.empty_like(data)
+        cap3 = len3.clone()
+        ctx.decompress_blocks(cbuf, off3, clen, nb3, back, off3, cap3, cap3, torch.zeros_like(clen), cst, None, stream=stream)
+        torch.cuda.synchronize()
+        assert int(cst.abs().sum().item()) == 0 and torch.equal(back, data), "compress -> decompress round trip failed"
+        del back
+
+        if not args.no_e2e:
+            import psutil
+            avail = psutil.virtual_memory().available
+            e2e_blocks = nb3
+            while e2e_blocks > BLOCKS_PER_FRAME3 and e2e_blocks * BLOCK3 * 2.2 > avail * 0.5:
+                e2e_blocks //= 2
+            e2e_blocks = e2e_blocks // BLOCKS_PER_FRAME3 * BLOCKS_PER_FRAME3
+            nf3 = e2e_blocks // BLOCKS_PER_FRAME3
+            fp = BLOCKS_PER_FRAME3 * BLOCK3
+            s, _keep = N.make_settings()          # CompressionSettings::default()
+            bound = ctx.frame_bound(s, fp)
+            in_t = torch.empty(e2e_blocks * BLOCK3, dtype=torch.uint8).pin_memory()
+            in_t.copy_(data[:e2e_blocks * BLOCK3])
+            out_t = torch.empty(nf3 * bound, dtype=torch.uint8).pin_memory()
+            i_off = np.arange(nf3, dtype=np.uint64) * fp
+            i_len = np.full(nf3, fp, dtype=np.uint64)
+            o_off = np.arange(nf3, dtype=np.uint64) * bound
+            o_cap = np.full(nf3, bound, dtype=np.uint64)
+            in_h, out_h = in_t.numpy(), out_t.numpy()
+
+            def step_e2e3():
+                return ctx.frames_compress(in_h, i_off, i_len, out_h, o_off, o_cap, s)
+
+            for _ in range(Wm):
+                fl, fs = step_e2e3()
+            assert not fs.any()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(K):
+                fl, fs = step_e2e3()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            barrier()
+            dt = max_over_ranks(dt)
+            tot = sum_over_ranks(e2e_blocks * BLOCK3)
+            comp_section["e2e"] = {"value": tot * K / GiB / dt, "unit": "GiB/s", "h2d_bytes_per_step": int(e2e_blocks * BLOCK3),
+                                   "d2h_bytes_per_step": int(fl.sum()), "ms_per_step": dt / K * 1e3,
+                                   "api": "lzf_frames_compress (host buffers, %d frames of %d x 4 MiB blocks, default settings)"
+                                          % (nf3, BLOCKS_PER_FRAME3)}
+            # the frames must decode back to the input (checked through the host frame API on 2 frames)
+            st_, det_, pl_, _c = ctx.frame_decompress(out_h[: int(fl[0])], cap=fp + 16)
+            assert st_ == 0 and np.array_equal(np.frombuffer(pl_, dtype=np.uint8), in_h[:fp])
+            del in_t, out_t
+        if rank == 0 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            ns = min(nb3, max(cores, 32))
+            h = data[:ns * BLOCK3].cpu().numpy()
+            v, rl, rout = cpu_compress_sample(h, ns, cores)
+            g = cbuf[:ns * BLOCK3].cpu().numpy()
+            gl = clen[:ns].cpu().numpy().view(np.uint32)
+            assert np.array_equal(gl, rl), "compressed sizes differ from the oracle"
+            for b in range(ns):
+                assert np.array_equal(g[b * BLOCK3:b * BLOCK3 + rl[b]], rout[b * BLOCK3:b * BLOCK3 + rl[b]])
+            comp_section["cpu_baseline"] = {"value": v, "unit": "GiB/s", "cores": cores, "kind": "port",
+                                            "sample": "first %d config-3 blocks (%d MiB), best of 2, C port of lz-fear compress2, one block "
+                                                      "per task; GPU output byte-identical on this sample" % (ns, ns * BLOCK3 >> 20)}
+
+    if rank == 0:
+        line = {
+            "metric": "LZ4 block decompress throughput (config 2: 64 KiB independent blocks, seq50)",
+            "value": dec_value, "unit": "GiB/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": dec_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "config2: decompress %d independent 64 KiB seq50 blocks per GPU (%.2f GiB plaintext, %.2f GiB compressed)"
+                                   % (nb, plain_bytes / GiB, comp_bytes / GiB),
+                       "l2": "inputs (%.1f GiB read + %.1f GiB written per step) exceed the 126 MB L2; no flush needed"
+                             % (comp_bytes / GiB, plain_bytes / GiB),
+                       "sharding": "independent blocks split evenly over ranks, no data-path collective"},
+            "roofline": dec_roof, "cpu_baseline": cpu_dec, "e2e": dec_e2e, "gpu_launches": dec_launches,
+            "clocks": clocks, "compress": comp_section,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

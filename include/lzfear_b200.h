@@ -158,6 +158,21 @@ int lzf_decompress_blocks(lzf_ctx* ctx,
 int lzf_xxh32_ranges(lzf_ctx* ctx, const uint8_t* d_data, const uint64_t* d_off, const uint64_t* d_len,
                      uint32_t nranges, uint32_t* d_hash, void* stream);
 
+/* Streaming XXH32 (seed 0) over HOST buffers, for Read/Write-style callers that see the plaintext one
+ * block at a time (twox-hash `XxHash32::with_seed(0)` / `Hasher::write` / `finish`,
+ * src/framed/compress.rs:172,233-235,279-281; src/framed/decompress.rs:138-139,276-278,207-211).
+ * The 16-byte stripes are hashed on the GPU; only the < 16-byte carry and the final avalanche
+ * (a dozen integer ops) are host glue. */
+typedef struct {
+    uint32_t acc[4];
+    uint8_t buf[16];
+    uint32_t buflen;
+    uint64_t total;
+} lzf_xxh32_state;
+void lzf_xxh32_init(lzf_xxh32_state* st);
+int lzf_xxh32_update(lzf_ctx* ctx, lzf_xxh32_state* st, const uint8_t* data, size_t n);
+uint32_t lzf_xxh32_finish(const lzf_xxh32_state* st);
+
 /* ------------------------------------------------------------------------------------------
  * Single-block host-pointer conveniences mirroring the Rust raw API.
  *   lzf_raw_compress_into  = compress2(input, 0, &mut fresh table, NoPartialWrites(out[..cap]))

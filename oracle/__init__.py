@@ -167,6 +167,15 @@ def frame_decompress(data, dictionary=b"", cap=None):
     return rc, d.value, out[: w.value].tobytes(), c.value
 
 
+def parse_header(data):
+    """LZ4FrameReader::new -> (rc, detail, FrameInfo)"""
+    p, n, _k = _buf(data)
+    info = FrameInfo()
+    d = C.c_int(0)
+    rc = lib().lzfo_frame_parse_header(p, n, C.byref(info), C.byref(d))
+    return rc, d.value, info
+
+
 def compress_blocks_mt(inp, in_off, in_len, out, out_off, hashlog=12, nthreads=1):
     nb = len(in_len)
     out_len = np.zeros(nb, dtype=np.uint32)

@@ -663,6 +663,10 @@ int lzfo_frame_decompress(const uint8_t* in, size_t n, const uint8_t* dict, size
         if (info.flags & FLAG_CONTENT_CHECKSUM) lzfo_xxh32_update(&ch, blk, outlen);   /* :276-278 */
         if (cap - o < outlen) { rc = LZFO_F_WRITE_ERROR; break; }
         memcpy(out + o, blk, outlen); o += outlen;
+        /* LZ4FrameIoReader::read (:54-61) hands an empty fill_buf() straight to the caller as
+         * Ok(0), which read_to_end (:286) takes for end-of-stream: a block that decodes to zero
+         * bytes ends decompress_frame early and successfully, with the rest of the frame unread. */
+        if (outlen == 0) break;
     }
     free(window);
     free(blk);

@@ -1,0 +1,980 @@
+// lzf_api.cu — the C ABI of include/lzfear_b200.h: context, batched block calls, single-block
+// host conveniences and the frame layer (a restatement of the glue in
+// src/framed/compress.rs:159-282 and src/framed/decompress.rs:101-161,197-288 around the
+// sm_100a block kernels).  There is no CPU code path in here: every entry point needs a CUDA
+// device and fails with LZF_ERR_NO_DEVICE / LZF_ERR_CUDA otherwise.
+#include "lzf_common.cuh"
+#include "lzf_frame.cuh"
+#include "lzf_kernels.cuh"
+
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+namespace lzf {
+
+struct Buf {            // grow-only allocation
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+// A bump arena carved out of one Buf (device) mirrored by one pinned host Buf: descriptors are
+// written on the host side and shipped with a single H2D copy.
+struct Arena {
+    size_t used = 0;
+    size_t take(size_t bytes, size_t align = 256) {
+        used = (used + align - 1) / align * align;
+        const size_t o = used;
+        used += bytes;
+        return o;
+    }
+};
+
+}  // namespace lzf
+using lzf::Arena;
+using lzf::Buf;
+
+struct lzf_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;      // used by the host-buffer entry points
+    cudaStream_t side = nullptr;        // content-checksum chain, overlapped with the block kernels
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    uint64_t launches = 0;
+    std::string err;
+    uint32_t* d_counter = nullptr;      // dynamic work counters (encode, decode)
+    Buf d_tables;                       // per-warp global hash tables (hashlog >= 14)
+    Buf d_desc, h_desc;                 // descriptor arenas (device / pinned host)
+    Buf d_res, h_res;                   // result arenas (device / pinned host)
+    Buf d_comp;                         // compressed-block scratch (frame compress)
+    Buf d_io_in, d_io_out;              // staging of host-buffer calls
+};
+
+namespace {
+
+int fail(lzf_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
+    if (c) {
+        c->err = what;
+        if (e != cudaSuccess) { c->err += ": "; c->err += cudaGetErrorString(e); }
+    }
+    return code;
+}
+#define LZF_CU(c, call)                                                         \
+    do {                                                                        \
+        cudaError_t e__ = (call);                                               \
+        if (e__ != cudaSuccess) return fail((c), LZF_ERR_CUDA, #call, e__);     \
+    } while (0)
+#define LZF_LAUNCHED(c, rc, n)                                                  \
+    do {                                                                        \
+        const int rc__ = (rc);                                                  \
+        if (rc__ != 0) return fail((c), LZF_ERR_CUDA, "kernel launch", (cudaError_t)rc__); \
+        (c)->launches += (n);                                                   \
+    } while (0)
+
+int ensure_dev(lzf_ctx* c, Buf& b, size_t bytes) {
+    if (bytes <= b.cap) return LZF_SUCCESS;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 8 + 4096;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&b.p, want); }
+    if (e != cudaSuccess) { b.p = nullptr; return fail(c, LZF_ERR_OOM, "cudaMalloc", e); }
+    b.cap = want;
+    return LZF_SUCCESS;
+}
+int ensure_host(lzf_ctx* c, Buf& b, size_t bytes) {
+    if (bytes <= b.cap) return LZF_SUCCESS;
+    if (b.p) { cudaFreeHost(b.p); b.p = nullptr; b.cap = 0; }
+    const size_t want = bytes + bytes / 8 + 4096;
+    cudaError_t e = cudaMallocHost(&b.p, want);
+    if (e != cudaSuccess) { b.p = nullptr; return fail(c, LZF_ERR_OOM, "cudaMallocHost", e); }
+    b.cap = want;
+    return LZF_SUCCESS;
+}
+
+inline void wr32(uint8_t* p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); }
+inline void wr64(uint8_t* p, uint64_t v) { wr32(p, (uint32_t)v); wr32(p + 4, (uint32_t)(v >> 32)); }
+
+}  // namespace
+
+extern "C" int lzf_abi_version(void) { return LZF_ABI_VERSION; }
+
+extern "C" int lzf_create(int device, lzf_ctx** out) {
+    if (!out) return LZF_ERR_INVALID_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return LZF_ERR_NO_DEVICE;
+    if (device < 0 || device >= ndev) return LZF_ERR_INVALID_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return LZF_ERR_CUDA;
+    lzf_ctx* c = new (std::nothrow) lzf_ctx();
+    if (!c) return LZF_ERR_OOM;
+    c->device = device;
+    if (cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || c->num_sms <= 0) {
+        delete c;
+        return LZF_ERR_CUDA;
+    }
+    bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) == cudaSuccess &&
+              cudaMalloc((void**)&c->d_counter, 256) == cudaSuccess;
+    if (!ok) { lzf_destroy(c); return LZF_ERR_CUDA; }
+    *out = c;
+    return LZF_SUCCESS;
+}
+
+extern "C" void lzf_destroy(lzf_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->side) cudaStreamSynchronize(c->side);
+    Buf* dev[] = {&c->d_tables, &c->d_desc, &c->d_res, &c->d_comp, &c->d_io_in, &c->d_io_out};
+    for (Buf* b : dev) if (b->p) cudaFree(b->p);
+    Buf* host[] = {&c->h_desc, &c->h_res};
+    for (Buf* b : host) if (b->p) cudaFreeHost(b->p);
+    if (c->d_counter) cudaFree(c->d_counter);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->side) cudaStreamDestroy(c->side);
+    delete c;
+}
+
+extern "C" const char* lzf_last_error(const lzf_ctx* c) { return c ? c->err.c_str() : "null ctx"; }
+extern "C" uint64_t lzf_launch_count(const lzf_ctx* c) { return c ? c->launches : 0; }
+extern "C" size_t lzf_compress_bound(size_t n) { return n + n / 255 + 16; }
+
+// ------------------------------------------------------------------------------------------------
+// batched block calls (device pointers, asynchronous on `stream`)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+int compress_blocks_impl(lzf_ctx* c, const uint8_t* d_in, const uint64_t* d_in_off, const uint32_t* d_in_len,
+                         uint32_t nblocks, uint32_t hashlog, uint32_t table_kind, uint32_t max_block_len,
+                         uint8_t* d_out, const uint64_t* d_out_off, const uint32_t* d_out_cap,
+                         uint32_t* d_out_len, int32_t* d_status, uint32_t* d_xxh_plain, uint32_t* d_xxh_stored,
+                         cudaStream_t s) {
+    if (hashlog == 0) hashlog = 12;
+    if (hashlog < 8 || hashlog > 16) return fail(c, LZF_ERR_INVALID_ARG, "hashlog must be 0 or 8..16");
+    if (table_kind != LZF_TABLE_U32 && table_kind != LZF_TABLE_U16) return fail(c, LZF_ERR_INVALID_ARG, "table_kind");
+    if (nblocks == 0) return LZF_SUCCESS;
+    if (!d_in || !d_in_off || !d_in_len || !d_out || !d_out_off || !d_out_len || !d_status)
+        return fail(c, LZF_ERR_INVALID_ARG, "null pointer");
+    lzf::EncodeArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = d_in; a.in_off = d_in_off; a.in_len = d_in_len; a.nblocks = nblocks;
+    a.hashlog = hashlog; a.table_kind = table_kind;
+    a.out = d_out; a.out_off = d_out_off; a.out_cap = d_out_cap; a.out_len = d_out_len; a.status = d_status;
+    a.xxh_plain = d_xxh_plain; a.xxh_stored = d_xxh_stored;
+    a.work_counter = c->d_counter;
+    a.max_block_len = max_block_len;
+    const size_t nslots = table_kind == LZF_TABLE_U16 ? ((size_t)2 << hashlog) : ((size_t)1 << hashlog);
+    if (nslots * 4 > 32 * 1024) {
+        const int rc = ensure_dev(c, c->d_tables, lzf_encode_global_table_warps(c->num_sms) * nslots * 4);
+        if (rc) return rc;
+        a.global_tables = (uint8_t*)c->d_tables.p;
+    }
+    LZF_CU(c, cudaMemsetAsync(c->d_counter, 0, 4, s));
+    LZF_LAUNCHED(c, lzf_launch_encode(&a, c->num_sms, s), 1);
+    return LZF_SUCCESS;
+}
+
+int decompress_blocks_impl(lzf_ctx* c, const uint8_t* d_in, const uint64_t* d_in_off, const uint32_t* d_in_len,
+                           uint32_t nblocks, const uint8_t* d_prefix, const uint64_t* d_prefix_off,
+                           const uint32_t* d_prefix_len, uint8_t* d_out, const uint64_t* d_out_off,
+                           const uint32_t* d_out_cap, const uint32_t* d_out_limit, uint32_t* d_out_len,
+                           int32_t* d_status, uint32_t* d_xxh_plain, cudaStream_t s) {
+    if (nblocks == 0) return LZF_SUCCESS;
+    if (!d_in || !d_in_off || !d_in_len || !d_out || !d_out_off || !d_out_cap || !d_out_limit || !d_out_len || !d_status)
+        return fail(c, LZF_ERR_INVALID_ARG, "null pointer");
+    if (d_prefix && (!d_prefix_off || !d_prefix_len)) return fail(c, LZF_ERR_INVALID_ARG, "prefix triple incomplete");
+    lzf::DecodeArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = d_in; a.in_off = d_in_off; a.in_len = d_in_len; a.nblocks = nblocks;
+    a.prefix = d_prefix; a.prefix_off = d_prefix_off; a.prefix_len = d_prefix_len;
+    a.out = d_out; a.out_off = d_out_off; a.out_cap = d_out_cap; a.out_limit = d_out_limit;
+    a.out_len = d_out_len; a.status = d_status; a.xxh_plain = d_xxh_plain;
+    a.work_counter = c->d_counter + 16;
+    LZF_CU(c, cudaMemsetAsync(c->d_counter + 16, 0, 4, s));
+    LZF_LAUNCHED(c, lzf_launch_decode(&a, c->num_sms, s), 1);
+    return LZF_SUCCESS;
+}
+
+}  // namespace
+
+extern "C" int lzf_compress_blocks(lzf_ctx* c, const uint8_t* d_in, const uint64_t* d_in_off, const uint32_t* d_in_len,
+                                   uint32_t nblocks, uint32_t hashlog, uint32_t table_kind,
+                                   uint8_t* d_out, const uint64_t* d_out_off, const uint32_t* d_out_cap,
+                                   uint32_t* d_out_len, int32_t* d_status,
+                                   uint32_t* d_xxh_plain, uint32_t* d_xxh_stored, void* stream) {
+    if (!c) return LZF_ERR_INVALID_ARG;
+    LZF_CU(c, cudaSetDevice(c->device));
+    return compress_blocks_impl(c, d_in, d_in_off, d_in_len, nblocks, hashlog, table_kind, 0, d_out, d_out_off,
+                                d_out_cap, d_out_len, d_status, d_xxh_plain, d_xxh_stored, (cudaStream_t)stream);
+}
+
+extern "C" int lzf_decompress_blocks(lzf_ctx* c, const uint8_t* d_in, const uint64_t* d_in_off, const uint32_t* d_in_len,
+                                     uint32_t nblocks, const uint8_t* d_prefix, const uint64_t* d_prefix_off,
+                                     const uint32_t* d_prefix_len, uint8_t* d_out, const uint64_t* d_out_off,
+                                     const uint32_t* d_out_cap, const uint32_t* d_out_limit, uint32_t* d_out_len,
+                                     int32_t* d_status, uint32_t* d_xxh_plain, void* stream) {
+    if (!c) return LZF_ERR_INVALID_ARG;
+    LZF_CU(c, cudaSetDevice(c->device));
+    return decompress_blocks_impl(c, d_in, d_in_off, d_in_len, nblocks, d_prefix, d_prefix_off, d_prefix_len, d_out,
+                                  d_out_off, d_out_cap, d_out_limit, d_out_len, d_status, d_xxh_plain,
+                                  (cudaStream_t)stream);
+}
+
+extern "C" int lzf_xxh32_ranges(lzf_ctx* c, const uint8_t* d_data, const uint64_t* d_off, const uint64_t* d_len,
+                                uint32_t nranges, uint32_t* d_hash, void* stream) {
+    if (!c) return LZF_ERR_INVALID_ARG;
+    if (nranges == 0) return LZF_SUCCESS;
+    if (!d_off || !d_len || !d_hash) return fail(c, LZF_ERR_INVALID_ARG, "null pointer");
+    LZF_CU(c, cudaSetDevice(c->device));
+    LZF_LAUNCHED(c, lzf_launch_xxh32_ranges(d_data, d_off, d_len, nranges, d_hash, (cudaStream_t)stream), 1);
+    return LZF_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------------------------
+// streaming XXH32 over host buffers (stripes on the GPU)
+// ------------------------------------------------------------------------------------------------
+extern "C" void lzf_xxh32_init(lzf_xxh32_state* st) {
+    if (!st) return;
+    memset(st, 0, sizeof(*st));
+    st->acc[0] = lzf::XP1 + lzf::XP2; st->acc[1] = lzf::XP2; st->acc[2] = 0; st->acc[3] = 0u - lzf::XP1;
+}
+
+extern "C" int lzf_xxh32_update(lzf_ctx* c, lzf_xxh32_state* st, const uint8_t* data, size_t n) {
+    if (!c || !st || (n && !data)) return LZF_ERR_INVALID_ARG;
+    if (n == 0) return LZF_SUCCESS;
+    LZF_CU(c, cudaSetDevice(c->device));
+    st->total += n;
+    // bytes that complete the carried partial stripe, then whole stripes, then the new carry
+    const size_t head = st->buflen ? ((16 - st->buflen) < n ? (16 - st->buflen) : n) : 0;
+    memcpy(st->buf + st->buflen, data, head);
+    const bool head_full = st->buflen + head == 16;
+    if (st->buflen && !head_full) { st->buflen += (uint32_t)head; return LZF_SUCCESS; }
+    const size_t body = (n - head) & ~(size_t)15;
+    const size_t tail = n - head - body;
+    const size_t dev_bytes = (head_full ? 16 : 0) + body;
+    if (dev_bytes) {
+        int rc;
+        if ((rc = ensure_dev(c, c->d_io_in, dev_bytes + 64))) return rc;
+        if ((rc = ensure_dev(c, c->d_desc, 4096))) return rc;
+        if ((rc = ensure_host(c, c->h_desc, 4096))) return rc;
+        uint8_t* din = (uint8_t*)c->d_io_in.p;
+        cudaStream_t s = c->stream;
+        memcpy(c->h_desc.p, st->acc, 16);
+        if (head_full) memcpy((uint8_t*)c->h_desc.p + 16, st->buf, 16);
+        LZF_CU(c, cudaMemcpyAsync(c->d_desc.p, c->h_desc.p, 32, cudaMemcpyHostToDevice, s));
+        if (head_full) LZF_CU(c, cudaMemcpyAsync(din, (uint8_t*)c->d_desc.p + 16, 16, cudaMemcpyDeviceToDevice, s));
+        if (body) LZF_CU(c, cudaMemcpyAsync(din + (head_full ? 16 : 0), data + head, body, cudaMemcpyHostToDevice, s));
+        LZF_LAUNCHED(c, lzf_launch_xxh32_stripes(din, dev_bytes / 16, (uint32_t*)c->d_desc.p, s), 1);
+        LZF_CU(c, cudaMemcpyAsync(c->h_desc.p, c->d_desc.p, 16, cudaMemcpyDeviceToHost, s));
+        LZF_CU(c, cudaStreamSynchronize(s));
+        memcpy(st->acc, c->h_desc.p, 16);
+    }
+    if (head_full) st->buflen = 0;
+    memcpy(st->buf, data + head + body, tail);
+    st->buflen = (uint32_t)tail;
+    return LZF_SUCCESS;
+}
+
+extern "C" uint32_t lzf_xxh32_finish(const lzf_xxh32_state* st) {
+    if (!st) return 0;
+    auto rotl = [](uint32_t x, int r) { return (x << r) | (x >> (32 - r)); };
+    uint32_t h = st->total >= 16 ? rotl(st->acc[0], 1) + rotl(st->acc[1], 7) + rotl(st->acc[2], 12) + rotl(st->acc[3], 18)
+                                 : lzf::XP5;
+    h += (uint32_t)st->total;
+    const uint8_t* p = st->buf;
+    uint32_t n = st->buflen;
+    while (n >= 4) {
+        const uint32_t x = uint32_t(p[0]) | (uint32_t(p[1]) << 8) | (uint32_t(p[2]) << 16) | (uint32_t(p[3]) << 24);
+        h = rotl(h + x * lzf::XP3, 17) * lzf::XP4; p += 4; n -= 4;
+    }
+    while (n) { h = rotl(h + uint32_t(*p) * lzf::XP5, 11) * lzf::XP1; p++; n--; }
+    h ^= h >> 15; h *= lzf::XP2;
+    h ^= h >> 13; h *= lzf::XP3;
+    h ^= h >> 16;
+    return h;
+}
+
+// ------------------------------------------------------------------------------------------------
+// single-block host-pointer conveniences (raw::compress2 / raw::decompress_raw shape)
+// ------------------------------------------------------------------------------------------------
+extern "C" int lzf_raw_compress_into(lzf_ctx* c, const uint8_t* in, size_t n, uint32_t table_kind, uint32_t hashlog,
+                                     uint8_t* out, size_t cap, size_t* written, int32_t* status) {
+    if (!c || !written || !status || (n && !in) || (cap && !out)) return LZF_ERR_INVALID_ARG;
+    *written = 0;
+    *status = LZF_OK;
+    // assert!(input.len() <= T::payload_size_limit())   src/raw/compress/mod.rs:167
+    if (n > 0xffffffffull || (table_kind == LZF_TABLE_U16 && n > 0xffffull)) { *status = LZF_PANIC; return LZF_SUCCESS; }
+    LZF_CU(c, cudaSetDevice(c->device));
+    const size_t capc = cap > 0xffffffffull ? 0xffffffffull : cap;
+    int rc;
+    if ((rc = ensure_dev(c, c->d_io_in, n + 64))) return rc;
+    if ((rc = ensure_dev(c, c->d_io_out, capc + 64))) return rc;
+    if ((rc = ensure_dev(c, c->d_desc, 4096))) return rc;
+    if ((rc = ensure_host(c, c->h_desc, 4096))) return rc;
+    uint8_t* h = (uint8_t*)c->h_desc.p;
+    uint8_t* d = (uint8_t*)c->d_desc.p;
+    // layout: in_off u64 @0, out_off u64 @8, in_len u32 @16, out_cap u32 @20 | results: out_len u32 @64, status i32 @68
+    memset(h, 0, 128);
+    *(uint32_t*)(h + 16) = (uint32_t)n;
+    *(uint32_t*)(h + 20) = (uint32_t)capc;
+    cudaStream_t s = c->stream;
+    LZF_CU(c, cudaMemcpyAsync(d, h, 128, cudaMemcpyHostToDevice, s));
+    if (n) LZF_CU(c, cudaMemcpyAsync(c->d_io_in.p, in, n, cudaMemcpyHostToDevice, s));
+    rc = compress_blocks_impl(c, (const uint8_t*)c->d_io_in.p, (const uint64_t*)d, (const uint32_t*)(d + 16), 1, hashlog,
+                              table_kind, (uint32_t)n, (uint8_t*)c->d_io_out.p, (const uint64_t*)(d + 8),
+                              (const uint32_t*)(d + 20), (uint32_t*)(d + 64), (int32_t*)(d + 68), nullptr, nullptr, s);
+    if (rc) return rc;
+    LZF_CU(c, cudaMemcpyAsync(h + 64, d + 64, 8, cudaMemcpyDeviceToHost, s));
+    LZF_CU(c, cudaStreamSynchronize(s));
+    const uint32_t olen = *(uint32_t*)(h + 64);
+    *status = *(int32_t*)(h + 68);
+    if (*status == LZF_OK && olen) {
+        LZF_CU(c, cudaMemcpyAsync(out, c->d_io_out.p, olen, cudaMemcpyDeviceToHost, s));
+        LZF_CU(c, cudaStreamSynchronize(s));
+    }
+    *written = *status == LZF_OK ? olen : 0;
+    return LZF_SUCCESS;
+}
+
+extern "C" int lzf_raw_decompress(lzf_ctx* c, const uint8_t* in, size_t n, const uint8_t* prefix, size_t plen,
+                                  uint8_t* out, size_t out_cap, size_t out_limit, size_t* out_len, int32_t* status) {
+    if (!c || !out_len || !status || (n && !in) || (plen && !prefix) || (out_cap && !out)) return LZF_ERR_INVALID_ARG;
+    *out_len = 0;
+    *status = LZF_OK;
+    if (n > 0x7fffffffull || plen > 0xffffffffull) return fail(c, LZF_ERR_UNSUPPORTED, "block larger than 2 GiB");
+    LZF_CU(c, cudaSetDevice(c->device));
+    const size_t capc = out_cap > 0xffffffffull ? 0xffffffffull : out_cap;
+    const size_t limc = out_limit > 0xffffffffull ? 0xffffffffull : out_limit;
+    int rc;
+    if ((rc = ensure_dev(c, c->d_io_in, n + plen + 128))) return rc;
+    if ((rc = ensure_dev(c, c->d_io_out, capc + 64))) return rc;
+    if ((rc = ensure_dev(c, c->d_desc, 4096))) return rc;
+    if ((rc = ensure_host(c, c->h_desc, 4096))) return rc;
+    uint8_t* h = (uint8_t*)c->h_desc.p;
+    uint8_t* d = (uint8_t*)c->d_desc.p;
+    const size_t poff = (n + 63) / 64 * 64;
+    // in_off @0, out_off @8, prefix_off @16, in_len @24, out_cap @28, out_limit @32, prefix_len @36 | out_len @64, status @68
+    memset(h, 0, 128);
+    *(uint64_t*)(h + 16) = poff;
+    *(uint32_t*)(h + 24) = (uint32_t)n;
+    *(uint32_t*)(h + 28) = (uint32_t)capc;
+    *(uint32_t*)(h + 32) = (uint32_t)limc;
+    *(uint32_t*)(h + 36) = (uint32_t)plen;
+    cudaStream_t s = c->stream;
+    LZF_CU(c, cudaMemcpyAsync(d, h, 128, cudaMemcpyHostToDevice, s));
+    uint8_t* din = (uint8_t*)c->d_io_in.p;
+    if (n) LZF_CU(c, cudaMemcpyAsync(din, in, n, cudaMemcpyHostToDevice, s));
+    if (plen) LZF_CU(c, cudaMemcpyAsync(din + poff, prefix, plen, cudaMemcpyHostToDevice, s));
+    rc = decompress_blocks_impl(c, din, (const uint64_t*)d, (const uint32_t*)(d + 24), 1, plen ? din : nullptr,
+                                (const uint64_t*)(d + 16), (const uint32_t*)(d + 36), (uint8_t*)c->d_io_out.p,
+                                (const uint64_t*)(d + 8), (const uint32_t*)(d + 28), (const uint32_t*)(d + 32),
+                                (uint32_t*)(d + 64), (int32_t*)(d + 68), nullptr, s);
+    if (rc) return rc;
+    LZF_CU(c, cudaMemcpyAsync(h + 64, d + 64, 8, cudaMemcpyDeviceToHost, s));
+    LZF_CU(c, cudaStreamSynchronize(s));
+    const uint32_t olen = *(uint32_t*)(h + 64);
+    *status = *(int32_t*)(h + 68);
+    const size_t ncopy = olen < capc ? olen : capc;
+    if (ncopy) {
+        LZF_CU(c, cudaMemcpyAsync(out, c->d_io_out.p, ncopy, cudaMemcpyDeviceToHost, s));
+        LZF_CU(c, cudaStreamSynchronize(s));
+    }
+    *out_len = olen;
+    return LZF_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------------------------
+// frame layer: settings / header
+// ------------------------------------------------------------------------------------------------
+extern "C" void lzf_settings_default(lzf_settings* s) {     // src/framed/compress.rs:44-55
+    if (!s) return;
+    memset(s, 0, sizeof(*s));
+    s->independent_blocks = 1;
+    s->block_checksums = 0;
+    s->content_checksum = 1;
+    s->block_size = 4u * 1024 * 1024;
+    s->hashlog = 12;
+}
+
+extern "C" size_t lzf_frame_bound(const lzf_settings* s, size_t n) {
+    const size_t bs = (s && s->block_size) ? (size_t)s->block_size : 1;
+    const size_t nblocks = (n + bs - 1) / bs;
+    return 19 + n + nblocks * 8 + 8;
+}
+
+extern "C" int lzf_frame_parse_header(const uint8_t* in, size_t n, lzf_frame_info* info, int32_t* detail) {
+    int32_t d = 0;
+    lzf_frame_info tmp;
+    if (!in && n) return LZF_F_INPUT_ERROR;
+    const int rc = lzf::parse_frame_header(in, n, info ? info : &tmp, &d);
+    if (detail) *detail = d;
+    return rc;
+}
+
+namespace {
+
+// header bytes of compress_internal (src/framed/compress.rs:163-200).  Returns LZF_F_*.
+int build_header(const lzf_settings* s, uint64_t content_size, uint8_t* hdr, uint32_t* hlen) {
+    uint8_t flags = 0;
+    if (s->independent_blocks) flags |= lzf::kFlagIndependent;
+    if (s->block_checksums) flags |= lzf::kFlagBlockChecksums;
+    if (s->content_checksum) flags |= lzf::kFlagContentChecksum;
+    if (s->has_dictionary_id) flags |= lzf::kFlagDictionaryId;
+    if (s->has_content_size) flags |= lzf::kFlagContentSize;
+    uint8_t bd = 0;
+    const int b = lzf::bd_new(s->block_size, &bd);            // compress.rs:183
+    if (b == 2) return LZF_F_PANIC;
+    if (b == 1) return LZF_F_INVALID_BLOCK_SIZE;
+    uint32_t h = 0;
+    wr32(hdr, LZF_MAGIC); h = 4;
+    hdr[h++] = (uint8_t)((1u << 6) | flags);
+    hdr[h++] = bd;
+    if (s->has_content_size) { wr64(hdr + h, content_size); h += 8; }
+    if (s->has_dictionary_id) { wr32(hdr + h, s->dictionary_id); h += 4; }
+    hdr[h] = (uint8_t)(lzf::xxh32_scalar(hdr + 4, h - 4) >> 8);   // compress.rs:197-199
+    h++;
+    *hlen = h;
+    return LZF_F_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// frame compress over device-resident plaintext.  All blocks of all frames: ONE encode launch,
+// content checksums on a side stream, then layout + assembly.
+// ------------------------------------------------------------------------------------------------
+int frames_compress_core(lzf_ctx* c, const lzf_settings* s, const uint8_t* d_in, const uint64_t* in_off,
+                         const uint64_t* in_len, uint32_t nframes, uint8_t* d_out, const uint64_t* out_off,
+                         const uint64_t* out_cap, uint64_t* out_len, int32_t* status, cudaStream_t st) {
+    if (!s || (nframes && (!in_off || !in_len || !out_off || !out_cap || !out_len || !status)))
+        return fail(c, LZF_ERR_INVALID_ARG, "null pointer");
+    for (uint32_t f = 0; f < nframes; f++) { out_len[f] = 0; status[f] = LZF_F_OK; }
+    if (nframes == 0) return LZF_SUCCESS;
+    if (!s->independent_blocks || (s->dictionary && s->dictionary_len))
+        return fail(c, LZF_ERR_UNSUPPORTED, "dependent blocks / dictionaries are not on the GPU path yet");
+    uint32_t hashlog = s->hashlog ? s->hashlog : 12;
+
+    // settings-level failures are identical for every frame
+    {
+        uint8_t hdr[20]; uint32_t hl;
+        const int hs = build_header(s, 0, hdr, &hl);
+        if (hs != LZF_F_OK) { for (uint32_t f = 0; f < nframes; f++) status[f] = hs; return LZF_SUCCESS; }
+    }
+    const uint64_t bs = s->block_size;
+
+    // ---- plan
+    uint64_t nblocks64 = 0;
+    for (uint32_t f = 0; f < nframes; f++) nblocks64 += (in_len[f] + bs - 1) / bs;
+    if (nblocks64 > 0x7fffffffull) return fail(c, LZF_ERR_UNSUPPORTED, "too many blocks in one call");
+    const uint32_t nblocks = (uint32_t)nblocks64;
+
+    Arena da;   // descriptor arena (host-written)
+    const size_t o_first = da.take((size_t)nframes * 4), o_nblk = da.take((size_t)nframes * 4);
+    const size_t o_hdr = da.take((size_t)nframes * 20);
+    const size_t o_foff = da.take((size_t)nframes * 8), o_fcap = da.take((size_t)nframes * 8);
+    const size_t o_hoff = da.take((size_t)nframes * 8), o_hlen = da.take((size_t)nframes * 8);
+    const size_t o_bin_off = da.take((size_t)nblocks * 8), o_bin_len = da.take((size_t)nblocks * 4);
+    const size_t o_bc_off = da.take((size_t)nblocks * 8);
+    Arena ra;   // result arena (device-written)
+    const size_t r_clen = ra.take((size_t)nblocks * 4), r_bst = ra.take((size_t)nblocks * 4);
+    const size_t r_xs = ra.take((size_t)nblocks * 4), r_dst = ra.take((size_t)nblocks * 8);
+    const size_t r_chash = ra.take((size_t)nframes * 4);
+    const size_t r_flen = ra.take((size_t)nframes * 8), r_fst = ra.take((size_t)nframes * 4);
+    const size_t r_host_lo = r_flen, r_host_hi = ra.used;   // only frame_len + frame_status travel back
+
+    int rc;
+    if ((rc = ensure_host(c, c->h_desc, da.used))) return rc;
+    if ((rc = ensure_dev(c, c->d_desc, da.used))) return rc;
+    if ((rc = ensure_dev(c, c->d_res, ra.used))) return rc;
+    if ((rc = ensure_host(c, c->h_res, ra.used))) return rc;
+    uint8_t* h = (uint8_t*)c->h_desc.p;
+    uint8_t* d = (uint8_t*)c->d_desc.p;
+    uint8_t* r = (uint8_t*)c->d_res.p;
+
+    uint32_t* first = (uint32_t*)(h + o_first); uint32_t* nblk = (uint32_t*)(h + o_nblk);
+    uint8_t* hdrs = h + o_hdr;
+    uint64_t* foff = (uint64_t*)(h + o_foff); uint64_t* fcap = (uint64_t*)(h + o_fcap);
+    uint64_t* hoff = (uint64_t*)(h + o_hoff); uint64_t* hlen = (uint64_t*)(h + o_hlen);
+    uint64_t* bin_off = (uint64_t*)(h + o_bin_off); uint32_t* bin_len = (uint32_t*)(h + o_bin_len);
+    uint64_t* bc_off = (uint64_t*)(h + o_bc_off);
+    uint32_t b = 0;
+    uint64_t comp_total = 0;
+    uint32_t max_block_len = 0;
+    for (uint32_t f = 0; f < nframes; f++) {
+        first[f] = b;
+        const uint64_t n = in_len[f];
+        const uint32_t nb = (uint32_t)((n + bs - 1) / bs);
+        nblk[f] = nb;
+        uint32_t hl = 0;
+        const uint64_t csize = s->has_content_size == 2 ? n : s->content_size;   // compress_with_size vs _unchecked
+        build_header(s, csize, hdrs + (size_t)f * 20 + 1, &hl);
+        hdrs[(size_t)f * 20] = (uint8_t)hl;
+        foff[f] = out_off[f]; fcap[f] = out_cap[f];
+        hoff[f] = in_off[f]; hlen[f] = n;
+        for (uint32_t i = 0; i < nb; i++, b++) {
+            const uint64_t o = (uint64_t)i * bs;
+            const uint32_t l = (uint32_t)((n - o) < bs ? (n - o) : bs);           // compress.rs:227 take(block_size)
+            bin_off[b] = in_off[f] + o;
+            bin_len[b] = l;
+            bc_off[b] = comp_total;
+            comp_total += ((uint64_t)l + 15) / 16 * 16;
+            if (l > max_block_len) max_block_len = l;
+        }
+    }
+    if ((rc = ensure_dev(c, c->d_comp, comp_total + 64))) return rc;
+
+    LZF_CU(c, cudaMemcpyAsync(d, h, da.used, cudaMemcpyHostToDevice, st));
+    // content checksum of each frame's plaintext (compress.rs:172,233-235,279-281) on the side stream
+    if (s->content_checksum) {
+        LZF_CU(c, cudaEventRecord(c->ev_fork, st));
+        LZF_CU(c, cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+        LZF_LAUNCHED(c, lzf_launch_xxh32_ranges(d_in, (const uint64_t*)(d + o_hoff), (const uint64_t*)(d + o_hlen), nframes,
+                                               (uint32_t*)(r + r_chash), c->side), 1);
+        LZF_CU(c, cudaEventRecord(c->ev_join, c->side));
+    }
+    if (nblocks) {
+        rc = compress_blocks_impl(c, d_in, (const uint64_t*)(d + o_bin_off), (const uint32_t*)(d + o_bin_len), nblocks,
+                                  hashlog, LZF_TABLE_U32, max_block_len, (uint8_t*)c->d_comp.p,
+                                  (const uint64_t*)(d + o_bc_off), nullptr, (uint32_t*)(r + r_clen), (int32_t*)(r + r_bst),
+                                  nullptr, s->block_checksums ? (uint32_t*)(r + r_xs) : nullptr, st);
+        if (rc) return rc;
+    }
+    if (s->content_checksum) LZF_CU(c, cudaStreamWaitEvent(st, c->ev_join, 0));
+    lzf::LayoutArgs la;
+    memset(&la, 0, sizeof(la));
+    la.nframes = nframes;
+    la.first_block = (const uint32_t*)(d + o_first); la.nblocks = (const uint32_t*)(d + o_nblk);
+    la.blk_in_len = (const uint32_t*)(d + o_bin_len); la.blk_comp_len = (const uint32_t*)(r + r_clen);
+    la.blk_status = (const int32_t*)(r + r_bst);
+    la.block_checksums = s->block_checksums ? 1 : 0; la.content_checksum = s->content_checksum ? 1 : 0;
+    la.headers = d + o_hdr;
+    la.out = d_out; la.out_off = (const uint64_t*)(d + o_foff); la.out_cap = (const uint64_t*)(d + o_fcap);
+    la.content_hash = (const uint32_t*)(r + r_chash);
+    la.blk_dst = (uint64_t*)(r + r_dst);
+    la.frame_len = (uint64_t*)(r + r_flen); la.frame_status = (int32_t*)(r + r_fst);
+    LZF_LAUNCHED(c, lzf_launch_layout(&la, st), 1);
+    if (nblocks) {
+        lzf::AssembleArgs aa;
+        memset(&aa, 0, sizeof(aa));
+        aa.nblocks = nblocks;
+        aa.in = d_in; aa.blk_in_off = (const uint64_t*)(d + o_bin_off); aa.blk_in_len = (const uint32_t*)(d + o_bin_len);
+        aa.comp = (const uint8_t*)c->d_comp.p; aa.blk_comp_off = (const uint64_t*)(d + o_bc_off);
+        aa.blk_comp_len = (const uint32_t*)(r + r_clen); aa.blk_status = (const int32_t*)(r + r_bst);
+        aa.blk_xxh_stored = s->block_checksums ? (const uint32_t*)(r + r_xs) : nullptr;
+        aa.blk_dst = (const uint64_t*)(r + r_dst); aa.out = d_out;
+        LZF_LAUNCHED(c, lzf_launch_assemble(&aa, max_block_len, st), 1);
+    }
+    uint8_t* hr = (uint8_t*)c->h_res.p;
+    LZF_CU(c, cudaMemcpyAsync(hr + r_host_lo, r + r_host_lo, r_host_hi - r_host_lo, cudaMemcpyDeviceToHost, st));
+    LZF_CU(c, cudaStreamSynchronize(st));
+    const uint64_t* flen = (const uint64_t*)(hr + r_flen);
+    const int32_t* fst = (const int32_t*)(hr + r_fst);
+    for (uint32_t f = 0; f < nframes; f++) { out_len[f] = flen[f]; status[f] = fst[f]; }
+    return LZF_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------------------------
+// frame decompress over device-resident frames (independent blocks)
+// ------------------------------------------------------------------------------------------------
+struct DecodeOut {          // optional extra per-frame results
+    uint64_t* consumed;     // nullable
+    int32_t* detail;        // nullable
+};
+
+int frames_decompress_core(lzf_ctx* c, const uint8_t* d_in, const uint64_t* in_off, const uint64_t* in_len,
+                           uint32_t nframes, uint8_t* d_out, const uint64_t* out_off, const uint64_t* out_cap,
+                           uint64_t* out_len, int32_t* status, DecodeOut extra, cudaStream_t st) {
+    if (nframes && (!in_off || !in_len || !out_off || !out_cap || !out_len || !status))
+        return fail(c, LZF_ERR_INVALID_ARG, "null pointer");
+    for (uint32_t f = 0; f < nframes; f++) {
+        out_len[f] = 0; status[f] = LZF_F_OK;
+        if (extra.consumed) extra.consumed[f] = 0;
+        if (extra.detail) extra.detail[f] = 0;
+    }
+    if (nframes == 0) return LZF_SUCCESS;
+    int rc;
+
+    // ---- pass 0: parse headers and count blocks (LZ4FrameReader::new + the length-word chase)
+    Arena da;
+    const size_t o_ioff = da.take((size_t)nframes * 8), o_ilen = da.take((size_t)nframes * 8);
+    const size_t o_ooff = da.take((size_t)nframes * 8), o_ocap = da.take((size_t)nframes * 8);
+    const size_t o_first = da.take((size_t)nframes * 4), o_nblk = da.take((size_t)nframes * 4);
+    const size_t o_hoff = da.take((size_t)nframes * 8), o_hlen = da.take((size_t)nframes * 8);
+    const size_t frame_desc_bytes = da.used;
+    if ((rc = ensure_host(c, c->h_desc, da.used))) return rc;
+    if ((rc = ensure_dev(c, c->d_desc, da.used))) return rc;
+    uint8_t* h = (uint8_t*)c->h_desc.p;
+    uint8_t* d = (uint8_t*)c->d_desc.p;
+    memcpy(h + o_ioff, in_off, (size_t)nframes * 8);
+    memcpy(h + o_ilen, in_len, (size_t)nframes * 8);
+    memcpy(h + o_ooff, out_off, (size_t)nframes * 8);
+    memcpy(h + o_ocap, out_cap, (size_t)nframes * 8);
+
+    Arena ra;
+    const size_t r_walk = ra.take((size_t)nframes * sizeof(lzf::WalkFrame));
+    if ((rc = ensure_dev(c, c->d_res, ra.used))) return rc;
+    if ((rc = ensure_host(c, c->h_res, ra.used))) return rc;
+    LZF_CU(c, cudaMemcpyAsync(d, h, o_first, cudaMemcpyHostToDevice, st));
+    lzf::WalkArgs wa;
+    memset(&wa, 0, sizeof(wa));
+    wa.nframes = nframes; wa.mode = 0;
+    wa.in = d_in; wa.in_off = (const uint64_t*)(d + o_ioff); wa.in_len = (const uint64_t*)(d + o_ilen);
+    wa.frames = (lzf::WalkFrame*)((uint8_t*)c->d_res.p + r_walk);
+    LZF_LAUNCHED(c, lzf_launch_walk(&wa, st), 1);
+    std::vector<lzf::WalkFrame> wf(nframes);
+    LZF_CU(c, cudaMemcpyAsync(c->h_res.p, (uint8_t*)c->d_res.p + r_walk, (size_t)nframes * sizeof(lzf::WalkFrame),
+                              cudaMemcpyDeviceToHost, st));
+    LZF_CU(c, cudaStreamSynchronize(st));
+    memcpy(wf.data(), c->h_res.p, (size_t)nframes * sizeof(lzf::WalkFrame));
+
+    uint64_t nblocks64 = 0;
+    bool any_dependent = false;
+    for (uint32_t f = 0; f < nframes; f++) {
+        if (wf[f].header_status != LZF_F_OK) { wf[f].nblocks = 0; continue; }
+        if (!(wf[f].flags & lzf::kFlagIndependent)) any_dependent = true;
+        nblocks64 += wf[f].nblocks;
+    }
+    if (any_dependent) return fail(c, LZF_ERR_UNSUPPORTED, "dependent-block frames are not on the GPU path yet");
+    if (nblocks64 > 0x7fffffffull) return fail(c, LZF_ERR_UNSUPPORTED, "too many blocks in one call");
+    const uint32_t nblocks = (uint32_t)nblocks64;
+
+    // ---- pass 1: block descriptors, decode, checksums
+    uint32_t* first = (uint32_t*)(h + o_first);
+    uint32_t* nblk = (uint32_t*)(h + o_nblk);
+    {
+        uint32_t b = 0;
+        for (uint32_t f = 0; f < nframes; f++) { first[f] = b; nblk[f] = wf[f].nblocks; b += wf[f].nblocks; }
+    }
+    Arena ba;   // device-only block arrays
+    ba.used = frame_desc_bytes;
+    const size_t o_bin_off = ba.take((size_t)nblocks * 8), o_bword = ba.take((size_t)nblocks * 4);
+    const size_t o_bcks = ba.take((size_t)nblocks * 4), o_boff = ba.take((size_t)nblocks * 8);
+    const size_t o_bcap = ba.take((size_t)nblocks * 4), o_blim = ba.take((size_t)nblocks * 4);
+    const size_t o_bplen = ba.take((size_t)nblocks * 8), o_bend = ba.take((size_t)nblocks * 8);
+    Arena rb;
+    const size_t r_olen = rb.take((size_t)nblocks * 4), r_bst = rb.take((size_t)nblocks * 4);
+    const size_t r_bxxh = rb.take((size_t)nblocks * 4), r_bcks = rb.take((size_t)nblocks * 4);
+    const size_t r_bend = rb.take((size_t)nblocks * 8);
+    const size_t r_chash = rb.take((size_t)nframes * 4);
+    if (ba.used > c->d_desc.cap) {
+        // growing d_desc would drop the frame arrays: re-upload them afterwards
+        if ((rc = ensure_dev(c, c->d_desc, ba.used))) return rc;
+        d = (uint8_t*)c->d_desc.p;
+        LZF_CU(c, cudaMemcpyAsync(d, h, o_first, cudaMemcpyHostToDevice, st));
+        wa.in_off = (const uint64_t*)(d + o_ioff); wa.in_len = (const uint64_t*)(d + o_ilen);
+    }
+    if ((rc = ensure_dev(c, c->d_res, rb.used))) return rc;
+    if ((rc = ensure_host(c, c->h_res, rb.used))) return rc;
+    uint8_t* r = (uint8_t*)c->d_res.p;
+    uint8_t* hr = (uint8_t*)c->h_res.p;
+    LZF_CU(c, cudaMemcpyAsync(d + o_first, h + o_first, o_hoff - o_first, cudaMemcpyHostToDevice, st));
+
+    bool any_block_checksums = false;
+    for (uint32_t f = 0; f < nframes; f++)
+        if (wf[f].header_status == LZF_F_OK && (wf[f].flags & lzf::kFlagBlockChecksums) && wf[f].nblocks) any_block_checksums = true;
+
+    if (nblocks) {
+        wa.mode = 1;
+        wa.first_block = (const uint32_t*)(d + o_first);
+        wa.out_off = (const uint64_t*)(d + o_ooff); wa.out_cap = (const uint64_t*)(d + o_ocap);
+        wa.blk_in_off = (uint64_t*)(d + o_bin_off); wa.blk_len_word = (uint32_t*)(d + o_bword);
+        wa.blk_checksum = (uint32_t*)(d + o_bcks);
+        wa.blk_out_off = (uint64_t*)(d + o_boff); wa.blk_out_cap = (uint32_t*)(d + o_bcap);
+        wa.blk_out_limit = (uint32_t*)(d + o_blim); wa.blk_payload_len = (uint64_t*)(d + o_bplen);
+        wa.blk_end = (uint64_t*)(d + o_bend);
+        LZF_LAUNCHED(c, lzf_launch_walk(&wa, st), 1);
+        if (any_block_checksums)    // decompress.rs:228-235: hash of the stored payload
+            LZF_LAUNCHED(c, lzf_launch_xxh32_ranges(d_in, (const uint64_t*)(d + o_bin_off), (const uint64_t*)(d + o_bplen),
+                                                   nblocks, (uint32_t*)(r + r_bxxh), st), 1);
+        rc = decompress_blocks_impl(c, d_in, (const uint64_t*)(d + o_bin_off), (const uint32_t*)(d + o_bword), nblocks,
+                                    nullptr, nullptr, nullptr, d_out, (const uint64_t*)(d + o_boff),
+                                    (const uint32_t*)(d + o_bcap), (const uint32_t*)(d + o_blim), (uint32_t*)(r + r_olen),
+                                    (int32_t*)(r + r_bst), nullptr, st);
+        if (rc) return rc;
+        LZF_CU(c, cudaMemcpyAsync(hr + r_olen, r + r_olen, r_bxxh - r_olen, cudaMemcpyDeviceToHost, st));
+        if (any_block_checksums) {
+            LZF_CU(c, cudaMemcpyAsync(hr + r_bxxh, r + r_bxxh, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, st));
+            LZF_CU(c, cudaMemcpyAsync(hr + r_bcks, d + o_bcks, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, st));
+        }
+        LZF_CU(c, cudaMemcpyAsync(hr + r_bend, d + o_bend, (size_t)nblocks * 8, cudaMemcpyDeviceToHost, st));
+        LZF_CU(c, cudaStreamSynchronize(st));
+    }
+    const uint32_t* b_olen = (const uint32_t*)(hr + r_olen);
+    const int32_t* b_st = (const int32_t*)(hr + r_bst);
+    const uint32_t* b_xxh = (const uint32_t*)(hr + r_bxxh);
+    const uint32_t* b_cks = (const uint32_t*)(hr + r_bcks);
+    const uint64_t* b_end = (const uint64_t*)(hr + r_bend);
+
+    // ---- resolve per-frame outcome in the reference's order (decompress.rs:197-279).  Pass 1 decoded
+    // block i of a frame at the fixed slot i * block_maxsize (exact for every frame whose non-final
+    // blocks are full, i.e. anything a compressor writes); the kernel reports each block's status
+    // and TRUE decoded length even when its slot was too small, so frames with short non-final
+    // blocks (hand-crafted, decompress.rs:165-166) are re-decoded below at their exact positions.
+    uint64_t* hoff = (uint64_t*)(h + o_hoff);
+    uint64_t* hlen = (uint64_t*)(h + o_hlen);
+    bool any_hash = false;
+    std::vector<uint8_t> want_hash(nframes, 0);
+    std::vector<uint32_t> redo_frames;              // frames needing exact placement
+    std::vector<uint32_t> delivered(nframes, 0);    // blocks whose plaintext the caller receives
+    for (uint32_t f = 0; f < nframes; f++) {
+        hoff[f] = out_off[f]; hlen[f] = 0;
+        const lzf::WalkFrame& w = wf[f];
+        if (w.header_status != LZF_F_OK) {
+            status[f] = w.header_status;
+            if (extra.detail) extra.detail[f] = w.header_detail;
+            continue;
+        }
+        const uint64_t bms = w.block_maxsize;
+        const bool bc = (w.flags & lzf::kFlagBlockChecksums) != 0;
+        const uint64_t capf = out_cap[f];
+        uint64_t o = 0;
+        int fs = LZF_F_OK, det = 0;
+        uint64_t consumed = w.consumed;
+        bool early_stop = false, irregular = false;
+        uint32_t i = 0;
+        for (; i < w.nblocks; i++) {
+            const uint32_t b = first[f] + i;
+            if (bc && b_xxh[b] != b_cks[b]) { fs = LZF_F_BLOCK_CHECKSUM_FAIL; break; }                     // :228-235
+            const int bst = b_st[b];
+            if (bst >= LZF_UNEXPECTED_END && bst <= LZF_INVALID_DEDUP_OFFSET) { fs = LZF_F_CODEC_ERROR; det = bst; break; }   // :247-248
+            const uint64_t ol = b_olen[b];
+            if (ol > bms) { fs = LZF_F_BLOCK_SIZE_OVERFLOW; break; }                                        // :272-274
+            if (o + ol > capf) { fs = LZF_F_WRITE_ERROR; break; }
+            const uint64_t rel = (uint64_t)i * bms;
+            const uint64_t slot_cap = rel < capf ? (bms < capf - rel ? bms : capf - rel) : 0;
+            if (ol && (o != rel || ol > slot_cap)) irregular = true;
+            o += ol;
+            if (ol == 0) { early_stop = true; consumed = b_end[b]; i++; break; }   // read_to_end sees Ok(0): decompress.rs:54-61,286
+        }
+        delivered[f] = i;
+        if (fs == LZF_F_OK && !early_stop) {
+            fs = w.term_status;                                  // EndMark / truncation / length-word overflow
+            if (fs == LZF_F_OK && (w.flags & lzf::kFlagContentChecksum)) { want_hash[f] = 1; any_hash = true; }
+        }
+        status[f] = fs;
+        out_len[f] = o;
+        hlen[f] = o;
+        if (irregular) redo_frames.push_back(f);
+        if (extra.detail) extra.detail[f] = det;
+        if (extra.consumed) extra.consumed[f] = consumed;
+    }
+    bool synced = true;
+    if (!redo_frames.empty()) {
+        uint32_t nredo = 0;
+        for (uint32_t f : redo_frames) nredo += delivered[f];
+        // host copies of the payload descriptors of pass 1
+        std::vector<uint64_t> p_in_off(nblocks);
+        std::vector<uint32_t> p_word(nblocks);
+        LZF_CU(c, cudaMemcpyAsync(p_in_off.data(), d + o_bin_off, (size_t)nblocks * 8, cudaMemcpyDeviceToHost, st));
+        LZF_CU(c, cudaMemcpyAsync(p_word.data(), d + o_bword, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, st));
+        LZF_CU(c, cudaStreamSynchronize(st));
+        Arena xa;
+        const size_t x_in_off = xa.take((size_t)nredo * 8), x_word = xa.take((size_t)nredo * 4);
+        const size_t x_out_off = xa.take((size_t)nredo * 8), x_cap = xa.take((size_t)nredo * 4);
+        const size_t x_lim = xa.take((size_t)nredo * 4), x_olen = xa.take((size_t)nredo * 4), x_st = xa.take((size_t)nredo * 4);
+        std::vector<uint8_t> xh(xa.used);
+        uint32_t k = 0;
+        for (uint32_t f : redo_frames) {
+            uint64_t o = 0;
+            for (uint32_t i = 0; i < delivered[f]; i++, k++) {
+                const uint32_t b = first[f] + i;
+                ((uint64_t*)(xh.data() + x_in_off))[k] = p_in_off[b];
+                ((uint32_t*)(xh.data() + x_word))[k] = p_word[b];
+                ((uint64_t*)(xh.data() + x_out_off))[k] = out_off[f] + o;
+                ((uint32_t*)(xh.data() + x_cap))[k] = b_olen[b];
+                ((uint32_t*)(xh.data() + x_lim))[k] = (uint32_t)wf[f].block_maxsize;
+                o += b_olen[b];
+            }
+        }
+        if ((rc = ensure_dev(c, c->d_comp, xa.used))) return rc;     // scratch free on this path
+        uint8_t* x = (uint8_t*)c->d_comp.p;
+        LZF_CU(c, cudaMemcpyAsync(x, xh.data(), xa.used, cudaMemcpyHostToDevice, st));
+        rc = decompress_blocks_impl(c, d_in, (const uint64_t*)(x + x_in_off), (const uint32_t*)(x + x_word), nredo,
+                                    nullptr, nullptr, nullptr, d_out, (const uint64_t*)(x + x_out_off),
+                                    (const uint32_t*)(x + x_cap), (const uint32_t*)(x + x_lim), (uint32_t*)(x + x_olen),
+                                    (int32_t*)(x + x_st), nullptr, st);
+        if (rc) return rc;
+        LZF_CU(c, cudaStreamSynchronize(st));    // xh must outlive the copy
+        synced = true;
+    }
+    (void)synced;
+    if (any_hash) {       // content checksum over the frame's plaintext (decompress.rs:207-211,276-278)
+        LZF_CU(c, cudaMemcpyAsync(d + o_hoff, h + o_hoff, frame_desc_bytes - o_hoff, cudaMemcpyHostToDevice, st));
+        LZF_LAUNCHED(c, lzf_launch_xxh32_ranges(d_out, (const uint64_t*)(d + o_hoff), (const uint64_t*)(d + o_hlen), nframes,
+                                               (uint32_t*)(r + r_chash), st), 1);
+        LZF_CU(c, cudaMemcpyAsync(hr + r_chash, r + r_chash, (size_t)nframes * 4, cudaMemcpyDeviceToHost, st));
+        LZF_CU(c, cudaStreamSynchronize(st));
+        const uint32_t* ch = (const uint32_t*)(hr + r_chash);
+        for (uint32_t f = 0; f < nframes; f++)
+            if (want_hash[f] && ch[f] != wf[f].content_checksum) status[f] = LZF_F_FRAME_CHECKSUM_FAIL;
+    }
+    return LZF_SUCCESS;
+}
+
+// Host-buffer batches usually come as one contiguous run of frames; then a single cudaMemcpy moves
+// the whole run and the device layout mirrors the host layout.  Otherwise frames are packed.
+struct HostLayout {
+    bool dense = false;
+    uint64_t base = 0, span = 0;
+    std::vector<uint64_t> dev_off;
+};
+HostLayout plan_layout(const uint64_t* off, const uint64_t* len, uint32_t n) {
+    HostLayout L;
+    L.dev_off.resize(n);
+    bool dense = n > 0;
+    for (uint32_t f = 0; f + 1 < n && dense; f++) dense = off[f + 1] == off[f] + len[f];
+    if (dense) {
+        L.dense = true;
+        L.base = off[0];
+        L.span = off[n - 1] + len[n - 1] - off[0];
+        for (uint32_t f = 0; f < n; f++) L.dev_off[f] = off[f] - L.base;
+    } else {
+        uint64_t t = 0;
+        for (uint32_t f = 0; f < n; f++) { L.dev_off[f] = t; t += (len[f] + 255) / 256 * 256; }
+        L.span = t;
+    }
+    return L;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// frame entry points
+// ------------------------------------------------------------------------------------------------
+extern "C" int lzf_frames_compress_device(lzf_ctx* c, const lzf_settings* s, const uint8_t* d_in, const uint64_t* in_off,
+                                          const uint64_t* in_len, uint32_t nframes, uint8_t* d_out,
+                                          const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len,
+                                          int32_t* status) {
+    if (!c) return LZF_ERR_INVALID_ARG;
+    LZF_CU(c, cudaSetDevice(c->device));
+    return frames_compress_core(c, s, d_in, in_off, in_len, nframes, d_out, out_off, out_cap, out_len, status, c->stream);
+}
+
+extern "C" int lzf_frames_compress(lzf_ctx* c, const lzf_settings* s, const uint8_t* in, const uint64_t* in_off,
+                                   const uint64_t* in_len, uint32_t nframes, uint8_t* out, const uint64_t* out_off,
+                                   const uint64_t* out_cap, uint64_t* out_len, int32_t* status) {
+    if (!c || !s) return LZF_ERR_INVALID_ARG;
+    if (nframes && (!in_off || !in_len || !out_off || !out_cap || !out_len || !status))
+        return fail(c, LZF_ERR_INVALID_ARG, "null pointer");
+    LZF_CU(c, cudaSetDevice(c->device));
+    std::vector<uint64_t> dcap(nframes);
+    for (uint32_t f = 0; f < nframes; f++) {
+        const uint64_t need = lzf_frame_bound(s, in_len[f]);
+        dcap[f] = out_cap[f] < need ? out_cap[f] : need;
+    }
+    const HostLayout li = plan_layout(in_off, in_len, nframes);
+    const HostLayout lo = plan_layout(out_off, dcap.data(), nframes);
+    int rc;
+    if ((rc = ensure_dev(c, c->d_io_in, li.span + 256))) return rc;
+    if ((rc = ensure_dev(c, c->d_io_out, lo.span + 256))) return rc;
+    uint8_t* din = (uint8_t*)c->d_io_in.p;
+    uint8_t* dout = (uint8_t*)c->d_io_out.p;
+    if (li.dense) {
+        if (li.span) LZF_CU(c, cudaMemcpyAsync(din, in + li.base, li.span, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        for (uint32_t f = 0; f < nframes; f++)
+            if (in_len[f]) LZF_CU(c, cudaMemcpyAsync(din + li.dev_off[f], in + in_off[f], in_len[f], cudaMemcpyHostToDevice, c->stream));
+    }
+    rc = frames_compress_core(c, s, din, li.dev_off.data(), in_len, nframes, dout, lo.dev_off.data(), dcap.data(), out_len,
+                              status, c->stream);
+    if (rc) return rc;
+    // compressed frames are much shorter than their capacity: always copy per frame
+    for (uint32_t f = 0; f < nframes; f++)
+        if (status[f] == LZF_F_OK && out_len[f])
+            LZF_CU(c, cudaMemcpyAsync(out + out_off[f], dout + lo.dev_off[f], out_len[f], cudaMemcpyDeviceToHost, c->stream));
+    LZF_CU(c, cudaStreamSynchronize(c->stream));
+    return LZF_SUCCESS;
+}
+
+extern "C" int lzf_frame_compress(lzf_ctx* c, const lzf_settings* s, const uint8_t* in, size_t n,
+                                  uint8_t* out, size_t cap, size_t* written, int32_t* status) {
+    if (!c || !s || !written || !status) return LZF_ERR_INVALID_ARG;
+    const uint64_t in_off = 0, in_len = n, out_off = 0, out_cap = cap;
+    uint64_t out_len = 0;
+    const int rc = lzf_frames_compress(c, s, in, &in_off, &in_len, 1, out, &out_off, &out_cap, &out_len, status);
+    *written = (size_t)out_len;
+    return rc;
+}
+
+extern "C" int lzf_frames_decompress_device(lzf_ctx* c, const uint8_t* d_in, const uint64_t* in_off, const uint64_t* in_len,
+                                            uint32_t nframes, uint8_t* d_out, const uint64_t* out_off,
+                                            const uint64_t* out_cap, uint64_t* out_len, int32_t* status, int32_t* detail) {
+    if (!c) return LZF_ERR_INVALID_ARG;
+    LZF_CU(c, cudaSetDevice(c->device));
+    DecodeOut ex{nullptr, detail};
+    return frames_decompress_core(c, d_in, in_off, in_len, nframes, d_out, out_off, out_cap, out_len, status, ex, c->stream);
+}
+
+namespace {
+int frames_decompress_host(lzf_ctx* c, const uint8_t* in, const uint64_t* in_off, const uint64_t* in_len,
+                           uint32_t nframes, uint8_t* out, const uint64_t* out_off, const uint64_t* out_cap,
+                           uint64_t* out_len, int32_t* status, int32_t* detail, uint64_t* consumed) {
+    if (nframes && (!in_off || !in_len || !out_off || !out_cap || !out_len || !status))
+        return fail(c, LZF_ERR_INVALID_ARG, "null pointer");
+    LZF_CU(c, cudaSetDevice(c->device));
+    std::vector<uint64_t> dcap(nframes);
+    for (uint32_t f = 0; f < nframes; f++) {
+        // a frame of C bytes decodes to at most ~C/5 blocks of <= 4 MiB; the device copy of the output
+        // is bounded by what the caller can take anyway
+        const uint64_t worst = (in_len[f] / 5 + 1) * (4ull << 20);
+        dcap[f] = out_cap[f] < worst ? out_cap[f] : worst;
+    }
+    const HostLayout li = plan_layout(in_off, in_len, nframes);
+    const HostLayout lo = plan_layout(out_off, dcap.data(), nframes);
+    int rc;
+    if ((rc = ensure_dev(c, c->d_io_in, li.span + 256))) return rc;
+    if ((rc = ensure_dev(c, c->d_io_out, lo.span + 256))) return rc;
+    uint8_t* din = (uint8_t*)c->d_io_in.p;
+    uint8_t* dout = (uint8_t*)c->d_io_out.p;
+    if (li.dense) {
+        if (li.span) LZF_CU(c, cudaMemcpyAsync(din, in + li.base, li.span, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        for (uint32_t f = 0; f < nframes; f++)
+            if (in_len[f]) LZF_CU(c, cudaMemcpyAsync(din + li.dev_off[f], in + in_off[f], in_len[f], cudaMemcpyHostToDevice, c->stream));
+    }
+    DecodeOut ex{consumed, detail};
+    rc = frames_decompress_core(c, din, li.dev_off.data(), in_len, nframes, dout, lo.dev_off.data(), dcap.data(), out_len,
+                                status, ex, c->stream);
+    if (rc) return rc;
+    bool full = lo.dense;      // every frame filled its capacity exactly: one copy moves the whole run
+    for (uint32_t f = 0; f < nframes && full; f++) full = out_len[f] == dcap[f];
+    if (full) {
+        if (lo.span) LZF_CU(c, cudaMemcpyAsync(out + lo.base, dout, lo.span, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        for (uint32_t f = 0; f < nframes; f++)
+            if (out_len[f]) LZF_CU(c, cudaMemcpyAsync(out + out_off[f], dout + lo.dev_off[f], out_len[f], cudaMemcpyDeviceToHost, c->stream));
+    }
+    LZF_CU(c, cudaStreamSynchronize(c->stream));
+    return LZF_SUCCESS;
+}
+}  // namespace
+
+extern "C" int lzf_frames_decompress(lzf_ctx* c, const uint8_t* in, const uint64_t* in_off, const uint64_t* in_len,
+                                     uint32_t nframes, uint8_t* out, const uint64_t* out_off, const uint64_t* out_cap,
+                                     uint64_t* out_len, int32_t* status, int32_t* detail) {
+    if (!c) return LZF_ERR_INVALID_ARG;
+    return frames_decompress_host(c, in, in_off, in_len, nframes, out, out_off, out_cap, out_len, status, detail, nullptr);
+}
+
+extern "C" int lzf_frame_decompress(lzf_ctx* c, const uint8_t* in, size_t n, const uint8_t* dict, size_t dlen,
+                                    uint8_t* out, size_t cap, size_t* written, size_t* consumed,
+                                    int32_t* status, int32_t* detail) {
+    if (!c || !written || !status) return LZF_ERR_INVALID_ARG;
+    if (dict && dlen) return fail(c, LZF_ERR_UNSUPPORTED, "dictionaries are not on the GPU path yet");
+    const uint64_t in_off = 0, in_len = n, out_off = 0, out_cap = cap;
+    uint64_t out_len = 0, cons = 0;
+    int32_t det = 0;
+    const int rc = frames_decompress_host(c, in, &in_off, &in_len, 1, out, &out_off, &out_cap, &out_len, status, &det, &cons);
+    *written = (size_t)out_len;
+    if (consumed) *consumed = (size_t)cons;
+    if (detail) *detail = det;
+    return rc;
+}

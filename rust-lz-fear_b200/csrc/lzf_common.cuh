@@ -4,8 +4,12 @@
 // (warp-uniform) arguments unless stated otherwise.
 #pragma once
 
-#include <cuda_runtime.h>
 #include <stdint.h>
+#ifndef LZF_SIMT_EMU   // tests/simt/simt_emu.h pre-defines the CUDA vocabulary for the CPU SIMT test harness
+#include <cuda_runtime.h>
+#define LZF_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define LZF_DYN_SMEM(name) extern __shared__ __align__(16) uint8_t name[]
+#endif
 
 #include "../../include/lzfear_b200.h"
 
@@ -51,16 +55,10 @@ constexpr uint32_t XP1 = 2654435761u, XP2 = 2246822519u, XP3 = 3266489917u, XP4 
 __device__ __forceinline__ uint32_t rotl32(uint32_t x, unsigned r) { return __funnelshift_l(x, x, r); }
 __device__ __forceinline__ uint32_t xxh_round(uint32_t acc, uint32_t x) { return rotl32(acc + x * XP2, 13) * XP1; }
 
-// XXH32(seed 0) of p[0..n) computed by one warp.  Lanes 0..3 each own one accumulator lane of
-// the 16-byte stripes; the tail and avalanche run on lane 0.  Returns the hash in every lane.
-__device__ __forceinline__ uint32_t warp_xxh32(const uint8_t* p, size_t n) {
+// Stripe phase of XXH32 by one warp: lanes 0..3 each own one accumulator of the 16-byte stripes.
+// `acc` holds the lane's incoming accumulator (lanes >= 4: ignored); returns the updated one.
+__device__ __forceinline__ uint32_t warp_xxh32_stripes(const uint8_t* p, size_t nstripes, uint32_t acc) {
     const unsigned lane = lane_id();
-    uint32_t acc = 0;
-    if (lane == 0) acc = XP1 + XP2;
-    else if (lane == 1) acc = XP2;
-    else if (lane == 2) acc = 0;
-    else if (lane == 3) acc = 0u - XP1;
-    const size_t nstripes = n >> 4;
     if (lane < 4) {
         const uint8_t* q = p + 4 * lane;
         const bool aligned = (reinterpret_cast<uintptr_t>(p) & 3u) == 0;
@@ -86,6 +84,19 @@ __device__ __forceinline__ uint32_t warp_xxh32(const uint8_t* p, size_t n) {
             for (; s < nstripes; s++) acc = xxh_round(acc, ld_u32_unaligned(q + s * 16));
         }
     }
+    return acc;
+}
+
+__device__ __forceinline__ uint32_t xxh32_seed_acc(unsigned lane) {
+    return lane == 0 ? XP1 + XP2 : lane == 1 ? XP2 : lane == 2 ? 0u : lane == 3 ? 0u - XP1 : 0u;
+}
+
+// XXH32(seed 0) of p[0..n) computed by one warp; the tail and avalanche run on lane 0.
+// Returns the hash in every lane.
+__device__ __forceinline__ uint32_t warp_xxh32(const uint8_t* p, size_t n) {
+    const unsigned lane = lane_id();
+    const size_t nstripes = n >> 4;
+    const uint32_t acc = warp_xxh32_stripes(p, nstripes, xxh32_seed_acc(lane));
     const uint32_t a0 = __shfl_sync(LZF_FULL_MASK, acc, 0);
     const uint32_t a1 = __shfl_sync(LZF_FULL_MASK, acc, 1);
     const uint32_t a2 = __shfl_sync(LZF_FULL_MASK, acc, 2);

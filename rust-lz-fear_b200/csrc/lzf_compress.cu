@@ -15,19 +15,10 @@
 // later lanes are discarded.  Forward/backward match extension (:117-145, :211-214) and the
 // sequence emit (:150-163, :239-260) are warp-parallel.  The per-warp hash table lives in shared
 // memory (16 KiB for the reference's 4096 x u32; 8 KiB when every position fits u16).
-#include "lzf_common.cuh"
+#include "lzf_kernels.cuh"
 
 namespace lzf {
 
-struct EncodeArgs {
-    const uint8_t* in; const uint64_t* in_off; const uint32_t* in_len; uint32_t nblocks;
-    uint32_t hashlog; uint32_t table_kind;
-    uint8_t* out; const uint64_t* out_off; const uint32_t* out_cap;
-    uint32_t* out_len; int32_t* status; uint32_t* xxh_plain; uint32_t* xxh_stored;
-    uint32_t* work_counter;      // zeroed before launch; dynamic block assignment
-    uint8_t* global_tables;      // per-warp tables when they do not fit shared memory
-    uint32_t max_block_len;      // every in_len[b] must be <= this (0 = unknown)
-};
 
 // offset of the j-th probe of a literal run from the run start: the closed form of
 //   cursor += step; step = step_counter >> 6; if literal_start + 1 != cursor { step_counter += 1 }
@@ -66,7 +57,7 @@ constexpr int kGlobalTableCtasPerSm = 4;   // bounds the global table scratch
 template <typename Slot, bool kHash4>
 __global__ void __launch_bounds__(kEncodeWarpsPerCta * 32)
 encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    LZF_DYN_SMEM(smem_raw);
     const unsigned lane = lane_id();
     const unsigned warp_in_cta = threadIdx.x >> 5;
     Slot* table;
@@ -275,7 +266,7 @@ extern "C" int lzf_launch_encode(const lzf::EncodeArgs* args, int num_sms, cudaS
     unsigned grid = (unsigned)(num_sms * ctas_per_sm);
     const unsigned need = (args->nblocks + kEncodeWarpsPerCta - 1) / kEncodeWarpsPerCta;
     if (grid > need) grid = need;
-    kern<<<grid, kEncodeWarpsPerCta * 32, dyn, stream>>>(*args, nslots, smem_tables ? 1 : 0);
+    LZF_LAUNCH(kern, grid, kEncodeWarpsPerCta * 32, dyn, stream, *args, nslots, smem_tables ? 1 : 0);
     return (int)cudaGetLastError();
 }
 

@@ -11,16 +11,10 @@
 // memory loads; long literal runs and stored blocks use 16-byte vector copies; matches are copied
 // lane-parallel with the sequential (overlapping) semantics of copy_overlapping
 // (src/raw/decompress.rs:80-138) preserved through modular source indexing.
-#include "lzf_common.cuh"
+#include "lzf_kernels.cuh"
 
 namespace lzf {
 
-struct DecodeArgs {
-    const uint8_t* in; const uint64_t* in_off; const uint32_t* in_len; uint32_t nblocks;
-    const uint8_t* prefix; const uint64_t* prefix_off; const uint32_t* prefix_len;
-    uint8_t* out; const uint64_t* out_off; const uint32_t* out_cap; const uint32_t* out_limit;
-    uint32_t* out_len; int32_t* status; uint32_t* xxh_plain;
-};
 
 // 128-byte register window over the compressed stream.
 struct Window {
@@ -184,9 +178,10 @@ decode_blocks_kernel(DecodeArgs a) {
 
 }  // namespace lzf
 
-extern "C" int lzf_launch_decode(const lzf::DecodeArgs* args, cudaStream_t stream) {
+extern "C" int lzf_launch_decode(const lzf::DecodeArgs* args, int num_sms, cudaStream_t stream) {
+    (void)num_sms;
     if (args->nblocks == 0) return 0;
     const unsigned grid = (args->nblocks + lzf::kDecodeWarpsPerCta - 1) / lzf::kDecodeWarpsPerCta;
-    lzf::decode_blocks_kernel<<<grid, lzf::kDecodeWarpsPerCta * 32, 0, stream>>>(*args);
+    LZF_LAUNCH(lzf::decode_blocks_kernel, grid, lzf::kDecodeWarpsPerCta * 32, 0, stream, *args);
     return (int)cudaGetLastError();
 }

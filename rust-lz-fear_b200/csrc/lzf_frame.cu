@@ -3,8 +3,8 @@
 //   * compress: per-frame layout scan + parallel assembly of `u32 len | payload | [u32 xxh]`
 //     (src/framed/compress.rs:244-263,277-281)
 //   * decompress: walking the block-length words of device-resident frames
-//     (src/framed/decompress.rs:205-235) and compaction of short non-final blocks
-#include "lzf_common.cuh"
+//     (src/framed/decompress.rs:205-235)
+#include "lzf_kernels.cuh"
 #include "lzf_frame.cuh"
 
 namespace lzf {
@@ -20,21 +20,19 @@ xxh32_ranges_kernel(const uint8_t* data, const uint64_t* off, const uint64_t* le
     if (lane_id() == 0) hash[r] = h;
 }
 
+// Stripe phase only, one warp, carrying a running state: acc[0..4) in/out (streaming content
+// checksums of the Read/Write-style host API, src/framed/compress.rs:233-235).
+__global__ void __launch_bounds__(32) xxh32_stripes_kernel(const uint8_t* data, uint64_t nstripes, uint32_t* acc) {
+    const unsigned lane = lane_id();
+    uint32_t a = lane < 4 ? acc[lane] : 0u;
+    a = warp_xxh32_stripes(data, nstripes, a);
+    if (lane < 4) acc[lane] = a;
+}
+
 // ------------------------------------------------------------------------------------------
 // compress: layout.  One warp per frame scans its blocks' stored sizes, decides the position of
 // every block inside the frame, and writes header, EndMark and content checksum.
 // ------------------------------------------------------------------------------------------
-struct LayoutArgs {
-    uint32_t nframes;
-    const uint32_t* first_block; const uint32_t* nblocks;
-    const uint32_t* blk_in_len; const uint32_t* blk_comp_len; const int32_t* blk_status;
-    int block_checksums; int content_checksum;
-    const uint8_t* headers;          // nframes x 20: [0] = header length, [1..] = header bytes
-    uint8_t* out; const uint64_t* out_off; const uint64_t* out_cap;
-    const uint32_t* content_hash;    // per frame (valid when content_checksum)
-    uint64_t* blk_dst;               // out: absolute offset in `out` of each block's length word (~0 = skip)
-    uint64_t* frame_len; int32_t* frame_status;
-};
 
 __global__ void __launch_bounds__(128) frame_layout_kernel(LayoutArgs a) {
     const unsigned lane = lane_id();
@@ -94,13 +92,6 @@ __global__ void __launch_bounds__(128) frame_layout_kernel(LayoutArgs a) {
 // compress: assembly.  grid = (blocks, slices); every CTA moves one 64 KiB slice of one block's
 // stored payload into the frame; slice 0 also writes the length word and the block checksum.
 // ------------------------------------------------------------------------------------------
-struct AssembleArgs {
-    uint32_t nblocks;
-    const uint8_t* in; const uint64_t* blk_in_off; const uint32_t* blk_in_len;
-    const uint8_t* comp; const uint64_t* blk_comp_off; const uint32_t* blk_comp_len; const int32_t* blk_status;
-    const uint32_t* blk_xxh_stored;  // nullable
-    const uint64_t* blk_dst; uint8_t* out;
-};
 constexpr uint32_t kSliceBytes = 64 * 1024;
 
 __global__ void __launch_bounds__(256) frame_assemble_kernel(AssembleArgs a) {
@@ -130,26 +121,6 @@ __global__ void __launch_bounds__(256) frame_assemble_kernel(AssembleArgs a) {
 // decompress: frame walk.  One thread per frame parses the header and chases the block-length
 // words (decompress.rs:205-235).  mode 0 = count blocks, mode 1 = also fill block descriptors.
 // ------------------------------------------------------------------------------------------
-struct WalkFrame {                 // per-frame result
-    int32_t header_status; int32_t header_detail;
-    uint32_t flags; uint32_t nblocks;          // blocks whose payload (and checksum) are fully present
-    uint64_t block_maxsize;
-    int32_t term_status;                       // LZF_F_OK if the EndMark (and content checksum) was read
-    uint32_t content_checksum;
-    uint64_t consumed;
-    uint64_t content_size; uint32_t dictionary_id; uint32_t has_fields;   // bit0 content size, bit1 dict id
-};
-struct WalkArgs {
-    uint32_t nframes; int mode;
-    const uint8_t* in; const uint64_t* in_off; const uint64_t* in_len;
-    WalkFrame* frames;
-    // mode 1
-    const uint32_t* first_block;
-    const uint64_t* out_off; const uint64_t* out_cap;
-    uint64_t* blk_in_off; uint32_t* blk_len_word; uint32_t* blk_checksum;
-    uint64_t* blk_out_off; uint32_t* blk_out_cap; uint32_t* blk_out_limit;
-    uint64_t* blk_payload_len;     // u64 copy of the payload length (for xxh32_ranges)
-};
 
 __device__ __forceinline__ uint32_t rd32_bytes(const uint8_t* p) {
     return uint32_t(p[0]) | (uint32_t(p[1]) << 8) | (uint32_t(p[2]) << 16) | (uint32_t(p[3]) << 24);
@@ -205,6 +176,7 @@ __global__ void __launch_bounds__(64) frame_walk_kernel(WalkArgs a) {
                 a.blk_len_word[b] = word;
                 a.blk_payload_len[b] = blen;
                 a.blk_checksum[b] = cks;
+                a.blk_end[b] = p;
                 const uint64_t rel = (uint64_t)i * bms;
                 const uint64_t capf = a.out_cap[f];
                 a.blk_out_off[b] = a.out_off[f] + (rel < capf ? rel : capf);
@@ -219,47 +191,21 @@ __global__ void __launch_bounds__(64) frame_walk_kernel(WalkArgs a) {
     if (a.mode == 0) a.frames[f] = w;
 }
 
-// ------------------------------------------------------------------------------------------
-// decompress: compaction (rare).  When a non-final block decodes to fewer than block_maxsize
-// bytes (hand-crafted frames, decompress.rs:165-166), later blocks are moved left so the frame's
-// plaintext is contiguous.  One warp per frame, blocks in order, forward copy (dst < src).
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32)
-frame_compact_kernel(uint32_t nframes, const uint32_t* first_block, const uint32_t* nblocks, const uint8_t* needs,
-                     const uint64_t* blk_out_off, const uint32_t* blk_out_len, const uint64_t* out_off, uint8_t* out) {
-    const uint32_t f = blockIdx.x;
-    if (f >= nframes || !needs[f]) return;
-    const unsigned lane = lane_id();
-    uint64_t dst = out_off[f];
-    for (uint32_t i = 0; i < nblocks[f]; i++) {
-        const uint32_t b = first_block[f] + i;
-        const uint64_t src = blk_out_off[b];
-        const uint64_t len = blk_out_len[b];
-        if (src != dst) {
-            for (uint64_t k0 = 0; k0 < len; k0 += 32) {
-                const uint64_t k = k0 + lane;
-                uint8_t v = 0;
-                if (k < len) v = out[src + k];
-                __syncwarp();
-                if (k < len) out[dst + k] = v;
-                __syncwarp();
-            }
-        }
-        dst += len;
-    }
-}
-
 }  // namespace lzf
 
 extern "C" int lzf_launch_xxh32_ranges(const uint8_t* data, const uint64_t* off, const uint64_t* len,
                                        uint32_t nranges, uint32_t* hash, cudaStream_t s) {
     if (!nranges) return 0;
-    lzf::xxh32_ranges_kernel<<<(nranges + 3) / 4, 128, 0, s>>>(data, off, len, nranges, hash);
+    LZF_LAUNCH(lzf::xxh32_ranges_kernel, (nranges + 3) / 4, 128, 0, s, data, off, len, nranges, hash);
+    return (int)cudaGetLastError();
+}
+extern "C" int lzf_launch_xxh32_stripes(const uint8_t* data, uint64_t nstripes, uint32_t* acc, cudaStream_t s) {
+    LZF_LAUNCH(lzf::xxh32_stripes_kernel, 1, 32, 0, s, data, nstripes, acc);
     return (int)cudaGetLastError();
 }
 extern "C" int lzf_launch_layout(const lzf::LayoutArgs* a, cudaStream_t s) {
     if (!a->nframes) return 0;
-    lzf::frame_layout_kernel<<<(a->nframes + 3) / 4, 128, 0, s>>>(*a);
+    LZF_LAUNCH(lzf::frame_layout_kernel, (a->nframes + 3) / 4, 128, 0, s, *a);
     return (int)cudaGetLastError();
 }
 extern "C" int lzf_launch_assemble(const lzf::AssembleArgs* a, uint32_t max_block_len, cudaStream_t s) {
@@ -267,18 +213,11 @@ extern "C" int lzf_launch_assemble(const lzf::AssembleArgs* a, uint32_t max_bloc
     uint32_t slices = (max_block_len + lzf::kSliceBytes - 1) / lzf::kSliceBytes;
     if (slices == 0) slices = 1;
     dim3 grid(a->nblocks, slices);
-    lzf::frame_assemble_kernel<<<grid, 256, 0, s>>>(*a);
+    LZF_LAUNCH(lzf::frame_assemble_kernel, grid, 256, 0, s, *a);
     return (int)cudaGetLastError();
 }
 extern "C" int lzf_launch_walk(const lzf::WalkArgs* a, cudaStream_t s) {
     if (!a->nframes) return 0;
-    lzf::frame_walk_kernel<<<(a->nframes + 63) / 64, 64, 0, s>>>(*a);
-    return (int)cudaGetLastError();
-}
-extern "C" int lzf_launch_compact(uint32_t nframes, const uint32_t* first_block, const uint32_t* nblocks,
-                                  const uint8_t* needs, const uint64_t* blk_out_off, const uint32_t* blk_out_len,
-                                  const uint64_t* out_off, uint8_t* out, cudaStream_t s) {
-    if (!nframes) return 0;
-    lzf::frame_compact_kernel<<<nframes, 32, 0, s>>>(nframes, first_block, nblocks, needs, blk_out_off, blk_out_len, out_off, out);
+    LZF_LAUNCH(lzf::frame_walk_kernel, (a->nframes + 63) / 64, 64, 0, s, *a);
     return (int)cudaGetLastError();
 }

@@ -1,0 +1,167 @@
+"""Parity checks shared by the SIMT-emulator tier (CPU, small sizes) and the `-m gpu` tier (the
+product .so on a B200): every check drives the C ABI through the product Python binding and
+compares with the oracle, bit for bit."""
+import numpy as np
+
+from lz_fear_b200 import _native as N
+from lz_fear_b200 import workloads as W
+
+
+def sample_inputs(scale=1):
+    """A spread of block contents: reference test strings are added by the callers."""
+    t = lambda n, s: W.text(n, seed=s).numpy().tobytes()
+    lo = lambda n, s: W.lowent(n, seed=s).numpy().tobytes()
+    rnd = lambda n, s: W.random_bytes(n, seed=s).numpy().tobytes()
+    cases = [b"", b"a", b"abcd" * 3, b"\0" * 13, b"\0" * 65536, rnd(5000, 1), t(70000, 3), lo(100000, 4), t(300, 5),
+             rnd(20000, 6)[:20000:1], bytes(np.random.default_rng(7).integers(0, 4, 20000, dtype=np.uint8)),
+             b"\0" * 1200 + rnd(800, 8) + b"\0" * 3000, t(65535, 9), t(65536, 10), t(65537, 11)]
+    for n in [1, 4, 5, 11, 12, 13, 14, 15, 16, 17, 20, 33, 64, 100, 255, 256, 270, 1000, 4096]:
+        cases += [t(n, n), b"\0" * n, lo(n, n + 1000), rnd(n, n + 2000)]
+    if scale > 1:
+        cases += [t(1 << 20, 21), lo(4 << 20, 22), rnd(1 << 20, 23), b"\0" * (4 << 20), t(4 << 20, 24)]
+    return cases
+
+
+def check_raw_compress(backend, oracle, inputs, table=N.TABLE_U32, hashlog=12):
+    for data in inputs:
+        if table == N.TABLE_U16 and len(data) > 0xFFFF:
+            continue
+        st, out = backend.ctx.raw_compress_into(data, table=table, hashlog=hashlog)
+        ost, oout = oracle.compress_block(data, table=table, hashlog=hashlog)
+        assert (st, out) == (ost, oout), "compress mismatch len=%d table=%d hashlog=%d" % (len(data), table, hashlog)
+        # bounded writer: cap = own length (src/framed/compress.rs:242) and a few tight caps
+        for cap in {len(data), len(oout), max(len(oout) - 1, 0), len(oout) // 2}:
+            st, out = backend.ctx.raw_compress_into(data, cap=cap, table=table, hashlog=hashlog)
+            ost, oo = oracle.compress_block(data, table=table, hashlog=hashlog, cap=cap)
+            assert st == ost and (st != 0 or out == oo), "capped compress mismatch len=%d cap=%d" % (len(data), cap)
+
+
+def check_raw_decompress(backend, oracle, blocks, limit_of=lambda b, n: n):
+    """blocks: list of (compressed bytes, plaintext length or None)"""
+    for comp, n in blocks:
+        lims = [1 << 30] if n is None else sorted({n, max(n - 1, 0), n + 5, n // 2})
+        for lim in lims:
+            cap = (n if n is not None else 1 << 16) + len(comp) + 64
+            st, out, ln = backend.ctx.raw_decompress(comp, out_limit=lim, cap=cap)
+            ost, oout, oln = oracle.decompress_raw(comp, out_limit=lim, cap=cap)
+            assert (st, ln, out) == (ost, oln, oout), "decompress mismatch comp_len=%d limit=%d: %s vs %s" % (
+                len(comp), lim, (st, ln), (ost, oln))
+
+
+def mutate(blob, seed, k=1):
+    rng = np.random.default_rng(seed)
+    a = bytearray(blob)
+    if not a:
+        return bytes(a)
+    for _ in range(k):
+        i = int(rng.integers(0, len(a)))
+        a[i] = int(rng.integers(0, 256))
+    if rng.integers(0, 4) == 0:
+        a = a[: int(rng.integers(0, len(a) + 1))]
+    return bytes(a)
+
+
+def check_batched_blocks(backend, oracle, inputs, use_torch_device=None):
+    """lzf_compress_blocks + lzf_decompress_blocks with (emulated or real) device buffers."""
+    import torch
+    dev = use_torch_device or "cpu"
+    nb = len(inputs)
+    lens = np.array([len(b) for b in inputs], dtype=np.uint32)
+    pad = lambda x: (x.astype(np.uint64) + 255) // 256 * 256
+    in_off = np.zeros(nb, dtype=np.uint64); in_off[1:] = np.cumsum(pad(lens))[:-1]
+    total = int(in_off[-1] + pad(lens)[-1]) + 256
+    flat = np.zeros(total, dtype=np.uint8)
+    for i, b in enumerate(inputs):
+        flat[int(in_off[i]): int(in_off[i]) + len(b)] = np.frombuffer(b, dtype=np.uint8)
+    T = lambda a: torch.from_numpy(a.view(np.int64) if a.dtype == np.uint64 else a.view(np.int32) if a.dtype == np.uint32 else a).to(dev)
+    d_in, d_off, d_len = T(flat), T(in_off), T(lens)
+    d_out = torch.zeros(total, dtype=torch.uint8, device=dev)
+    d_olen = torch.zeros(nb, dtype=torch.int32, device=dev)
+    d_st = torch.zeros(nb, dtype=torch.int32, device=dev)
+    d_xp = torch.zeros(nb, dtype=torch.int32, device=dev)
+    d_xs = torch.zeros(nb, dtype=torch.int32, device=dev)
+    backend.ctx.compress_blocks(d_in, d_off, d_len, nb, d_out, d_off, None, d_olen, d_st, d_xp, d_xs)
+    if dev != "cpu":
+        torch.cuda.synchronize()
+    out = d_out.cpu().numpy(); olen = d_olen.cpu().numpy().view(np.uint32); st = d_st.cpu().numpy()
+    xp = d_xp.cpu().numpy().view(np.uint32); xs = d_xs.cpu().numpy().view(np.uint32)
+    comp_blocks = []
+    for i, b in enumerate(inputs):
+        ost, oo = oracle.compress_block(b, cap=len(b))
+        assert st[i] == ost, "status of block %d (len %d): %d vs %d" % (i, len(b), st[i], ost)
+        assert xp[i] == oracle.xxh32(b), "plain xxh32 of block %d" % i
+        if ost == 0:
+            got = out[int(in_off[i]): int(in_off[i]) + int(olen[i])].tobytes()
+            assert got == oo, "bytes of block %d (len %d)" % (i, len(b))
+            assert xs[i] == oracle.xxh32(oo)
+            comp_blocks.append(oo)
+        else:
+            assert xs[i] == oracle.xxh32(b)
+            comp_blocks.append(None)
+    # decode what compressed (and the stored ones via the INCOMPRESSIBLE bit)
+    words = np.array([(len(c) if c is not None else (len(b) | N.INCOMPRESSIBLE)) for c, b in zip(comp_blocks, inputs)],
+                     dtype=np.uint32)
+    cflat = np.zeros(total, dtype=np.uint8)
+    for i, (c, b) in enumerate(zip(comp_blocks, inputs)):
+        src = c if c is not None else b
+        cflat[int(in_off[i]): int(in_off[i]) + len(src)] = np.frombuffer(src, dtype=np.uint8)
+    d_cin, d_words = T(cflat), T(words)
+    d_plain = torch.zeros(total, dtype=torch.uint8, device=dev)
+    d_cap = T(lens.copy()); d_lim = T(lens.copy())
+    backend.ctx.decompress_blocks(d_cin, d_off, d_words, nb, d_plain, d_off, d_cap, d_lim, d_olen, d_st, d_xp)
+    if dev != "cpu":
+        torch.cuda.synchronize()
+    plain = d_plain.cpu().numpy(); olen = d_olen.cpu().numpy().view(np.uint32); st = d_st.cpu().numpy()
+    xp = d_xp.cpu().numpy().view(np.uint32)
+    for i, b in enumerate(inputs):
+        assert st[i] == 0 and olen[i] == len(b), "decode status of block %d: %d len %d/%d" % (i, st[i], olen[i], len(b))
+        assert plain[int(in_off[i]): int(in_off[i]) + len(b)].tobytes() == b, "decode bytes of block %d" % i
+        assert xp[i] == oracle.xxh32(b)
+
+
+FRAME_SETTINGS = [
+    dict(),
+    dict(block_size=64 << 10),
+    dict(block_size=64 << 10, block_checksums=True),
+    dict(block_size=256 << 10, content_checksum=False),
+    dict(block_size=1 << 20, block_checksums=True, content_checksum=False),
+    dict(block_size=64 << 10, content_size=12345),
+    dict(block_size=64 << 10, dictionary_id=0xDEADBEEF, block_checksums=True),
+]
+
+
+def check_frames(backend, oracle, inputs, settings_list=FRAME_SETTINGS):
+    for kw in settings_list:
+        for data in inputs:
+            st, frame = backend.ctx.frame_compress(data, **kw)
+            orc, oframe = oracle.frame_compress(data, **kw)
+            assert st == orc, "frame compress status %s len=%d: %d vs %d" % (kw, len(data), st, orc)
+            assert frame == oframe, "frame bytes differ %s len=%d" % (kw, len(data))
+            cap = len(data) + 64
+            st, det, plain, cons = backend.ctx.frame_decompress(frame, cap=cap)
+            orc, odet, oplain, ocons = oracle.frame_decompress(frame, cap=cap)
+            assert (st, det, plain) == (orc, odet, oplain), "frame decompress %s len=%d: %s vs %s" % (
+                kw, len(data), (st, det, len(plain)), (orc, odet, len(oplain)))
+            assert st == 0 and plain == data and cons == ocons == len(frame)
+
+
+def check_frame_decode_errors(backend, oracle, frames, dependent_ok=False):
+    """Arbitrary / mutated frames: status, detail and the plaintext decoded before the failure."""
+    n_ok = 0
+    for blob in frames:
+        rc, det, info = N.parse_frame_header(blob)
+        orc, odet, oinfo = oracle.parse_header(blob)
+        assert (rc, det) == (orc, odet), "header parse"
+        if rc == 0:
+            assert (info.flags, info.block_maxsize, info.header_len) == (oinfo.flags, oinfo.block_maxsize, oinfo.header_len)
+            if not (info.flags & 0x20) and not dependent_ok:
+                continue           # dependent-block frames: not on the GPU path yet
+        cap = 1 << 22
+        orc, odet, oplain, ocons = oracle.frame_decompress(blob, cap=cap)
+        st, det, plain, cons = backend.ctx.frame_decompress(blob, cap=cap)
+        assert (st, det) == (orc, odet), "frame status %s vs oracle %s (len %d)" % ((st, det), (orc, odet), len(blob))
+        assert plain == oplain, "plaintext before failure differs (status %d)" % st
+        if st == 0:
+            assert cons == ocons
+            n_ok += 1
+    return n_ok

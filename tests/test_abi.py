@@ -1,0 +1,83 @@
+"""The shipped C-ABI library: builds for sm_100a, loads, exports every symbol include/*.h declares,
+and refuses to work without a CUDA device (no CPU fallback).  No compute calls here."""
+import ctypes
+import importlib.util
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _build():
+    spec = importlib.util.spec_from_file_location("lzf_build", os.path.join(ROOT, "rust-lz-fear_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.build()
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "lzfear_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(lzf_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    lib_path = _build()
+    lib = ctypes.CDLL(lib_path)
+    names = declared_symbols()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(lib, name), "liblzfear_b200.so does not export %s" % name
+    lib.lzf_abi_version.restype = ctypes.c_int
+    assert lib.lzf_abi_version() == 1
+
+
+def test_python_binding_covers_the_header():
+    from lz_fear_b200 import _native
+    assert sorted(_native.EXPORTED_SYMBOLS) == declared_symbols()
+
+
+def test_library_targets_sm_100a_and_contains_the_kernels():
+    lib_path = _build()
+    out = subprocess.run(["cuobjdump", "-lelf", lib_path], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in out.stdout
+    syms = subprocess.run(["cuobjdump", "-res-usage", lib_path], capture_output=True, text=True).stdout
+    for kern in ("encode_blocks_kernel", "decode_blocks_kernel", "xxh32_ranges_kernel", "frame_layout_kernel",
+                 "frame_assemble_kernel", "frame_walk_kernel"):
+        assert kern in syms, kern
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from lz_fear_b200 import _native
+    saved = (_native._lib, _native._lib_path)
+    try:
+        _native._lib = None
+        _native.load_library(_build())
+        with pytest.raises(_native.NativeLibraryError):
+            _native.Context(0)
+    finally:
+        _native._lib, _native._lib_path = saved
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    from lz_fear_b200 import _native
+    with pytest.raises(_native.NativeLibraryError):
+        _native.load_library(str(tmp_path / "nope.so"))
+
+
+def test_product_sources_never_touch_the_oracle_or_the_emulator():
+    pkg = os.path.join(ROOT, "rust-lz-fear_b200")
+    for base, _dirs, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                txt = open(os.path.join(base, f), errors="replace").read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "lzf_oracle" not in txt, f
+                assert "simt_emu.h\"" not in txt and "libsimt" not in txt, f

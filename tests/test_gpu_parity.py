@@ -1,0 +1,203 @@
+"""`-m gpu` tier: the shipped liblzfear_b200.so on a real B200, through the C ABI, against the
+oracle — bit-exact on the same seeded inputs, the committed golden fixtures, and size-independent
+properties at BASELINE.json sizes."""
+import numpy as np
+import pytest
+
+import parity
+from lz_fear_b200 import _native as N
+from lz_fear_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+
+def _strings(vectors):
+    return [s.encode("latin-1") for v in vectors["roundtrip_strings"].values() for s in v]
+
+
+def test_raw_compress_matches_oracle(gpu, oracle, vectors):
+    parity.check_raw_compress(gpu, oracle, parity.sample_inputs(scale=16) + _strings(vectors))
+
+
+def test_raw_compress_u16_table(gpu, oracle, vectors):
+    inputs = [b for b in parity.sample_inputs() + _strings(vectors) if len(b) <= 0xFFFF]
+    parity.check_raw_compress(gpu, oracle, inputs, table=N.TABLE_U16)
+    assert gpu.ctx.raw_compress_into(bytes(70000), table=N.TABLE_U16)[0] == N.PANIC
+
+
+def test_raw_compress_large_hashlog(gpu, oracle):
+    inputs = [b for b in parity.sample_inputs(scale=16) if len(b) >= 1000][:12]
+    for hashlog in (13, 14, 16):
+        parity.check_raw_compress(gpu, oracle, inputs, hashlog=hashlog)
+
+
+def test_decode_kats(gpu, oracle, vectors):
+    parity.check_raw_decompress(gpu, oracle, [(bytes(k["input"]), None) for k in vectors["decode_kats"]])
+    assert gpu.ctx.raw_decompress(bytes([0x11, 97, 1, 0, 0x22, 98, 99, 2, 0]))[:2] == (0, b"aaaaaabcbcbcbc")
+
+
+def test_raw_decompress_matches_oracle(gpu, oracle):
+    blocks = [(oracle.compress_block(d)[1], len(d)) for d in parity.sample_inputs(scale=16)]
+    parity.check_raw_decompress(gpu, oracle, blocks)
+
+
+def test_raw_decompress_malformed(gpu, oracle):
+    base = [oracle.compress_block(d)[1] for d in parity.sample_inputs() if 20 <= len(d) <= 70000]
+    blocks = [(parity.mutate(comp, 100 * i + k, k=1 + k % 3), None) for i, comp in enumerate(base) for k in range(8)]
+    blocks += [(bytes([0x0F]), None), (bytes([0xF0]), None), (bytes([0xF0, 0xFF]), None), (bytes([0, 0, 0]), None),
+               (bytes([0x10, 65, 0x01]), None), (bytes([0x1F, 65, 1, 0, 0xFF]), None), (bytes([0x00, 1, 0]), None)]
+    parity.check_raw_decompress(gpu, oracle, blocks)
+
+
+def test_raw_decompress_with_prefix(gpu, oracle):
+    prefix = b"0123456789abcdef" * 8
+    comp = bytes([0x42, 120, 121, 122, 119, 20, 0, 0x00, 3, 0])
+    for lim in (6, 10, 1 << 20):
+        assert gpu.ctx.raw_decompress(comp, prefix=prefix, out_limit=lim, cap=256) == \
+            oracle.decompress_raw(comp, prefix=prefix, out_limit=lim, cap=256)
+    assert gpu.ctx.raw_decompress(comp, prefix=prefix[:10], out_limit=1 << 20, cap=256)[0] == N.INVALID_DEDUP_OFFSET
+
+
+def test_big_compression_roundtrip(gpu, oracle):               # src/lib.rs:97-106, 80 000 000 bytes
+    i = np.arange(80_000_000, dtype=np.uint64).astype(np.uint8)
+    data = ((i * np.uint8(0xA) + np.uint8(33)) ^ np.uint8(0xA2)).astype(np.uint8)
+    st, comp = gpu.ctx.raw_compress_into(data)
+    assert (st, comp) == oracle.compress_block(data)
+    st, out, n = gpu.ctx.raw_decompress(comp, cap=len(data) + 16)
+    assert st == 0 and n == len(data) and np.array_equal(np.frombuffer(out, dtype=np.uint8), data)
+
+
+def test_batched_blocks_device(gpu, oracle):
+    inputs = [b for b in parity.sample_inputs(scale=16) if len(b) > 0]
+    parity.check_batched_blocks(gpu, oracle, inputs, use_torch_device="cuda")
+
+
+def test_frames_roundtrip_and_bytes(gpu, oracle):
+    s = parity.sample_inputs(scale=16)
+    inputs = [b"", b"a", bytes(65536), s[6], s[7][:70001], s[5] * 30, s[-1] + s[-3] + s[-5][:1234567]]
+    parity.check_frames(gpu, oracle, inputs)
+    st, frame = gpu.ctx.frame_compress(bytes(65536))              # BASELINE config 1 KAT
+    assert st == 0 and len(frame) == 286 and frame[-4:] == bytes([0x1C, 0xE8, 0x64, 0x0F])
+
+
+def test_frame_decode_corpus(gpu, oracle, corpora):
+    parity.check_frame_decode_errors(gpu, oracle, [b for _, b in corpora["decode"]])
+
+
+def test_roundtrip_and_interop_corpora(gpu, oracle, corpora):
+    for name, data in corpora["roundtrip_fuzz"] + corpora["interop_decode"]:
+        st, frame = gpu.ctx.frame_compress(data)
+        assert (st, frame) == oracle.frame_compress(data), name
+        st, det, plain, cons = gpu.ctx.frame_decompress(frame, cap=len(data) + 16)
+        assert (st, plain) == (0, data), name
+
+
+def test_frame_decode_mutations(gpu, oracle):
+    s = parity.sample_inputs()
+    data = s[6] + s[5]
+    frames = []
+    for kw in parity.FRAME_SETTINGS[1:5]:
+        rc, frame = oracle.frame_compress(data, **kw)
+        for k in range(40):
+            frames.append(parity.mutate(frame, hash(str(sorted(kw.items()))) % 1000 + k, k=1 + k % 3))
+        frames += [frame[:n] for n in (0, 3, 6, 7, 10, 11, len(frame) - 5, len(frame) - 1)]
+    parity.check_frame_decode_errors(gpu, oracle, frames)
+
+
+def test_config2_seq50_decompress_vs_oracle(gpu, oracle):
+    """4096 of the config-2 blocks bit-exact against the oracle (the full 4 GiB runs in bench.py)."""
+    import torch
+    nb = 4096
+    comp, off, ln = W.seq50_blocks(nb, device="cuda")
+    out = torch.empty(nb * 65536, dtype=torch.uint8, device="cuda")
+    out_off = torch.arange(nb, device="cuda", dtype=torch.int64) * 65536
+    cap = torch.full((nb,), 65536, dtype=torch.int32, device="cuda")
+    olen = torch.zeros(nb, dtype=torch.int32, device="cuda")
+    st = torch.zeros(nb, dtype=torch.int32, device="cuda")
+    xx = torch.zeros(nb, dtype=torch.int32, device="cuda")
+    gpu.ctx.decompress_blocks(comp, off, ln, nb, out, out_off, cap, cap, olen, st, xx)
+    torch.cuda.synchronize()
+    assert int(st.abs().sum()) == 0 and bool((olen == 65536).all())
+    c, o = comp.cpu().numpy(), out.cpu().numpy()
+    offs, lens = off.cpu().numpy(), ln.cpu().numpy()
+    ref = np.empty(nb * 65536, dtype=np.uint8)
+    ool, ost = oracle.decompress_blocks_mt(c, offs.astype(np.uint64), lens.astype(np.uint32), ref,
+                                           out_off.cpu().numpy().astype(np.uint64), np.full(nb, 65536, np.uint32),
+                                           np.full(nb, 65536, np.uint32), nthreads=8)
+    assert not ost.any() and np.array_equal(ref, o)
+    xs = xx.cpu().numpy().view(np.uint32)
+    for b in range(0, nb, 97):
+        assert xs[b] == oracle.xxh32(ref[b * 65536:(b + 1) * 65536])
+
+
+def test_config3_text_compress_vs_oracle(gpu, oracle):
+    """64 of the config-3 blocks (4 MiB text) byte-identical to the oracle, then decoded back."""
+    import torch
+    nb, B = 64, 4 << 20
+    data = W.TextSource(device="cuda").make(nb * B)
+    off = torch.arange(nb, device="cuda", dtype=torch.int64) * B
+    ln = torch.full((nb,), B, dtype=torch.int32, device="cuda")
+    comp = torch.empty(nb * B, dtype=torch.uint8, device="cuda")
+    olen = torch.zeros(nb, dtype=torch.int32, device="cuda")
+    st = torch.zeros(nb, dtype=torch.int32, device="cuda")
+    gpu.ctx.compress_blocks(data, off, ln, nb, comp, off, None, olen, st)
+    torch.cuda.synchronize()
+    assert int(st.abs().sum()) == 0
+    h = data.cpu().numpy()
+    ref = np.empty(nb * B, dtype=np.uint8)
+    rlen, rst = oracle.compress_blocks_mt(h, off.cpu().numpy().astype(np.uint64), np.full(nb, B, np.uint32), ref,
+                                          off.cpu().numpy().astype(np.uint64), nthreads=8)
+    got_len = olen.cpu().numpy().view(np.uint32)
+    assert np.array_equal(got_len, rlen)
+    g = comp.cpu().numpy()
+    for b in range(nb):
+        assert np.array_equal(g[b * B: b * B + rlen[b]], ref[b * B: b * B + rlen[b]]), b
+    # and back
+    plain = torch.empty(nb * B, dtype=torch.uint8, device="cuda")
+    cap = torch.full((nb,), B, dtype=torch.int32, device="cuda")
+    gpu.ctx.decompress_blocks(comp, off, olen, nb, plain, off, cap, cap, olen.clone(), st, None)
+    torch.cuda.synchronize()
+    assert int(st.abs().sum()) == 0 and torch.equal(plain, data)
+
+
+def test_mixed_entropy_frames_roundtrip_property(gpu):
+    """config-4 style: random / text / lowent blocks; encode -> decode is the identity, stored blocks
+    appear exactly for the random class."""
+    import torch
+    B, nb = 1 << 20, 48
+    data = W.mixed_blocks(nb, B, device="cuda")
+    s, _k = N.make_settings(block_size=B)
+    nframes = 6
+    per = nb // nframes * B
+    in_off = np.arange(nframes, dtype=np.uint64) * per
+    in_len = np.full(nframes, per, dtype=np.uint64)
+    bound = gpu.ctx.frame_bound(s, per)
+    out_off = np.arange(nframes, dtype=np.uint64) * ((bound + 255) // 256 * 256)
+    frames = torch.empty(int(out_off[-1]) + bound, dtype=torch.uint8, device="cuda")
+    flen, fst = gpu.ctx.frames_compress_device(data, in_off, in_len, frames, out_off, np.full(nframes, bound, np.uint64), s)
+    assert not fst.any()
+    back = torch.empty_like(data)
+    olen, st, det = gpu.ctx.frames_decompress_device(frames, out_off, flen, back, in_off, in_len)
+    assert not st.any() and (olen == in_len).all() and torch.equal(back, data)
+    f0 = frames[: int(flen[0])].cpu().numpy()
+    first_word = int.from_bytes(f0[7:11].tobytes(), "little")
+    assert first_word == (B | 0x80000000)                         # block 0 is random -> stored
+
+
+def test_streaming_xxh32_and_host_mirror(gpu, oracle):
+    import io
+    import lz_fear_b200 as L
+    L.raw.set_default_context(gpu.ctx)
+    data = W.text(300000, 77).numpy().tobytes()
+    assert gpu.ctx.xxh32(data) == oracle.xxh32(data)
+    out = io.BytesIO()
+    L.CompressionSettings.default().block_size(64 << 10).block_checksums(True).compress(io.BytesIO(data), out)
+    assert out.getvalue() == oracle.frame_compress(data, block_size=64 << 10, block_checksums=True)[1]
+    rd = L.LZ4FrameReader(io.BytesIO(out.getvalue()))
+    assert rd.block_size() == 64 << 10 and rd.frame_size() is None
+    assert rd.into_read().read_to_end() == data
+    assert L.decompress_frame(io.BytesIO(out.getvalue())) == data
+    buf = bytearray()
+    L.raw.decompress_raw(oracle.compress_block(data)[1], b"", buf, 1 << 30)
+    assert bytes(buf) == data
+    L.raw.set_default_context(None)

@@ -1,0 +1,140 @@
+"""Runs the REAL kernel + C-ABI sources (rust-lz-fear_b200/csrc) on the CPU SIMT emulator
+(tests/simt) and checks them bit-for-bit against the oracle.  Same checks as the `-m gpu` tier
+(tests/test_gpu_parity.py) at sizes the emulator finishes in seconds."""
+import numpy as np
+import pytest
+
+import parity
+from lz_fear_b200 import _native as N
+
+
+def _strings(vectors):
+    return [s.encode("latin-1") for v in vectors["roundtrip_strings"].values() for s in v]
+
+
+def test_raw_compress_matches_oracle(emu, oracle, vectors):
+    parity.check_raw_compress(emu, oracle, parity.sample_inputs() + _strings(vectors))
+
+
+def test_raw_compress_u16_table(emu, oracle, vectors):          # src/lib.rs:26-27 helper path
+    inputs = [b for b in parity.sample_inputs() + _strings(vectors) if len(b) <= 0xFFFF]
+    parity.check_raw_compress(emu, oracle, inputs, table=N.TABLE_U16)
+    st, _ = emu.ctx.raw_compress_into(bytes(70000), table=N.TABLE_U16)
+    assert st == N.PANIC                                        # assert at src/raw/compress/mod.rs:167
+
+
+def test_raw_compress_large_hashlog(emu, oracle):               # BASELINE config 5 extension
+    inputs = [b for b in parity.sample_inputs() if 1000 <= len(b) <= 100000][:6]
+    for hashlog in (13, 14, 16):
+        parity.check_raw_compress(emu, oracle, inputs, hashlog=hashlog)
+
+
+def test_decode_kats(emu, oracle, vectors):                     # src/raw/decompress.rs:153-175
+    blocks = [(bytes(k["input"]), None) for k in vectors["decode_kats"]]
+    parity.check_raw_decompress(emu, oracle, blocks)
+    st, out, n = emu.ctx.raw_decompress(bytes([0x11, 97, 1, 0, 0x22, 98, 99, 2, 0]))
+    assert (st, out) == (0, b"aaaaaabcbcbcbc")
+
+
+def test_raw_decompress_matches_oracle(emu, oracle):
+    blocks = []
+    for data in parity.sample_inputs():
+        st, comp = oracle.compress_block(data)
+        blocks.append((comp, len(data)))
+    parity.check_raw_decompress(emu, oracle, blocks)
+
+
+def test_raw_decompress_seq50(emu, oracle):
+    from lz_fear_b200 import workloads as W
+    comp, off, ln = W.seq50_blocks(4, seed=11)
+    c = comp.numpy()
+    blocks = [(c[int(o): int(o) + int(l)].tobytes(), 65536) for o, l in zip(off, ln)]
+    parity.check_raw_decompress(emu, oracle, blocks)
+
+
+def test_raw_decompress_malformed(emu, oracle):
+    """error precedence of SURVEY §8 row D1 on mutated blocks"""
+    base = [oracle.compress_block(d)[1] for d in parity.sample_inputs() if 20 <= len(d) <= 70000][:12]
+    blocks = []
+    for i, comp in enumerate(base):
+        for k in range(6):
+            blocks.append((parity.mutate(comp, 100 * i + k, k=1 + k % 3), None))
+    blocks += [(bytes([0x0F]), None), (bytes([0xF0]), None), (bytes([0xF0, 0xFF]), None), (bytes([0x00, 0x00, 0x00]), None),
+               (bytes([0x10, 65, 0x01]), None), (bytes([0x1F, 65, 1, 0, 0xFF]), None), (bytes([0x00, 1, 0]), None)]
+    parity.check_raw_decompress(emu, oracle, blocks)
+
+
+def test_raw_decompress_with_prefix(emu, oracle):
+    prefix = b"0123456789abcdef" * 8
+    comp = bytes([0x42, 120, 121, 122, 119, 20, 0, 0x00, 3, 0])      # lits "xyzw", match 6 @ off 20 -> reaches prefix
+    for lim in (6, 10, 1 << 20):
+        st, out, n = emu.ctx.raw_decompress(comp, prefix=prefix, out_limit=lim, cap=256)
+        assert (st, out, n) == oracle.decompress_raw(comp, prefix=prefix, out_limit=lim, cap=256)
+    st, out, n = emu.ctx.raw_decompress(comp, prefix=prefix[:10], out_limit=1 << 20, cap=256)
+    assert st == N.INVALID_DEDUP_OFFSET
+
+
+def test_batched_blocks(emu, oracle):
+    inputs = [b for b in parity.sample_inputs() if len(b) > 0]
+    parity.check_batched_blocks(emu, oracle, inputs)
+
+
+def test_frames_roundtrip_and_bytes(emu, oracle):
+    inputs = [b"", b"a", bytes(65536), parity.sample_inputs()[6], parity.sample_inputs()[7][:70001],
+              parity.sample_inputs()[5] * 30]
+    parity.check_frames(emu, oracle, inputs)
+    z = bytes(65536)                                               # BASELINE config 1 KAT
+    st, frame = emu.ctx.frame_compress(z)
+    assert st == 0 and len(frame) == 286 and frame[-4:] == bytes([0x1C, 0xE8, 0x64, 0x0F])
+
+
+def test_frame_settings_errors(emu, oracle):
+    data = b"x" * 1000
+    assert emu.ctx.frame_compress(data, block_size=12345)[0] == N.F_INVALID_BLOCK_SIZE
+    assert emu.ctx.frame_compress(data, block_size=16 << 20)[0] == N.F_PANIC
+    st, frame = emu.ctx.frame_compress(data, cap=10)
+    assert st == N.F_WRITE_ERROR == oracle.F_WRITE_ERROR
+    with pytest.raises(N.LzfCallError):
+        emu.ctx.frame_compress(data, independent_blocks=False)     # not on the GPU path yet: fails loudly
+
+
+def test_frame_decode_corpus(emu, oracle, corpora):              # fuzz/corpus/decode replay
+    blobs = [b for _, b in corpora["decode"]]
+    n_ok = parity.check_frame_decode_errors(emu, oracle, blobs[::3])
+    assert n_ok >= 0
+
+
+def test_frame_decode_mutations(emu, oracle):
+    data = parity.sample_inputs()[6] + parity.sample_inputs()[5]
+    frames = []
+    for kw in parity.FRAME_SETTINGS[1:5]:
+        rc, frame = oracle.frame_compress(data, **kw)
+        for k in range(12):
+            frames.append(parity.mutate(frame, hash(str(kw)) % 1000 + k, k=1 + k % 2))
+        frames += [frame[:n] for n in (0, 3, 6, 7, 10, 11, len(frame) - 5, len(frame) - 1)]
+    parity.check_frame_decode_errors(emu, oracle, frames)
+
+
+def test_short_and_empty_blocks_in_frame(emu, oracle):
+    import struct
+    hdr = bytes([0x04, 0x22, 0x4D, 0x18, 0x60, 0x40, 0x82])
+    a = bytes([0x30]) + b"abc"
+    big = oracle.compress_block(bytes(65536))[1]
+    frames = [
+        hdr + struct.pack("<I", 4) + a + struct.pack("<I", 1) + b"\x00" + struct.pack("<I", 4) + a + struct.pack("<I", 0),
+        hdr + struct.pack("<I", 4) + a + struct.pack("<I", len(big)) + big + struct.pack("<I", 4) + a + struct.pack("<I", 0),
+        hdr + struct.pack("<I", 3 | 0x80000000) + b"xyz" + struct.pack("<I", 4) + a + struct.pack("<I", 0),
+        hdr + struct.pack("<I", 70000) + bytes(70000),
+    ]
+    parity.check_frame_decode_errors(emu, oracle, frames)
+
+
+def test_streaming_xxh32(emu, oracle):
+    rng = np.random.default_rng(5)
+    data = rng.integers(0, 256, 100000, dtype=np.uint8).tobytes()
+    st = emu.ctx.xxh32_new()
+    pos = 0
+    for step in [0, 1, 3, 15, 16, 17, 31, 32, 1000, 4096, 5, 50000]:
+        emu.ctx.xxh32_update(st, data[pos: pos + step])
+        pos += step
+        assert emu.ctx.xxh32_finish(st) == oracle.xxh32(data[:pos])
