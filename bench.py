@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--no-compress", action="store_true", help="skip the config-3 compress section")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-xxh", action="store_true", help="experiment: skip the fused XXH32 epilogue")
     return ap.parse_args()
 
 
@@ -246,7 +247,7 @@ def main():
     plain_bytes = nb * BLOCK2
 
     def step_decompress():
-        ctx.decompress_blocks(comp, in_off, in_len, nb, plain, in_off, cap, cap, olen, st, xx, stream=stream)
+        ctx.decompress_blocks(comp, in_off, in_len, nb, plain, in_off, cap, cap, olen, st, None if args.no_xxh else xx, stream=stream)
 
     for _ in range(Wm):
         step_decompress()

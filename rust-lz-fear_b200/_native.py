@@ -103,7 +103,8 @@ def load_library(path=None):
     global _lib, _lib_path
     if path is None and _lib is not None:
         return _lib
-    path = path or _DEFAULT_LIB
+    # LZF_B200_LIB: explicit opt-in to another build of the SAME CUDA library (kernel tuning variants)
+    path = path or os.environ.get("LZF_B200_LIB") or _DEFAULT_LIB
     if not os.path.exists(path):
         raise NativeLibraryError(
             "%s not found: build it with `python rust-lz-fear_b200/build.py` (there is no CPU fallback)" % path)

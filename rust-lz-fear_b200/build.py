@@ -33,15 +33,20 @@ def up_to_date():
     return all(os.path.getmtime(d) <= t for d in _deps())
 
 
-def build(force=False, verbose=False):
-    if not force and up_to_date():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines/out: tuning variants (e.g. defines=["LZF_DEC_MINCTAS=4"], out="build/variant.so")."""
+    target = out or LIB
+    if not force and not defines and out is None and up_to_date():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
-          [os.path.join(CSRC, s) for s in SOURCES]
+    os.makedirs(os.path.dirname(os.path.abspath(target)), exist_ok=True)
+    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-o", os.path.abspath(target)] + [os.path.join(CSRC, s) for s in SOURCES]
     subprocess.check_call(cmd, cwd=CSRC)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None))

@@ -166,4 +166,43 @@ __device__ __forceinline__ void warp_copy(uint8_t* __restrict__ dst, const uint8
     if (lane < tail) dst[done + lane] = src[done + lane];
 }
 
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers ------------------------------
+// One elected lane arms the barrier with the byte count and issues the copy; every lane of the
+// warp then waits on the barrier's phase parity.  Sizes and both addresses are multiples of 16.
+#ifndef LZF_SIMT_EMU
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    // order earlier generic-proxy accesses of the destination before the async-proxy write
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) { return __reduce_max_sync(LZF_FULL_MASK, v); }
+#else
+// CPU SIMT test harness: the copy is synchronous, the barrier is always complete
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t) { *bar = 0; }
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t*) { memcpy(smem_dst, gmem_src, bytes); }
+__device__ __forceinline__ void bulk_prefetch_l2(const void*, uint32_t) {}
+__device__ __forceinline__ void mbar_wait(uint64_t*, uint32_t) { __syncwarp(); }   // the issuing lane has copied by then
+__device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) {
+    for (int s = 16; s; s >>= 1) { const uint32_t o = __shfl_xor_sync(LZF_FULL_MASK, v, s); v = o > v ? o : v; }
+    return v;
+}
+#endif
+
 }  // namespace lzf

@@ -5,18 +5,44 @@
 // optional `prefix`; stored blocks (bit 31 of the length word, src/framed/decompress.rs:217,
 // 249-251) are copied verbatim.  XXH32 of the decoded bytes is fused into the block epilogue.
 //
-// Mapping: a warp walks the sequence chain of its block.  The compressed stream is held in a
-// 128-byte register window (one aligned 32-bit word per lane, refilled with one coalesced load),
-// so tokens, offsets and short literal runs are served by warp shuffles instead of dependent
-// memory loads; long literal runs and stored blocks use 16-byte vector copies; matches are copied
-// lane-parallel with the sequential (overlapping) semantics of copy_overlapping
-// (src/raw/decompress.rs:80-138) preserved through modular source indexing.
+// Mapping (persistent warps, dynamic block queue):
+//   * the compressed stream is staged into a per-warp shared-memory window with TMA bulk copies
+//     (cp.async.bulk + mbarrier), the following window is prefetched into L2;
+//   * FAST PATH, up to 32 sequences per step: the warp walks the token chain in shared memory
+//     (the only serial part: one byte load + a few integer ops per sequence), lane k keeps the
+//     k-th sequence; a warp scan turns (literal length + match length) into output positions;
+//     every lane then copies its own literals and its own match.  Matches that read bytes another
+//     match of the same step still has to produce wait for it (round loop ordered by a ballot), so
+//     the sequential semantics of copy_overlapping (src/raw/decompress.rs:80-138) are preserved;
+//   * the step's output is assembled in a shared-memory staging ring and written to HBM with
+//     16-byte vector stores;
+//   * SLOW PATH, one sequence per step, warp-cooperative: anything with an LSIC length extension
+//     (long literal runs / long matches become 16-byte vectorised warp copies), sequences that
+//     touch the end of the block, every error and the out-of-capacity "dry" mode.
 #include "lzf_kernels.cuh"
 
 namespace lzf {
 
+#ifndef LZF_DEC_MINCTAS
+#define LZF_DEC_MINCTAS 5                  // resident CTAs per SM the register budget is tuned for (48 regs)
+#endif
+#ifndef LZF_DEC_WIN
+#define LZF_DEC_WIN 1024
+#endif
+constexpr int kDecodeWarpsPerCta = 8;
+constexpr uint32_t kWin = LZF_DEC_WIN;     // staged bytes of compressed stream per refill
+constexpr uint32_t kStage = 2048;          // output staging ring (power of two, > 32 * 32 + 16)
+constexpr uint32_t kStageMask = kStage - 1;
+constexpr uint32_t kFastSeqMax = 3 + 14;   // token + 14 literals + offset: no LSIC byte anywhere
 
-// 128-byte register window over the compressed stream.
+struct __align__(16) DecodeWarpSmem {
+    uint8_t win[kWin];
+    uint8_t stage[kStage];
+    uint64_t mbar;
+    uint64_t pad;
+};
+
+// 128-byte register window over the compressed stream (slow path).
 struct Window {
     const uint8_t* base;   // block start
     const uint8_t* end;    // block end
@@ -29,22 +55,15 @@ struct Window {
         const uint8_t* w = reinterpret_cast<const uint8_t*>(wa) + 4 * lane_id();
         reg = (w < end) ? __ldg(reinterpret_cast<const uint32_t*>(w)) : 0u;
     }
-    // true when bytes [pos, pos+need) are inside the window
     __device__ __forceinline__ bool covers(uint64_t pos, uint32_t need) const {
         const uintptr_t a = reinterpret_cast<uintptr_t>(base + pos);
         return a >= wa && a + need <= wa + 128;
     }
-    // up to 4 bytes at pos (caller guarantees covers(pos, 4) or that the excess is ignored)
     __device__ __forceinline__ uint32_t u32(uint64_t pos) const {
         const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(base + pos) - wa);
         const uint32_t lo = __shfl_sync(LZF_FULL_MASK, reg, a >> 2);
         const uint32_t hi = __shfl_sync(LZF_FULL_MASK, reg, (a >> 2) + 1);   // wraps mod 32: only used when covered
         return __funnelshift_r(lo, hi, (a & 3u) * 8u);
-    }
-    __device__ __forceinline__ uint32_t u8(uint64_t pos) const {
-        const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(base + pos) - wa);
-        const uint32_t w = __shfl_sync(LZF_FULL_MASK, reg, a >> 2);
-        return (w >> ((a & 3u) * 8u)) & 0xffu;
     }
 };
 
@@ -53,135 +72,311 @@ __device__ __forceinline__ uint8_t hist_byte(const uint8_t* out, const uint8_t* 
     return i >= 0 ? out[i] : prefix_end[i];
 }
 
-constexpr int kDecodeWarpsPerCta = 4;
+struct BlockState {
+    const uint8_t* in; uint64_t n;
+    uint8_t* out; uint64_t cap, limit, plen; const uint8_t* prefix_end;
+    uint64_t pos, olen;
+    int status; bool dry; bool finished;
+};
 
-__global__ void __launch_bounds__(kDecodeWarpsPerCta * 32)
-decode_blocks_kernel(DecodeArgs a) {
+// One sequence, warp-cooperative, exactly the reference's order of checks (decompress.rs:61-75).
+__device__ __forceinline__ void slow_sequence(BlockState& s) {
     const unsigned lane = lane_id();
-    const uint32_t b = blockIdx.x * kDecodeWarpsPerCta + (threadIdx.x >> 5);
-    if (b >= a.nblocks) return;
-
-    const uint32_t len_word = a.in_len[b];
-    const uint64_t n = len_word & ~LZF_INCOMPRESSIBLE;
-    const uint8_t* in = a.in + a.in_off[b];
-    uint8_t* out = a.out + a.out_off[b];
-    const uint64_t cap = a.out_cap[b];
-    const uint64_t limit = a.out_limit[b];
-    const uint64_t plen = a.prefix ? a.prefix_len[b] : 0;
-    const uint8_t* prefix_end = a.prefix ? a.prefix + a.prefix_off[b] + plen : nullptr;
-
-    int status = LZF_OK;
-    uint64_t olen = 0;
-
-    if (len_word & LZF_INCOMPRESSIBLE) {
-        // stored block: output.extend_from_slice(buf)   src/framed/decompress.rs:249-251
-        olen = n;
-        if (n <= cap) warp_copy(out, in, n);
-    } else {
-        Window win;
-        win.base = in;
-        win.end = in + n;
-        win.wa = 0;
-        win.reg = 0;
-        if (n) win.load(0);
-        uint64_t pos = 0;
-        bool dry = false;   // physical cap exceeded: keep parsing for exact error reporting, stop writing
-
-        while (pos < n) {                                                   // :61
-            if (!win.covers(pos, 4)) win.load(pos);
-            const uint32_t t4 = win.u32(pos);
-            const uint32_t token = t4 & 0xffu;
+    const uint8_t* in = s.in;
+    const uint64_t n = s.n;
+    uint8_t* out = s.out;
+    Window win;
+    win.base = in; win.end = in + n;
+    win.load(s.pos);
+    uint64_t pos = s.pos, olen = s.olen;
+    const uint32_t t4 = win.u32(pos);
+    const uint32_t token = t4 & 0xffu;
+    pos += 1;
+    uint64_t lit = token >> 4;
+    if (lit == 15) {                                                    // read_lsic :30-43
+        for (;;) {
+            if (pos >= n) { s.status = LZF_UNEXPECTED_END; s.pos = pos; return; }
+            const uint32_t more = __ldg(in + pos);
             pos += 1;
-            uint64_t lit = token >> 4;
-            if (lit == 15) {                                                // read_lsic :30-43
-                for (;;) {
-                    if (pos >= n) { status = LZF_UNEXPECTED_END; break; }
-                    const uint32_t more = __ldg(in + pos);
-                    pos += 1;
-                    lit += more;
-                    if (more != 0xffu) break;
-                }
-                if (status) break;
-            }
-            if (n - pos < lit) { status = LZF_UNEXPECTED_END; break; }      // :67 read_exact
-            if (lit) {
-                if (!dry && olen + lit > cap) dry = true;
-                if (!dry) {
-                    if (lit <= 32 && win.covers(pos, (uint32_t)lit)) {
-                        // literals straight out of the register window
-                        const uint32_t aoff = (uint32_t)(reinterpret_cast<uintptr_t>(in + pos) - win.wa) + lane;
-                        const uint32_t w = __shfl_sync(LZF_FULL_MASK, win.reg, aoff >> 2);
-                        if (lane < lit) out[olen + lane] = (uint8_t)(w >> ((aoff & 3u) * 8u));
-                    } else {
-                        warp_copy(out + olen, in + pos, lit);
-                    }
-                }
-                olen += lit;
-                pos += lit;
-            }
-            if (n - pos < 2) { pos = n; break; }                            // :70 (recent-std EOF behaviour)
-            if (!win.covers(pos, 4)) win.load(pos);
-            const uint32_t o4 = win.u32(pos);
-            const uint32_t offset = o4 & 0xffffu;
-            pos += 2;
-            uint64_t mlen = token & 0xfu;
-            if (mlen == 15) {                                               // :71 read_lsic
-                for (;;) {
-                    if (pos >= n) { status = LZF_UNEXPECTED_END; break; }
-                    const uint32_t more = __ldg(in + pos);
-                    pos += 1;
-                    mlen += more;
-                    if (more != 0xffu) break;
-                }
-                if (status) break;
-            }
-            mlen += 4;
-            if (olen + mlen > limit) { status = LZF_MEMORY_LIMIT_EXCEEDED; break; }      // :72-74
-            if (offset == 0) { status = LZF_ZERO_DEDUP_OFFSET; break; }                  // :83
-            if (offset > olen && offset - olen > plen) { status = LZF_INVALID_DEDUP_OFFSET; break; }   // :84-89
-            if (!dry && olen + mlen > cap) dry = true;
-            if (!dry) {
-                __syncwarp();   // literal bytes just stored by other lanes are match history
-                uint8_t* dst = out + olen;
-                const int64_t src0 = (int64_t)olen - (int64_t)offset;
-                if (offset >= 32) {
-                    // each 32-byte step only reads bytes at least 32 behind its own writes
-                    for (uint64_t k0 = 0; k0 < mlen; k0 += 32) {
-                        const uint64_t k = k0 + lane;
-                        if (k < mlen) dst[k] = hist_byte(out, prefix_end, src0 + (int64_t)k);
-                        __syncwarp();
-                    }
-                } else {
-                    // overlapping run: out[olen+k] = hist[olen-offset + (k mod offset)]
-                    for (uint64_t k0 = 0; k0 < mlen; k0 += 32) {
-                        const uint64_t k = k0 + lane;
-                        if (k < mlen) dst[k] = hist_byte(out, prefix_end, src0 + (int64_t)(k % offset));
-                    }
-                }
-            }
-            olen += mlen;
-            __syncwarp();
+            lit += more;
+            if (more != 0xffu) break;
         }
     }
-    if (status == LZF_OK && olen > cap) status = LZF_OUTPUT_CAP;
-    __syncwarp();
-    if (a.xxh_plain) {
-        uint32_t h = 0;
-        if (status == LZF_OK) h = warp_xxh32(out, olen);
-        if (lane == 0) a.xxh_plain[b] = h;
+    if (n - pos < lit) { s.status = LZF_UNEXPECTED_END; s.pos = pos; return; }   // :67 read_exact
+    if (lit) {
+        if (!s.dry && olen + lit > s.cap) s.dry = true;
+        if (!s.dry) warp_copy(out + olen, in + pos, lit);
+        olen += lit;
+        pos += lit;
     }
-    if (lane == 0) {
-        a.out_len[b] = (uint32_t)(olen > 0xffffffffull ? 0xffffffffull : olen);
-        a.status[b] = status;
+    s.olen = olen;
+    if (n - pos < 2) { s.pos = n; s.finished = true; return; }          // :70 (recent-std EOF behaviour)
+    if (!win.covers(pos, 4)) win.load(pos);
+    const uint32_t offset = win.u32(pos) & 0xffffu;
+    pos += 2;
+    uint64_t mlen = token & 0xfu;
+    if (mlen == 15) {                                                   // :71 read_lsic
+        for (;;) {
+            if (pos >= n) { s.status = LZF_UNEXPECTED_END; s.pos = pos; return; }
+            const uint32_t more = __ldg(in + pos);
+            pos += 1;
+            mlen += more;
+            if (more != 0xffu) break;
+        }
+    }
+    mlen += 4;
+    s.pos = pos;
+    if (olen + mlen > s.limit) { s.status = LZF_MEMORY_LIMIT_EXCEEDED; return; }          // :72-74
+    if (offset == 0) { s.status = LZF_ZERO_DEDUP_OFFSET; return; }                        // :83
+    if (offset > olen && offset - olen > s.plen) { s.status = LZF_INVALID_DEDUP_OFFSET; return; }   // :84-89
+    if (!s.dry && olen + mlen > s.cap) s.dry = true;
+    if (!s.dry) {
+        __syncwarp();   // literal bytes just stored by other lanes are match history
+        uint8_t* dst = out + olen;
+        const int64_t src0 = (int64_t)olen - (int64_t)offset;
+        if (offset >= 32) {
+            if (offset >= mlen && src0 >= 0 && mlen >= 64) {
+                warp_copy(dst, out + src0, mlen);                       // non-overlapping: vectorised
+            } else {
+                // each 32-byte step only reads bytes at least 32 behind its own writes
+                for (uint64_t k0 = 0; k0 < mlen; k0 += 32) {
+                    const uint64_t k = k0 + lane;
+                    if (k < mlen) dst[k] = hist_byte(out, s.prefix_end, src0 + (int64_t)k);
+                    __syncwarp();
+                }
+            }
+        } else {
+            // overlapping run: out[olen+k] = hist[olen-offset + (k mod offset)]
+            for (uint64_t k0 = 0; k0 < mlen; k0 += 32) {
+                const uint64_t k = k0 + lane;
+                if (k < mlen) dst[k] = hist_byte(out, s.prefix_end, src0 + (int64_t)(k % offset));
+            }
+        }
+    }
+    s.olen = olen + mlen;
+    __syncwarp();
+}
+
+// Writes staged output [from, upto) to global memory.  `whole` = false: upto is rounded down to a
+// 16-byte boundary of the destination address (the remainder stays staged); returns the new
+// flushed position.
+__device__ __forceinline__ uint32_t flush_stage(const uint8_t* stage, uint8_t* out, uint32_t sbase, uint32_t from,
+                                                uint32_t upto, bool whole) {
+    const unsigned lane = lane_id();
+    const uintptr_t oa = reinterpret_cast<uintptr_t>(out);
+    if (!whole) {
+        const uint32_t r = (uint32_t)((oa + upto) & 15u);
+        if (upto - from < r) return from;
+        upto -= r;
+    }
+    if (upto <= from) return from;
+    uint32_t a = from;
+    uint32_t head = (uint32_t)((16u - ((oa + a) & 15u)) & 15u);
+    if (head > upto - a) head = upto - a;
+    if (lane < head) out[a + lane] = stage[(sbase + a + lane) & kStageMask];
+    a += head;
+    const uint32_t nvec = (upto - a) >> 4;
+    for (uint32_t v = lane; v < nvec; v += 32) {
+        const uint32_t p = a + 16 * v;
+        *reinterpret_cast<uint4*>(out + p) = *reinterpret_cast<const uint4*>(stage + ((sbase + p) & kStageMask));
+    }
+    a += nvec * 16;
+    const uint32_t tail = upto - a;     // only when `whole`
+    if (lane < tail) out[a + lane] = stage[(sbase + a + lane) & kStageMask];
+    return upto;
+}
+
+__global__ void __launch_bounds__(kDecodeWarpsPerCta * 32, LZF_DEC_MINCTAS)
+decode_blocks_kernel(DecodeArgs a) {
+    LZF_DYN_SMEM(smem_raw);
+    const unsigned lane = lane_id();
+    DecodeWarpSmem& sm = reinterpret_cast<DecodeWarpSmem*>(smem_raw)[threadIdx.x >> 5];
+    if (lane == 0) mbar_init(&sm.mbar, 1);
+    __syncwarp();
+    uint32_t phase = 0;
+
+    for (;;) {
+        uint32_t b = 0;
+        if (lane == 0) b = atomicAdd(a.work_counter, 1u);
+        b = __shfl_sync(LZF_FULL_MASK, b, 0);
+        if (b >= a.nblocks) break;
+
+        const uint32_t len_word = a.in_len[b];
+        BlockState s;
+        s.n = len_word & ~LZF_INCOMPRESSIBLE;
+        s.in = a.in + a.in_off[b];
+        s.out = a.out + a.out_off[b];
+        s.cap = a.out_cap[b];
+        s.limit = a.out_limit[b];
+        s.plen = a.prefix ? a.prefix_len[b] : 0;
+        s.prefix_end = a.prefix ? a.prefix + a.prefix_off[b] + s.plen : nullptr;
+        s.pos = 0; s.olen = 0; s.status = LZF_OK; s.dry = false; s.finished = false;
+
+        if (len_word & LZF_INCOMPRESSIBLE) {
+            // stored block: output.extend_from_slice(buf)   src/framed/decompress.rs:249-251
+            s.olen = s.n;
+            if (s.n <= s.cap) warp_copy(s.out, s.in, s.n);
+        } else {
+            // positions q are relative to the 16-byte aligned address at or below the block start
+            const uintptr_t in_addr = reinterpret_cast<uintptr_t>(s.in);
+            const uintptr_t a0 = in_addr & ~uintptr_t(15);
+            const uint32_t q0 = (uint32_t)(in_addr - a0);
+            const uint64_t qn = q0 + s.n;
+            const uint64_t qn16 = (qn + 15) & ~uint64_t(15);
+            uint64_t wq = 0;          // window start (multiple of 16), relative to a0
+            uint32_t wlen = 0;        // staged bytes
+            const uint32_t sbase = (uint32_t)(reinterpret_cast<uintptr_t>(s.out) & 15u);
+            uint32_t flushed = 0;     // output below this position is in global memory; [flushed, olen) is staged
+            // the fast path works in 32-bit output positions and never exceeds this bound
+            const uint64_t bound64 = s.cap < s.limit ? s.cap : s.limit;
+            const uint32_t bound = bound64 > 0xfffff000ull ? 0xfffff000u : (uint32_t)bound64;
+
+            while (s.pos < s.n && s.status == LZF_OK && !s.finished) {
+                const uint64_t q = q0 + s.pos;
+                // ---- (re)fill the staged window
+                if (q < wq || q + kFastSeqMax > wq + wlen) {
+                    const uint64_t want = q & ~uint64_t(15);
+                    const uint64_t avail = qn16 - want;
+                    const uint32_t nbytes = avail < kWin ? (uint32_t)avail : kWin;
+                    if (want != wq || nbytes != wlen) {
+                        __syncwarp();
+                        if (lane == 0) {
+                            bulk_load(sm.win, reinterpret_cast<const uint8_t*>(a0) + want, nbytes, &sm.mbar);
+                            if (avail > kWin) {
+                                const uint64_t more = avail - kWin;
+                                bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(a0) + want + kWin, more < kWin ? (uint32_t)more : kWin);
+                            }
+                        }
+                        mbar_wait(&sm.mbar, phase);
+                        phase ^= 1u;
+                        wq = want;
+                        wlen = nbytes;
+                    }
+                }
+                const uint64_t wend64 = (wq + wlen) < qn ? (wq + wlen) : qn;
+                // window-relative positions from here on
+                const uint32_t wend = (uint32_t)(wend64 - wq);
+                uint32_t p = (uint32_t)(q - wq);
+
+                // ---- walk: up to 32 LSIC-free sequences that lie completely inside the window
+                uint32_t cnt = 0, my_p = 0;
+                if (s.olen + 32u * 32u <= bound) {
+#pragma unroll
+                    for (int k = 0; k < 32; k++) {
+                        if (p + 3 > wend) break;
+                        const uint32_t tok = sm.win[p];
+                        const uint32_t lit = tok >> 4;
+                        const uint32_t e = p + 3 + lit;
+                        if (lit == 15u || (tok & 15u) == 15u || e > wend) break;
+                        if (lane == (unsigned)k) my_p = p;
+                        p = e;
+                        cnt = k + 1;
+                    }
+                }
+                // ---- per-lane decode of the sequence headers, output positions by warp scan
+                uint32_t lit = 0, ml = 0, off = 1, tot = 0;
+                if (lane < cnt) {
+                    const uint32_t tok = sm.win[my_p];
+                    lit = tok >> 4;
+                    ml = (tok & 15u) + 4u;
+                    off = (uint32_t)sm.win[my_p + 1 + lit] | ((uint32_t)sm.win[my_p + 2 + lit] << 8);
+                    tot = lit + ml;
+                }
+                uint32_t inc = tot;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(LZF_FULL_MASK, inc, d);
+                    if (lane >= (unsigned)d) inc += t;
+                }
+                const uint32_t olen0 = (uint32_t)s.olen;
+                const uint32_t o_k = olen0 + inc - tot;                       // output position of my literals
+                const uint32_t dstp = o_k + lit;                               // ... and of my match
+                // offsets must be non-zero and inside prefix ++ output (decompress.rs:83-89); anything
+                // else is replayed by the slow path, which reports the error exactly like the reference
+                const bool bad = lane < cnt && (off == 0u || (uint64_t)off > (uint64_t)dstp + s.plen);
+                const uint32_t fb = __ballot_sync(LZF_FULL_MASK, bad);
+                if (fb) cnt = min(cnt, (uint32_t)(__ffs(fb) - 1));
+                if (cnt == 0) {
+                    flushed = flush_stage(sm.stage, s.out, sbase, flushed, (uint32_t)s.olen, true);
+                    __syncwarp();
+                    slow_sequence(s);
+                    flushed = (uint32_t)s.olen;
+                    continue;
+                }
+                const bool act = lane < cnt;
+                const uint32_t out_end = __shfl_sync(LZF_FULL_MASK, o_k + tot, cnt - 1);
+                const uint32_t in_end = __shfl_sync(LZF_FULL_MASK, my_p + 3 + lit, cnt - 1);
+
+                // ---- literals: every lane copies its own run into the staging ring
+                if (act) {
+                    const uint8_t* src = sm.win + my_p + 1;
+                    const uint32_t d = sbase + o_k;
+                    for (uint32_t i = 0; i < lit; i++) sm.stage[(d + i) & kStageMask] = src[i];
+                }
+                __syncwarp();
+
+                // ---- matches: a lane may go once everything its source range needs is complete
+                const int64_t srcp = (int64_t)dstp - (int64_t)off;
+                uint32_t pending = __ballot_sync(LZF_FULL_MASK, act);
+                while (pending) {
+                    const uint32_t first = __ffs(pending) - 1;
+                    const uint32_t dst_first = __shfl_sync(LZF_FULL_MASK, dstp, first);
+                    const bool ready = ((pending >> lane) & 1u) && (lane == first || srcp + (int64_t)ml <= (int64_t)dst_first);
+                    if (ready) {
+                        const uint32_t d = sbase + dstp;
+                        if (srcp >= (int64_t)flushed) {
+                            const uint32_t sp = sbase + (uint32_t)srcp;           // staged -> staged (in order: overlap-safe)
+                            for (uint32_t i = 0; i < ml; i++) sm.stage[(d + i) & kStageMask] = sm.stage[(sp + i) & kStageMask];
+                        } else if (srcp >= 0 && srcp + (int64_t)ml <= (int64_t)flushed) {
+                            const uint8_t* g = s.out + srcp;                      // flushed history -> staged
+                            for (uint32_t i = 0; i < ml; i++) sm.stage[(d + i) & kStageMask] = g[i];
+                        } else {
+                            for (uint32_t i = 0; i < ml; i++) {                   // straddles the flush point or the prefix
+                                const int64_t x = srcp + i;
+                                sm.stage[(d + i) & kStageMask] =
+                                    x >= (int64_t)flushed ? sm.stage[(sbase + (uint32_t)x) & kStageMask] : hist_byte(s.out, s.prefix_end, x);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    pending &= ~__ballot_sync(LZF_FULL_MASK, ready);
+                }
+                s.olen = out_end;
+                s.pos += in_end - (uint32_t)(q - wq);
+                flushed = flush_stage(sm.stage, s.out, sbase, flushed, out_end, false);
+                __syncwarp();
+            }
+            flushed = flush_stage(sm.stage, s.out, sbase, flushed, (uint32_t)s.olen, true);
+        }
+        if (s.status == LZF_OK && s.olen > s.cap) s.status = LZF_OUTPUT_CAP;
+        __syncwarp();
+        if (a.xxh_plain) {
+            uint32_t h = 0;
+            if (s.status == LZF_OK) h = warp_xxh32(s.out, s.olen);
+            if (lane == 0) a.xxh_plain[b] = h;
+        }
+        if (lane == 0) {
+            a.out_len[b] = (uint32_t)(s.olen > 0xffffffffull ? 0xffffffffull : s.olen);
+            a.status[b] = s.status;
+        }
     }
 }
 
 }  // namespace lzf
 
 extern "C" int lzf_launch_decode(const lzf::DecodeArgs* args, int num_sms, cudaStream_t stream) {
-    (void)num_sms;
+    using namespace lzf;
     if (args->nblocks == 0) return 0;
-    const unsigned grid = (args->nblocks + lzf::kDecodeWarpsPerCta - 1) / lzf::kDecodeWarpsPerCta;
-    LZF_LAUNCH(lzf::decode_blocks_kernel, grid, lzf::kDecodeWarpsPerCta * 32, 0, stream, *args);
+    const size_t dyn = sizeof(DecodeWarpSmem) * kDecodeWarpsPerCta;
+    cudaError_t e = cudaFuncSetAttribute(decode_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess) return (int)e;
+    int ctas_per_sm = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, decode_blocks_kernel, kDecodeWarpsPerCta * 32, dyn);
+    if (e != cudaSuccess) return (int)e;
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    unsigned grid = (unsigned)(num_sms * ctas_per_sm);
+    const unsigned need = (args->nblocks + kDecodeWarpsPerCta - 1) / kDecodeWarpsPerCta;
+    if (grid > need) grid = need;
+    LZF_LAUNCH(decode_blocks_kernel, grid, kDecodeWarpsPerCta * 32, dyn, stream, *args);
     return (int)cudaGetLastError();
 }

@@ -294,7 +294,7 @@ class LZ4FrameIoReader:
             del self.buffer[:]
             self.frame_reader.decode_block(self.buffer, self.dictionary)
             self.bytes_taken = 0
-        return memoryview(self.buffer)[self.bytes_taken:]
+        return bytes(self.buffer[self.bytes_taken:])
 
     def consume(self, amt):
         self.bytes_taken += amt
@@ -305,9 +305,8 @@ class LZ4FrameIoReader:
             return self.read_to_end()
         mybuf = self.fill_buf()
         take = min(len(mybuf), n)
-        out = bytes(mybuf[:take])
         self.consume(take)
-        return out
+        return mybuf[:take]
 
     def read_to_end(self):
         """std::io::Read::read_to_end: stops at the first read() that returns 0 bytes."""

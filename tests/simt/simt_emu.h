@@ -16,6 +16,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <ucontext.h>
+#include <execinfo.h>
 
 #include <algorithm>
 #include <functional>
@@ -128,8 +129,14 @@ inline uint64_t collective(Op op, uint64_t value, uint32_t arg) {
     int live = 0;
     for (int l = 0; l < kWarp; l++) if (base + l < (int)g.fibres.size() && !g.fibres[base + l].done) live++;
     if (live != kWarp) { fprintf(stderr, "simt: collective with %d live lanes (partial warps unsupported)\n", live); abort(); }
+    static const bool trace = getenv("SIMT_TRACE") != nullptr;
+    if (trace) { void* bt[4]; backtrace(bt, 4); fprintf(stderr, "T warp %d lane %d op %d val %llu\n", me / kWarp, lane, (int)op, (unsigned long long)value); }
     if (w.arrived == 0) w.op = (int)op;
-    else if (w.op != (int)op) { fprintf(stderr, "simt: divergent collectives in one warp (%d vs %d)\n", w.op, (int)op); abort(); }
+    else if (w.op != (int)op) {
+        fprintf(stderr, "simt: divergent collectives in one warp (%d vs %d) at lane %d\n", w.op, (int)op, lane);
+        void* bt[16]; const int nbt = backtrace(bt, 16); backtrace_symbols_fd(bt, nbt, 2);
+        abort();
+    }
     w.in[lane] = value;
     w.arg[lane] = arg;   // per-lane argument (shfl source lane etc.)
     const uint32_t gen = w.generation;
