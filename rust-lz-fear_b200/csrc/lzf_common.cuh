@@ -122,6 +122,128 @@ __device__ __forceinline__ uint32_t warp_xxh32(const uint8_t* p, size_t n) {
     return __shfl_sync(LZF_FULL_MASK, h, 0);
 }
 
+// XXH32(seed 0) of EIGHT byte ranges at once: lane = 4 * j + a hashes accumulator a of range j
+// (pointer/length are per lane group; a group with len 0 still yields XXH32("")).  The four
+// accumulator chains of one range are inherently serial, so a single range can only ever keep
+// 4 lanes busy; packing 8 independent ranges (blocks / frames) into one warp fills all 32.
+// Returns the hash of range j in all four lanes of group j.
+__device__ __forceinline__ uint32_t warp_xxh32_x8(const uint8_t* p, uint64_t n) {
+    const unsigned lane = lane_id();
+    const unsigned a = lane & 3u;
+    const uint64_t nstripes = n >> 4;
+    uint32_t acc = xxh32_seed_acc(a);
+    {
+        const uint8_t* q = p + 4 * a;
+        uint64_t s = 0;
+        if ((reinterpret_cast<uintptr_t>(p) & 3u) == 0) {
+            const uint32_t* qw = reinterpret_cast<const uint32_t*>(q);
+            for (; s + 8 <= nstripes; s += 8) {
+                uint32_t x[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) x[i] = qw[(s + i) * 4];
+#pragma unroll
+                for (int i = 0; i < 8; i++) acc = xxh_round(acc, x[i]);
+            }
+            for (; s < nstripes; s++) acc = xxh_round(acc, qw[s * 4]);
+        } else {
+            for (; s < nstripes; s++) acc = xxh_round(acc, ld_u32_unaligned(q + s * 16));
+        }
+    }
+    const unsigned g = lane & ~3u;
+    const uint32_t a0 = __shfl_sync(LZF_FULL_MASK, acc, g);
+    const uint32_t a1 = __shfl_sync(LZF_FULL_MASK, acc, g + 1);
+    const uint32_t a2 = __shfl_sync(LZF_FULL_MASK, acc, g + 2);
+    const uint32_t a3 = __shfl_sync(LZF_FULL_MASK, acc, g + 3);
+    uint32_t h = 0;
+    if (a == 0) {
+        if (n >= 16) h = rotl32(a0, 1) + rotl32(a1, 7) + rotl32(a2, 12) + rotl32(a3, 18);
+        else h = XP5;
+        h += (uint32_t)n;
+        const uint8_t* t = p + (nstripes << 4);
+        unsigned rem = (unsigned)(n & 15);
+        while (rem >= 4) {
+            uint32_t x = uint32_t(t[0]) | (uint32_t(t[1]) << 8) | (uint32_t(t[2]) << 16) | (uint32_t(t[3]) << 24);
+            h = rotl32(h + x * XP3, 17) * XP4;
+            t += 4; rem -= 4;
+        }
+        while (rem) { h = rotl32(h + uint32_t(*t) * XP5, 11) * XP1; t++; rem--; }
+        h ^= h >> 15; h *= XP2;
+        h ^= h >> 13; h *= XP3;
+        h ^= h >> 16;
+    }
+    return __shfl_sync(LZF_FULL_MASK, h, g);
+}
+
+// ---- per-CTA queue of finished blocks whose XXH32 is still owed -------------------------------
+// A warp that finishes a block pushes (pointer, length, destination slot); the warp that pushes
+// the 8th entry of a group hashes the whole group with warp_xxh32_x8; the last warp to leave the
+// CTA hashes the remainder.  Keeps the checksum fused in the block kernel at 1/8 of the issue cost.
+#ifdef LZF_SIMT_EMU
+__device__ __forceinline__ void spin_pause() { simt::yield(); }
+#else
+__device__ __forceinline__ void spin_pause() { __nanosleep(32); }
+#endif
+
+constexpr uint32_t kHashRing = 64;     // entries; a power of two, multiple of 8
+struct HashEntry { const uint8_t* p; uint64_t n; uint32_t* dst; uint32_t pad; };
+struct HashQueue {
+    uint32_t count;                    // tickets handed out
+    uint32_t warps_done;
+    volatile uint32_t ready[kHashRing];   // ticket + 1 once the entry is written
+    HashEntry e[kHashRing];
+};
+
+__device__ __forceinline__ void hash_queue_init(HashQueue* q) {
+    if (threadIdx.x == 0) { q->count = 0; q->warps_done = 0; }
+    for (uint32_t i = threadIdx.x; i < kHashRing; i += blockDim.x) q->ready[i] = 0;
+    __syncthreads();
+}
+
+// hashes tickets [first, first + cnt), cnt <= 8
+__device__ __forceinline__ void hash_queue_run(HashQueue* q, uint32_t first, uint32_t cnt) {
+    const unsigned lane = lane_id();
+    const uint32_t j = lane >> 2;
+    const uint8_t* p = nullptr; uint64_t n = 0; uint32_t* dst = nullptr;
+    if (j < cnt) {
+        const uint32_t slot = (first + j) & (kHashRing - 1);
+        while (q->ready[slot] != first + j + 1) spin_pause();
+        __threadfence_block();
+        p = q->e[slot].p; n = q->e[slot].n; dst = q->e[slot].dst;
+    }
+    __syncwarp();                                          // every lane has seen its flag and copied its entry
+    if (j < cnt && (lane & 3u) == 0) q->ready[(first + j) & (kHashRing - 1)] = 0;   // slot may be reused
+    const uint32_t h = warp_xxh32_x8(p, n);
+    if (j < cnt && (lane & 3u) == 0 && dst) *dst = h;
+}
+
+// warp-uniform call; `dst` == nullptr entries are skipped by the caller
+__device__ __forceinline__ void hash_queue_push(HashQueue* q, const uint8_t* p, uint64_t n, uint32_t* dst) {
+    const unsigned lane = lane_id();
+    uint32_t t = 0;
+    if (lane == 0) {
+        t = atomicAdd(&q->count, 1u);
+        const uint32_t slot = t & (kHashRing - 1);
+        // a slot is reused only after its previous occupant (ticket t - kHashRing) has been consumed
+        while (q->ready[slot] != 0) spin_pause();
+        q->e[slot].p = p; q->e[slot].n = n; q->e[slot].dst = dst;
+        __threadfence_block();
+        q->ready[slot] = t + 1;
+    }
+    t = __shfl_sync(LZF_FULL_MASK, t, 0);
+    if ((t & 7u) == 7u) hash_queue_run(q, t - 7u, 8u);
+}
+
+// called once per warp when it leaves the kernel's work loop
+__device__ __forceinline__ void hash_queue_finish(HashQueue* q, uint32_t nwarps) {
+    const unsigned lane = lane_id();
+    uint32_t d = 0, total = 0;
+    __syncwarp();
+    if (lane == 0) { __threadfence_block(); d = atomicAdd(&q->warps_done, 1u); total = *(volatile uint32_t*)&q->count; }
+    d = __shfl_sync(LZF_FULL_MASK, d, 0);
+    total = __shfl_sync(LZF_FULL_MASK, total, 0);
+    if (d == nwarps - 1 && (total & 7u)) hash_queue_run(q, total & ~7u, total & 7u);
+}
+
 // ---- warp-wide byte copy, non-overlapping, any alignment -----------------------------------
 // Copies n bytes src -> dst.  Short runs go byte-per-lane; long runs align the destination to
 // 16 bytes and move one uint4 per lane per step, re-aligning the source with funnel shifts.

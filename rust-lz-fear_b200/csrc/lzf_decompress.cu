@@ -189,10 +189,11 @@ __device__ __forceinline__ uint32_t flush_stage(const uint8_t* stage, uint8_t* o
 __global__ void __launch_bounds__(kDecodeWarpsPerCta * 32, LZF_DEC_MINCTAS)
 decode_blocks_kernel(DecodeArgs a) {
     LZF_DYN_SMEM(smem_raw);
+    __shared__ HashQueue hashq;
     const unsigned lane = lane_id();
     DecodeWarpSmem& sm = reinterpret_cast<DecodeWarpSmem*>(smem_raw)[threadIdx.x >> 5];
     if (lane == 0) mbar_init(&sm.mbar, 1);
-    __syncwarp();
+    hash_queue_init(&hashq);
     uint32_t phase = 0;
 
     for (;;) {
@@ -350,16 +351,17 @@ decode_blocks_kernel(DecodeArgs a) {
         }
         if (s.status == LZF_OK && s.olen > s.cap) s.status = LZF_OUTPUT_CAP;
         __syncwarp();
-        if (a.xxh_plain) {
-            uint32_t h = 0;
-            if (s.status == LZF_OK) h = warp_xxh32(s.out, s.olen);
-            if (lane == 0) a.xxh_plain[b] = h;
-        }
         if (lane == 0) {
             a.out_len[b] = (uint32_t)(s.olen > 0xffffffffull ? 0xffffffffull : s.olen);
             a.status[b] = s.status;
         }
+        if (a.xxh_plain) {
+            // XXH32 of the decoded bytes: queued so that 8 blocks are hashed per warp pass
+            if (s.status == LZF_OK) hash_queue_push(&hashq, s.out, s.olen, a.xxh_plain + b);
+            else if (lane == 0) a.xxh_plain[b] = 0;
+        }
     }
+    hash_queue_finish(&hashq, kDecodeWarpsPerCta);
 }
 
 }  // namespace lzf

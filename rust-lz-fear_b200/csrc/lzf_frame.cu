@@ -10,14 +10,16 @@
 namespace lzf {
 
 // ------------------------------------------------------------------------------------------
-// XXH32 of ranges: one warp per range
+// XXH32 of ranges: 8 ranges per warp (4 lanes = the 4 accumulator chains of one range)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 xxh32_ranges_kernel(const uint8_t* data, const uint64_t* off, const uint64_t* len, uint32_t nranges, uint32_t* hash) {
-    const uint32_t r = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (r >= nranges) return;
-    const uint32_t h = warp_xxh32(data + off[r], len[r]);
-    if (lane_id() == 0) hash[r] = h;
+    const uint32_t warp = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const unsigned lane = lane_id();
+    const uint32_t r = warp * 8 + (lane >> 2);
+    const bool valid = r < nranges;
+    const uint32_t h = warp_xxh32_x8(valid ? data + off[r] : nullptr, valid ? len[r] : 0);
+    if (valid && (lane & 3u) == 0) hash[r] = h;
 }
 
 // Stripe phase only, one warp, carrying a running state: acc[0..4) in/out (streaming content
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(64) frame_walk_kernel(WalkArgs a) {
 extern "C" int lzf_launch_xxh32_ranges(const uint8_t* data, const uint64_t* off, const uint64_t* len,
                                        uint32_t nranges, uint32_t* hash, cudaStream_t s) {
     if (!nranges) return 0;
-    LZF_LAUNCH(lzf::xxh32_ranges_kernel, (nranges + 3) / 4, 128, 0, s, data, off, len, nranges, hash);
+    LZF_LAUNCH(lzf::xxh32_ranges_kernel, (nranges + 31) / 32, 128, 0, s, data, off, len, nranges, hash);
     return (int)cudaGetLastError();
 }
 extern "C" int lzf_launch_xxh32_stripes(const uint8_t* data, uint64_t nstripes, uint32_t* acc, cudaStream_t s) {

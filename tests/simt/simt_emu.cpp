@@ -51,7 +51,16 @@ void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, std::function<void()> 
                 if (g.fibres[t].done) remaining--;
             }
             if (g.collectives + g.bar_generation == before && remaining == rem_before) {
-                if (++idle_rounds > 4) { fprintf(stderr, "simt: deadlock (lanes waiting on a collective that never completes)\n"); abort(); }
+                if (++idle_rounds > 4) {
+                    fprintf(stderr, "simt: deadlock (lanes waiting on a collective that never completes)\n");
+                    for (size_t w = 0; w < g.warps.size(); w++) {
+                        unsigned live = 0;
+                        for (int l = 0; l < kWarp; l++) live += !g.fibres[w * kWarp + l].done;
+                        fprintf(stderr, "  warp %zu: live %u, pending op %d with %u arrivals; cta barrier arrivals %u\n", w, live,
+                                g.warps[w].op, g.warps[w].arrived, g.bar_arrived);
+                    }
+                    abort();
+                }
             } else idle_rounds = 0;
         }
         g.cur = -1;

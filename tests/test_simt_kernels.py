@@ -138,3 +138,59 @@ def test_streaming_xxh32(emu, oracle):
         emu.ctx.xxh32_update(st, data[pos: pos + step])
         pos += step
         assert emu.ctx.xxh32_finish(st) == oracle.xxh32(data[:pos])
+
+
+def test_batched_frames_pipeline_and_hash_queue(simt_lib_path, oracle, monkeypatch):
+    """Many frames through the host-buffer batch calls with tiny pipeline chunks (several chunks per
+    call, all three slots in rotation) on a 1-SM device (one CTA: the XXH32 queue wraps its ring)."""
+    from lz_fear_b200 import _native
+    from lz_fear_b200 import workloads as W
+    monkeypatch.setenv("LZF_B200_CHUNK_BYTES", "20000")
+    monkeypatch.setenv("SIMT_NUM_SMS", "1")
+    saved = (_native._lib, _native._lib_path)
+    _native.load_library(simt_lib_path)
+    ctx = _native.Context(0)
+    try:
+        rng = np.random.default_rng(3)
+        datas = []
+        for i in range(90):
+            n = int(rng.integers(0, 9000))
+            kind = i % 3
+            datas.append(W.text(n, i).numpy().tobytes() if kind == 0 else
+                         W.lowent(n, i).numpy().tobytes() if kind == 1 else W.random_bytes(n, i).numpy().tobytes())
+        s, _k = _native.make_settings(block_size=64 << 10, block_checksums=True)
+        in_len = np.array([len(d) for d in datas], dtype=np.uint64)
+        in_off = np.zeros(len(datas), dtype=np.uint64); in_off[1:] = np.cumsum(in_len)[:-1]
+        inp = np.frombuffer(b"".join(datas), dtype=np.uint8)
+        caps = np.array([ctx.frame_bound(s, int(n)) for n in in_len], dtype=np.uint64)
+        out_off = np.zeros(len(datas), dtype=np.uint64); out_off[1:] = np.cumsum(caps)[:-1]
+        out = np.zeros(int(caps.sum()), dtype=np.uint8)
+        flen, fst = ctx.frames_compress(inp, in_off, in_len, out, out_off, caps, s)
+        assert not fst.any()
+        frames = []
+        for i, d in enumerate(datas):
+            got = out[int(out_off[i]): int(out_off[i]) + int(flen[i])].tobytes()
+            assert got == oracle.frame_compress(d, block_size=64 << 10, block_checksums=True)[1], i
+            frames.append(got)
+        # decode them back in one batch (dense output layout), corrupting two frames on the way
+        frames[5] = frames[5][:-1] + bytes([frames[5][-1] ^ 1])
+        frames[50] = frames[50][:len(frames[50]) // 2]
+        fl = np.array([len(f) for f in frames], dtype=np.uint64)
+        fo = np.zeros(len(frames), dtype=np.uint64); fo[1:] = np.cumsum(fl)[:-1]
+        fin = np.frombuffer(b"".join(frames), dtype=np.uint8)
+        back = np.zeros(int(in_len.sum()) + 1, dtype=np.uint8)
+        olen, st, det = ctx.frames_decompress(fin, fo, fl, back, in_off, in_len)
+        for i, d in enumerate(datas):
+            orc, odet, oplain, _c = oracle.frame_decompress(frames[i], cap=len(d))
+            assert (st[i], det[i], olen[i]) == (orc, odet, len(oplain)), i
+            assert back[int(in_off[i]): int(in_off[i]) + len(oplain)].tobytes() == oplain
+        assert st[5] == _native.F_FRAME_CHECKSUM_FAIL and st[50] != 0
+        # 150 blocks through ONE CTA: the per-CTA XXH32 queue (ring of 64) wraps twice
+        class _B:
+            pass
+        b = _B()
+        b.ctx = ctx
+        parity.check_batched_blocks(b, oracle, [d for d in datas if d] + [d[:777] for d in datas if len(d) > 800])
+    finally:
+        ctx.close()
+        _native._lib, _native._lib_path = saved
