@@ -64,7 +64,11 @@ struct lzf_ctx {
     std::string err;
     lzf_slot slots[kSlots];
     lzf_slot* cur = nullptr;            // slot the current call works in
-    uint64_t chunk_bytes = 96ull << 20; // payload per pipeline chunk of the host-buffer frame calls
+    // payload per pipeline chunk of the host-buffer frame calls.  A chunk is one kernel launch, and one
+    // warp owns one block, so a chunk must still hold enough blocks to fill the GPU (148 SMs x tens of
+    // warps): ~1 GiB of 64 KiB blocks for decode; compress (4 MiB blocks, ~1800 resident warps) needs more.
+    uint64_t chunk_bytes = 1ull << 30;
+    uint64_t compress_chunk_bytes = 8ull << 30;
 };
 
 namespace {
@@ -141,7 +145,7 @@ extern "C" int lzf_create(int device, lzf_ctx** out) {
     c->cur = &c->slots[0];
     if (const char* e = getenv("LZF_B200_CHUNK_BYTES")) {       // tuning / test knob
         const unsigned long long v = strtoull(e, nullptr, 10);
-        if (v) c->chunk_bytes = v;
+        if (v) c->chunk_bytes = c->compress_chunk_bytes = v;
     }
     if (!ok) { lzf_destroy(c); return LZF_ERR_CUDA; }
     *out = c;
@@ -937,7 +941,7 @@ extern "C" int lzf_frames_compress(lzf_ctx* c, const lzf_settings* s, const uint
     if (nframes && (!in_off || !in_len || !out_off || !out_cap || !out_len || !status))
         return fail(c, LZF_ERR_INVALID_ARG, "null pointer");
     LZF_CU(c, cudaSetDevice(c->device));
-    const std::vector<uint32_t> chunks = plan_chunks(in_len, nframes, c->chunk_bytes);
+    const std::vector<uint32_t> chunks = plan_chunks(in_len, nframes, c->compress_chunk_bytes);
     const uint32_t nchunks = (uint32_t)chunks.size() - 1;
     CompressChunk st[kSlots];
     int rc = LZF_SUCCESS;

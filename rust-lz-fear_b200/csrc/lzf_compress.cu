@@ -4,21 +4,32 @@
 // fresh zeroed EncoderTable and cursor 0, writing through NoPartialWrites(out[..cap])
 // (src/framed/compress.rs:242,294-308).  The emitted bytes are IDENTICAL to the reference's.
 //
-// The reference parse is one serial chain per block (hash -> table swap -> candidate compare).
-// We keep its exact semantics but evaluate it 32 probes at a time ("speculate 32 probes, commit
-// the prefix"): within a literal run the k-th future probe position is a closed-form function of
-// the run start (the step/step_counter recurrence of :174-175,225-231), so lane k hashes probe k,
-// reads its table slot, and — when a lower lane of the same batch hits the same slot — takes that
-// lane's position as its candidate, exactly what the serial mem::swap (:68) would have left
-// there.  A ballot picks the first lane whose candidate is a real >= 4-byte match (or that hits
-// the end-of-block rule :178); lanes up to the winner commit their table writes in lane order,
-// later lanes are discarded.  Forward/backward match extension (:117-145, :211-214) and the
-// sequence emit (:150-163, :239-260) are warp-parallel.  The per-warp hash table lives in shared
-// memory (16 KiB for the reference's 4096 x u32; 8 KiB when every position fits u16).
+// The reference parse is one serial chain per block (hash -> table swap -> candidate compare ->
+// extend -> emit).  We keep its exact semantics but evaluate it 32 positions at a time:
+//
+//   * a BATCH is 32 probe positions of the current literal run, one per lane.  While the run is
+//     young (fewer than 67 probes, src/raw/compress/mod.rs:174-175,225-231: step == 1) they are 32
+//     CONSECUTIVE bytes; afterwards they follow the closed form of the step recurrence;
+//   * every lane hashes its position, reads its table slot and verifies its table candidate with
+//     one 4-byte load — one L2 round trip for the whole batch instead of one per probe;
+//   * the serial table semantics (mem::swap at :68) are restored with __match_any_sync: a lane
+//     whose slot was overwritten by an earlier *inserted* lane of the same batch takes that lane's
+//     position as its candidate;
+//   * a ballot picks the first lane whose candidate is a real >= 4-byte match (or that hits the
+//     end-of-block rule :178).  In a consecutive batch the parse then CONTINUES inside the same batch:
+//     the match end lands on some later lane, the lanes in between were never probed (only
+//     `cursor - 2` is inserted, :218) and the lanes after it are re-evaluated against the updated
+//     set of inserted lanes — several sequences per batch without re-hashing anything;
+//   * forward and backward match extension (:117-145, :211-214) share one round trip: 24 lanes
+//     compare 96 bytes ahead, 8 lanes 32 bytes behind;
+//   * table writes are committed once per batch (last inserted lane per slot wins);
+//   * a whole short sequence (token, LSIC, literals, offset, LSIC) is written with one byte per
+//     lane; long literal runs use 16-byte vector copies.
+// The per-warp hash table lives in shared memory (16 KiB for the reference's 4096 x u32; 8 KiB
+// when every position fits u16).
 #include "lzf_kernels.cuh"
 
 namespace lzf {
-
 
 // offset of the j-th probe of a literal run from the run start: the closed form of
 //   cursor += step; step = step_counter >> 6; if literal_start + 1 != cursor { step_counter += 1 }
@@ -29,10 +40,16 @@ __device__ __forceinline__ uint64_t probe_offset(uint32_t j) {
     const uint64_t q = t >> 6, r = t & 63;
     return 2 + 32 * q * (q - 1) + r * q;
 }
+constexpr uint32_t kConsecutiveProbes = 67;     // probe_offset(j) == j for j < 67
 
-// hash_for_u32, 64-bit little-endian branch (:40-51): ((v << 24) * 889523592379) >> (64 - hashlog)
-__device__ __forceinline__ uint32_t hash5(uint64_t v, uint32_t hashlog) {
-    return (uint32_t)(((v << 24) * 889523592379ull) >> (64 - hashlog));
+// hash_for_u32, 64-bit little-endian branch (:40-51): ((v << 24) * 889523592379) >> (64 - hashlog),
+// evaluated from the five low bytes of v in 32-bit arithmetic.
+__device__ __forceinline__ uint32_t hash5(uint32_t v32, uint32_t b4, uint32_t hashlog) {
+    const uint32_t x_lo = v32 << 24;
+    const uint32_t x_hi = (v32 >> 8) | (b4 << 24);
+    const uint32_t k_lo = 0x1BBCDCBBu, k_hi = 0xCFu;           // 889523592379 = 0xCF1BBCDCBB
+    const uint32_t hi = __umulhi(x_lo, k_lo) + x_lo * k_hi + x_hi * k_lo;
+    return hi >> (32 - hashlog);
 }
 // hash_for_u16 (:58-61): one more bit than hashlog because the u16 table has twice the slots
 __device__ __forceinline__ uint32_t hash4(uint32_t v, uint32_t hashlog) {
@@ -40,24 +57,73 @@ __device__ __forceinline__ uint32_t hash4(uint32_t v, uint32_t hashlog) {
 }
 
 // bytes write_lsic_tail (:243-260) emits for `value`
-__device__ __forceinline__ uint64_t lsic_len(uint64_t value) {
+__device__ __forceinline__ uint32_t lsic_len(uint32_t value) {
     return value < 15 ? 0 : (value - 15) / 255 + 1;
 }
 // warp-parallel write_lsic_tail
-__device__ __forceinline__ void write_lsic(uint8_t* dst, uint64_t value) {
+__device__ __forceinline__ void write_lsic(uint8_t* dst, uint32_t value) {
     if (value < 15) return;
-    const uint64_t nbytes = (value - 15) / 255 + 1;
+    const uint32_t nbytes = (value - 15) / 255 + 1;
     const uint8_t last = (uint8_t)((value - 15) % 255);
-    for (uint64_t i = lane_id(); i < nbytes; i += 32) dst[i] = (i == nbytes - 1) ? last : 0xff;
+    for (uint32_t i = lane_id(); i < nbytes; i += 32) dst[i] = (i == nbytes - 1) ? last : 0xff;
 }
 
-constexpr int kEncodeWarpsPerCta = 4;
+// 4 bytes at in[pos] (any alignment), pos + 4 <= block length: the aligned words read all hold at
+// least one byte of the range, so nothing outside the allocation is touched
+__device__ __forceinline__ uint32_t ld4(const uint8_t* in, uint32_t pos) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(in + pos);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+    const unsigned sh = (unsigned)(a & 3u) * 8u;
+    const uint32_t lo = __ldg(w);
+    if (sh == 0) return lo;
+    return __funnelshift_r(lo, __ldg(w + 1), sh);
+}
+
+// One LZ4 sequence (write_group :150-163, or the literal-only tail :182-189 when `final`).
+// Returns false when the bounded writer would refuse it (NoPartialWrites, compress.rs:298-301).
+__device__ __forceinline__ bool emit_sequence(uint8_t* out, uint64_t& opos, uint64_t cap, const uint8_t* in,
+                                              uint32_t lit_start, uint32_t L, uint32_t offset, uint32_t extra, bool final) {
+    const unsigned lane = lane_id();
+    const uint32_t ll = lsic_len(L), ml = final ? 0u : lsic_len(extra);
+    const uint64_t total = 1ull + ll + L + (final ? 0u : 2u + ml);
+    if (opos + total > cap) return false;
+    uint8_t* o = out + opos;
+    const uint8_t token = (uint8_t)(((L < 15 ? L : 15) << 4) | (final ? 0u : (extra < 15 ? extra : 15)));
+    if (total <= 32) {
+        // one byte per lane: token | lsic(L) | literals | offset | lsic(extra)
+        if (lane < total) {
+            uint8_t v;
+            if (lane == 0) v = token;
+            else if (lane < 1 + ll) v = (lane == ll) ? (uint8_t)((L - 15) % 255) : 0xff;
+            else if (lane < 1 + ll + L) v = __ldg(in + lit_start + (lane - 1 - ll));
+            else if (lane < 1 + ll + L + 2) v = (uint8_t)(offset >> (8 * (lane - 1 - ll - L)));
+            else v = (lane == total - 1) ? (uint8_t)((extra - 15) % 255) : 0xff;
+            o[lane] = v;
+        }
+    } else {
+        if (lane == 0) o[0] = token;
+        write_lsic(o + 1, L);
+        warp_copy(o + 1 + ll, in + lit_start, L);
+        if (!final) {
+            if (lane < 2) o[1 + ll + L + lane] = (uint8_t)(offset >> (8 * lane));
+            write_lsic(o + 1 + ll + L + 2, extra);
+        }
+    }
+    opos += total;
+    return true;
+}
+
+#ifndef LZF_ENC_WARPS
+#define LZF_ENC_WARPS 4
+#endif
+constexpr int kEncodeWarpsPerCta = LZF_ENC_WARPS;
 constexpr int kGlobalTableCtasPerSm = 4;   // bounds the global table scratch
 
 template <typename Slot, bool kHash4>
 __global__ void __launch_bounds__(kEncodeWarpsPerCta * 32)
 encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
     LZF_DYN_SMEM(smem_raw);
+    __shared__ HashQueue hashq;
     const unsigned lane = lane_id();
     const unsigned warp_in_cta = threadIdx.x >> 5;
     Slot* table;
@@ -68,6 +134,8 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
         table = reinterpret_cast<Slot*>(a.global_tables) + gw * nslots;
     }
     const uint32_t hashlog = a.hashlog;
+    const uint32_t lower_mask = (1u << lane) - 1u;
+    hash_queue_init(&hashq);
 
     for (;;) {
         uint32_t b = 0;
@@ -75,21 +143,20 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
         b = __shfl_sync(LZF_FULL_MASK, b, 0);
         if (b >= a.nblocks) break;
 
-        const uint64_t len = a.in_len[b];
+        const uint32_t len = a.in_len[b];
         const uint8_t* in = a.in + a.in_off[b];
-        const uint8_t* in_end = in + len;
         uint8_t* out = a.out + a.out_off[b];
-        const uint64_t cap = a.out_cap ? (uint64_t)a.out_cap[b] : len;
+        const uint64_t cap = a.out_cap ? (uint64_t)a.out_cap[b] : (uint64_t)len;
 
         int status = LZF_OK;
         uint64_t opos = 0;
 
         // assert!(input.len() <= T::payload_size_limit())  :167 ; Slot width must hold every position
-        const bool too_big = (kHash4 && len > 0xffffull) || (sizeof(Slot) == 2 && len > 0x10000ull) ||
+        const bool too_big = (kHash4 && len > 0xffffu) || (sizeof(Slot) == 2 && len > 0x10000u) ||
                              (a.max_block_len && len > a.max_block_len);
         if (too_big) {
             status = LZF_PANIC;
-        } else {
+        } else if (len) {
             // fresh zeroed table (U32Table::default :32-36 / template_table.clone() compress.rs:270)
             {
                 uint4* t4 = reinterpret_cast<uint4*>(table);
@@ -98,138 +165,199 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
             }
             __syncwarp();
 
-            uint64_t cursor = 0;
-            while (cursor < len) {                                            // :171
-                const uint64_t literal_start = cursor;
-                uint32_t j0 = 0;
-                bool finished = false;
-                uint64_t cur = 0, cnd = 0;
-                for (;;) {                                                    // :177, 32 probes per trip
-                    const uint64_t p = literal_start + probe_offset(j0 + lane);
-                    const bool is_end = (p >= len) || (len - p < 12);         // :178
-                    uint64_t v = 0;
-                    uint32_t h = 0xffff0000u | lane;                          // unique key for idle lanes
-                    if (!is_end) {
-                        v = ld_u64_unaligned(in + p, in_end);
-                        h = kHash4 ? hash4((uint32_t)v, hashlog) : hash5(v, hashlog);
-                    }
-                    const uint32_t same = __match_any_sync(LZF_FULL_MASK, h);
-                    const uint32_t lower = same & ((1u << lane) - 1u);
-                    const uint32_t src_lane = lower ? (31u - __clz(lower)) : lane;
-                    const uint32_t p_lo = (uint32_t)p;
-                    const uint32_t in_batch = __shfl_sync(LZF_FULL_MASK, p_lo, src_lane);
-                    uint64_t cand = 0;
-                    bool ok = false;
-                    if (!is_end) {
-                        cand = lower ? (uint64_t)in_batch : (uint64_t)table[h];   // table.replace :196 (read half)
-                        ok = (p != 0) && (p - cand <= 0xffffull) &&               // :200-201
-                             ld_u32_unaligned(in + cand) == (uint32_t)v;           // >= MINMATCH bytes :206
-                    }
-                    const uint32_t trig = __ballot_sync(LZF_FULL_MASK, ok || is_end);
-                    if (trig == 0) {
-                        if ((same >> lane) == 1u) table[h] = (Slot)p;         // last writer of each slot wins
-                        __syncwarp();
-                        j0 += 32;
-                        continue;
-                    }
-                    const uint32_t w = __ffs(trig) - 1;
-                    const bool w_is_end = __shfl_sync(LZF_FULL_MASK, (int)is_end, w) != 0;
-                    // probes before the winner (and the winner itself when it is a match) did replace()
-                    const uint32_t commit = w_is_end ? ((1u << w) - 1u) : ((2u << w) - 1u);
-                    if (((commit >> lane) & 1u) && ((same & commit) >> lane) == 1u) table[h] = (Slot)p;
-                    __syncwarp();
-                    finished = w_is_end;
-                    cur = literal_start + probe_offset(j0 + w);
-                    cnd = __shfl_sync(LZF_FULL_MASK, (uint32_t)cand, w);
-                    break;
+            uint32_t lit_start = 0;     // start of the current literal run
+            uint32_t j = 0;             // probes already done in the current run
+            bool done = false;
+            while (!done) {                                                   // :171 / :177, 32 probes per trip
+                // ---- the batch: one probe position per lane
+                const bool consecutive = j + 32 <= kConsecutiveProbes;
+                const uint64_t p64 = (uint64_t)lit_start + (consecutive ? (uint64_t)(j + lane) : probe_offset(j + lane));
+                const bool is_end = p64 >= len || len - (uint32_t)p64 < 12;    // :178
+                const uint32_t p = (uint32_t)p64;
+                const uint32_t endmask = __ballot_sync(LZF_FULL_MASK, is_end);
+                uint32_t v32 = 0, h = 0xffff0000u | lane;                     // unique key for idle lanes
+                uint32_t tcand = 0;
+                if (!is_end) {
+                    const uintptr_t ad = reinterpret_cast<uintptr_t>(in + p);
+                    const uint32_t* w = reinterpret_cast<const uint32_t*>(ad & ~uintptr_t(3));
+                    const unsigned sh = (unsigned)(ad & 3u) * 8u;
+                    const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1);          // 12 bytes remain: both words are inside the block
+                    v32 = __funnelshift_r(w0, w1, sh);
+                    h = kHash4 ? hash4(v32, hashlog) : hash5(v32, (w1 >> sh) & 0xffu, hashlog);
+                    tcand = table[h];                                         // table.replace :196 (read half)
                 }
+                const uint32_t same = __match_any_sync(LZF_FULL_MASK, h);
+                // table candidate: addressable (:200-201) and >= MINMATCH equal bytes (:206)
+                bool t_ok = false;
+                if (!is_end && p != 0 && p - tcand <= 0xffffu) t_ok = ld4(in, tcand) == v32;
+                const uint32_t base = __shfl_sync(LZF_FULL_MASK, p, 0);
 
-                if (finished) {
-                    // final literal-only sequence  :178-190
-                    const uint64_t L = len - literal_start;
-                    const uint64_t total = 1 + lsic_len(L) + L;
-                    if (opos + total > cap) { status = LZF_WRITER_FULL; break; }
-                    if (lane == 0) out[opos] = (uint8_t)((L < 15 ? L : 15) << 4);
-                    write_lsic(out + opos + 1, L);
-                    warp_copy(out + opos + 1 + lsic_len(L), in + literal_start, L);
-                    opos += total;
-                    cursor = len;
-                    break;
-                }
-
-                // ---- forward extension: count_matching_bytes(input[cur..len-5], input[cnd..])  :117-145,203-204
-                const uint64_t limit = len - 5 - cur;
-                uint64_t matching = 4;
+                uint32_t ins = 0;       // lanes whose probe (or cursor-2 insert) has happened, in order
+                uint32_t s = 0;         // first lane of the current run inside this batch
+                bool committed = false;
                 for (;;) {
-                    const uint64_t idx = matching + (uint64_t)lane * 8;
-                    uint32_t cnt = 0;
-                    if (idx < limit) {
-                        const uint64_t x = ld_u64_unaligned(in + cur + idx, in_end) ^ ld_u64_unaligned(in + cnd + idx, in_end);
-                        cnt = x ? (uint32_t)(__ffsll((long long)x) - 1) >> 3 : 8u;
-                        const uint64_t room = limit - idx;
-                        if (cnt > room) cnt = (uint32_t)room;
-                    }
-                    const uint32_t stop = __ballot_sync(LZF_FULL_MASK, cnt != 8u);
-                    if (stop == 0) { matching += 256; continue; }
-                    const uint32_t f = __ffs(stop) - 1;
-                    matching += (uint64_t)f * 8 + __shfl_sync(LZF_FULL_MASK, cnt, f);
-                    break;
-                }
-                // ---- backtrack  :211-214
-                uint64_t backtrack = 0;
-                {
-                    const uint64_t max_backtrack = min(cur - literal_start, cnd);
-                    while (backtrack < max_backtrack) {
-                        const uint64_t k = backtrack + lane;
-                        const bool eq = k < max_backtrack && in[cur - 1 - k] == in[cnd - 1 - k];
-                        const uint32_t stop = __ballot_sync(LZF_FULL_MASK, !eq);
-                        if (stop == 0) { backtrack += 32; continue; }
-                        backtrack += __ffs(stop) - 1;
+                    // ---- candidates as the serial algorithm would see them: lane k of the current run
+                    // comes after every insert recorded so far AND after the probes s..k-1 of its own run
+                    const uint32_t inb = same & (ins | ~((1u << s) - 1u)) & lower_mask;
+                    const uint32_t src = inb ? (31u - __clz(inb)) : lane;
+                    const uint32_t pj = __shfl_sync(LZF_FULL_MASK, p, src);
+                    const uint32_t vj = __shfl_sync(LZF_FULL_MASK, v32, src);
+                    const uint32_t cand = inb ? pj : tcand;
+                    const bool ok = !is_end && lane >= s && (inb ? (vj == v32 && p - pj <= 0xffffu) : t_ok);
+                    const uint32_t trig = __ballot_sync(LZF_FULL_MASK, (ok || is_end) && lane >= s);
+                    if (trig == 0) {
+                        ins |= ~((1u << s) - 1u);                             // every lane from s on probed and missed
+                        j += 32 - s;
                         break;
                     }
+                    const uint32_t w = __ffs(trig) - 1;
+                    if ((endmask >> w) & 1u) {
+                        // final literal-only sequence  :178-190
+                        if (!emit_sequence(out, opos, cap, in, lit_start, len - lit_start, 0, 0, true)) status = LZF_WRITER_FULL;
+                        done = true;
+                        committed = true;                                     // the table is never read again
+                        break;
+                    }
+                    ins |= ((2u << w) - 1u) & ~((1u << s) - 1u);             // probes s..w happened
+                    const uint32_t cur = __shfl_sync(LZF_FULL_MASK, p, w);
+                    const uint32_t cnd = __shfl_sync(LZF_FULL_MASK, cand, w);
+
+                    // ---- extension: lanes 0..23 look 96 bytes ahead (count_matching_bytes :117-145 over
+                    // input[cur..len-5]), lanes 24..31 look 32 bytes behind (backtrack :211-214)
+                    const uint32_t limit = len - 5 - cur;                     // bytes of current_batch :195
+                    const uint32_t max_back = min(cur - lit_start, cnd);
+                    uint32_t cnt = 4;                                         // bytes this lane's word contributes
+                    if (lane < 24) {
+                        const uint32_t f = 4 + 4 * lane;
+                        if (f < limit) {
+                            const uint32_t x = ld4(in, cur + f) ^ ld4(in, cnd + f);   // cur + f + 4 <= len - 1
+                            const uint32_t c = x ? (uint32_t)(__ffs((int)x) - 1) >> 3 : 4u;
+                            cnt = min(c, limit - f);
+                        } else cnt = 0;
+                    } else {
+                        const uint32_t t = lane - 24;                         // word t covers bytes [4t, 4t+4) behind
+                        if (4 * t < max_back) {
+                            const uint32_t avail = min(4u, max_back - 4 * t);
+                            uint32_t c = 0;
+                            if (avail == 4) {
+                                const uint32_t x = ld4(in, cur - 4 * t - 4) ^ ld4(in, cnd - 4 * t - 4);
+                                c = x ? (uint32_t)__clz((int)x) >> 3 : 4u;    // equal bytes counted from the top (nearest to cur)
+                            } else {
+                                while (c < avail && in[cur - 4 * t - 1 - c] == in[cnd - 4 * t - 1 - c]) c++;
+                            }
+                            cnt = c;
+                        } else cnt = 0;
+                    }
+                    const uint32_t stop = __ballot_sync(LZF_FULL_MASK, cnt != 4u);
+                    uint32_t matching;
+                    {
+                        const uint32_t fstop = stop & 0x00ffffffu;
+                        if (fstop) {
+                            const uint32_t fl = __ffs(fstop) - 1;
+                            matching = 4 + 4 * fl + __shfl_sync(LZF_FULL_MASK, cnt, fl);
+                        } else {
+                            // long match: stream on, 8 bytes per lane and step
+                            matching = 100;
+                            for (;;) {
+                                const uint32_t idx = matching + lane * 8;
+                                uint32_t c = 0;
+                                if (idx < limit) {
+                                    const uint32_t room = limit - idx;
+                                    if (room >= 8) {
+                                        const uint32_t x0 = ld4(in, cur + idx) ^ ld4(in, cnd + idx);
+                                        const uint32_t x1 = ld4(in, cur + idx + 4) ^ ld4(in, cnd + idx + 4);
+                                        c = x0 ? (uint32_t)(__ffs((int)x0) - 1) >> 3 : (x1 ? 4u + ((uint32_t)(__ffs((int)x1) - 1) >> 3) : 8u);
+                                    } else {
+                                        while (c < room && in[cur + idx + c] == in[cnd + idx + c]) c++;
+                                    }
+                                }
+                                const uint32_t st2 = __ballot_sync(LZF_FULL_MASK, c != 8u);
+                                if (st2 == 0) { matching += 256; continue; }
+                                const uint32_t f2 = __ffs(st2) - 1;
+                                matching += f2 * 8 + __shfl_sync(LZF_FULL_MASK, c, f2);
+                                break;
+                            }
+                        }
+                    }
+                    uint32_t backtrack;
+                    {
+                        const uint32_t bstop = stop >> 24;
+                        if (bstop) {
+                            const uint32_t bl = __ffs(bstop) - 1;
+                            backtrack = 4 * bl + __shfl_sync(LZF_FULL_MASK, cnt, 24 + bl);
+                        } else {
+                            backtrack = 32;
+                            while (backtrack < max_back) {
+                                const uint32_t k = backtrack + lane;
+                                const bool eq = k < max_back && in[cur - 1 - k] == in[cnd - 1 - k];
+                                const uint32_t st2 = __ballot_sync(LZF_FULL_MASK, !eq);
+                                if (st2 == 0) { backtrack += 32; continue; }
+                                backtrack += __ffs(st2) - 1;
+                                break;
+                            }
+                        }
+                    }
+                    const uint32_t extra = matching - 4 + backtrack;          // :206,214
+                    const uint32_t cursor = cur + matching;                   // :215
+
+                    // ---- write_group  :150-163,235-236
+                    if (!emit_sequence(out, opos, cap, in, lit_start, cur - backtrack - lit_start, cur - cnd, extra, false)) {
+                        status = LZF_WRITER_FULL;
+                        done = true;
+                        committed = true;
+                        break;
+                    }
+                    lit_start = cursor;
+                    j = 0;
+
+                    // ---- table.replace(input, cursor - 2)  :218, and where the parse resumes
+                    const uint32_t q2 = cursor - 2;
+                    if (consecutive && cursor - base < 32) {
+                        const uint32_t l2 = q2 - base;
+                        // a lane past the 12-byte rule has no hash; its insert can never be read again
+                        if (!((endmask >> l2) & 1u)) ins |= 1u << l2;
+                        s = cursor - base;
+                        continue;                                             // next sequence of the same batch
+                    }
+                    // the match left the batch: commit, then insert cursor - 2 behind everything committed
+                    {
+                        const uint32_t later = same & ins & ~lower_mask & ~(1u << lane);
+                        if (((ins >> lane) & 1u) && later == 0) table[h] = (Slot)p;
+                        __syncwarp();
+                        if (lane == 0) {
+                            uint32_t h2;
+                            if (kHash4) h2 = hash4(ld4(in, q2), hashlog);
+                            else if (len - q2 >= 8) h2 = hash5(ld4(in, q2), in[q2 + 4], hashlog);
+                            else h2 = 0;                                      // :43 unwrap_or(0) -> hash of 0
+                            table[h2] = (Slot)q2;
+                        }
+                        committed = true;
+                    }
+                    break;
                 }
-                const uint64_t extra = matching - 4 + backtrack;              // :206,214
-                const uint32_t offset = (uint32_t)(cur - cnd);                // :208
-                cursor = cur + matching;                                      // :215
-                // table.replace(input, cursor - 2)  :218
-                if (lane == 0) {
-                    const uint64_t q = cursor - 2;
-                    uint32_t h2;
-                    if (kHash4) h2 = hash4(ld_u32_unaligned(in + q), hashlog);
-                    else h2 = hash5(len - q >= 8 ? ld_u64_unaligned(in + q, in_end) : 0ull, hashlog);   // :43 unwrap_or(0)
-                    table[h2] = (Slot)q;
+                if (!committed) {
+                    // last inserted lane of each slot wins (mem::swap order, :64-71)
+                    const uint32_t later = same & ins & ~lower_mask & ~(1u << lane);
+                    if (((ins >> lane) & 1u) && later == 0) table[h] = (Slot)p;
                 }
                 __syncwarp();
-
-                // ---- write_group  :150-163,235-236
-                const uint64_t L = cur - backtrack - literal_start;
-                const uint64_t ll = lsic_len(L), ml = lsic_len(extra);
-                const uint64_t total = 1 + ll + L + 2 + ml;
-                if (opos + total > cap) { status = LZF_WRITER_FULL; break; }
-                uint8_t* o = out + opos;
-                if (lane == 0) o[0] = (uint8_t)(((L < 15 ? L : 15) << 4) | (extra < 15 ? extra : 15));
-                write_lsic(o + 1, L);
-                warp_copy(o + 1 + ll, in + literal_start, L);
-                if (lane < 2) o[1 + ll + L + lane] = (uint8_t)(offset >> (8 * lane));
-                write_lsic(o + 1 + ll + L + 2, extra);
-                opos += total;
             }
         }
 
         __syncwarp();
-        if (a.xxh_plain || a.xxh_stored) {
-            const uint32_t hp = warp_xxh32(in, len);
-            if (lane == 0 && a.xxh_plain) a.xxh_plain[b] = hp;
-            if (a.xxh_stored) {
-                const uint32_t hs = (status == LZF_OK) ? warp_xxh32(out, opos) : hp;
-                if (lane == 0) a.xxh_stored[b] = hs;
-            }
-        }
         if (lane == 0) {
             a.out_len[b] = (status == LZF_OK) ? (uint32_t)opos : 0u;
             a.status[b] = status;
         }
+        // XXH32 of the plaintext / of the stored bytes (compressed, or the plaintext when stored raw):
+        // queued so that 8 blocks are hashed per warp pass
+        if (a.xxh_plain) hash_queue_push(&hashq, in, len, a.xxh_plain + b);
+        if (a.xxh_stored) {
+            if (status == LZF_OK) hash_queue_push(&hashq, out, opos, a.xxh_stored + b);
+            else hash_queue_push(&hashq, in, len, a.xxh_stored + b);
+        }
     }
+    hash_queue_finish(&hashq, kEncodeWarpsPerCta);
 }
 
 }  // namespace lzf

@@ -21,6 +21,8 @@
 //     touch the end of the block, every error and the out-of-capacity "dry" mode.
 #include "lzf_kernels.cuh"
 
+#include <stdlib.h>
+
 namespace lzf {
 
 #ifndef LZF_DEC_MINCTAS
@@ -36,11 +38,33 @@ constexpr uint32_t kStageMask = kStage - 1;
 constexpr uint32_t kFastSeqMax = 3 + 14;   // token + 14 literals + offset: no LSIC byte anywhere
 
 struct __align__(16) DecodeWarpSmem {
-    uint8_t win[kWin];
-    uint8_t stage[kStage];
+    uint8_t win[kWin];            // staged compressed bytes
+    uint8_t step[kWin + 32];      // step[p] = encoded size of the LSIC-free sequence whose token is win[p]; 0 = not fast
+    uint8_t stage[kStage];        // output staging ring
+    uint16_t plist[32];           // token positions of the current step
     uint64_t mbar;
     uint64_t pad;
 };
+
+// step[] for the freshly staged window: 4 positions per lane and pass, SIMD-in-a-word.
+//   step = 3 + (token >> 4), or 0 when either nibble is 15 (LSIC extension -> slow path) or when
+//   the sequence would end beyond `wend` (window / block end -> refill or slow path).
+__device__ __forceinline__ void build_steps(DecodeWarpSmem& sm, uint32_t wlen, uint32_t wend) {
+    const unsigned lane = lane_id();
+    const uint32_t* w4 = reinterpret_cast<const uint32_t*>(sm.win);
+    uint32_t* s4 = reinterpret_cast<uint32_t*>(sm.step);
+    const uint32_t nwords = (wlen + 3) >> 2;
+    for (uint32_t i = lane; i < nwords; i += 32) {
+        const uint32_t w = w4[i];
+        const uint32_t special = __vcmpeq4(w & 0xf0f0f0f0u, 0xf0f0f0f0u) | __vcmpeq4(w & 0x0f0f0f0fu, 0x0f0f0f0fu);
+        s4[i] = (((w >> 4) & 0x0f0f0f0fu) + 0x03030303u) & ~special;
+    }
+    __syncwarp();
+    // the last kFastSeqMax positions may describe sequences that cross wend; wend itself terminates a walk
+    const uint32_t p = wend - min(wend, kFastSeqMax + 1u) + lane;
+    if (p <= wend && (p == wend || p + sm.step[p] > wend)) sm.step[p] = 0;
+    __syncwarp();
+}
 
 // 128-byte register window over the compressed stream (slow path).
 struct Window {
@@ -252,28 +276,27 @@ decode_blocks_kernel(DecodeArgs a) {
                         phase ^= 1u;
                         wq = want;
                         wlen = nbytes;
+                        build_steps(sm, wlen, (uint32_t)(((wq + wlen) < qn ? (wq + wlen) : qn) - wq));
                     }
                 }
-                const uint64_t wend64 = (wq + wlen) < qn ? (wq + wlen) : qn;
                 // window-relative positions from here on
-                const uint32_t wend = (uint32_t)(wend64 - wq);
                 uint32_t p = (uint32_t)(q - wq);
 
-                // ---- walk: up to 32 LSIC-free sequences that lie completely inside the window
-                uint32_t cnt = 0, my_p = 0;
+                // ---- walk: up to 32 LSIC-free sequences that lie completely inside the window.  This is
+                // the only serial part of the decoder: one shared-memory byte per sequence.
+                uint32_t cnt = 0;
                 if (s.olen + 32u * 32u <= bound) {
-#pragma unroll
+#pragma unroll 8
                     for (int k = 0; k < 32; k++) {
-                        if (p + 3 > wend) break;
-                        const uint32_t tok = sm.win[p];
-                        const uint32_t lit = tok >> 4;
-                        const uint32_t e = p + 3 + lit;
-                        if (lit == 15u || (tok & 15u) == 15u || e > wend) break;
-                        if (lane == (unsigned)k) my_p = p;
-                        p = e;
+                        const uint32_t d = sm.step[p];
+                        if (d == 0) break;
+                        sm.plist[k] = (uint16_t)p;
+                        p += d;
                         cnt = k + 1;
                     }
                 }
+                __syncwarp();
+                const uint32_t my_p = sm.plist[lane];
                 // ---- per-lane decode of the sequence headers, output positions by warp scan
                 uint32_t lit = 0, ml = 0, off = 1, tot = 0;
                 if (lane < cnt) {
@@ -296,7 +319,11 @@ decode_blocks_kernel(DecodeArgs a) {
                 // else is replayed by the slow path, which reports the error exactly like the reference
                 const bool bad = lane < cnt && (off == 0u || (uint64_t)off > (uint64_t)dstp + s.plen);
                 const uint32_t fb = __ballot_sync(LZF_FULL_MASK, bad);
-                if (fb) cnt = min(cnt, (uint32_t)(__ffs(fb) - 1));
+                uint32_t in_end = p;
+                if (fb) {
+                    const uint32_t keep = (uint32_t)(__ffs(fb) - 1);
+                    if (keep < cnt) { cnt = keep; in_end = sm.plist[keep]; }     // the next sequence starts where the kept ones end
+                }
                 if (cnt == 0) {
                     flushed = flush_stage(sm.stage, s.out, sbase, flushed, (uint32_t)s.olen, true);
                     __syncwarp();
@@ -306,7 +333,6 @@ decode_blocks_kernel(DecodeArgs a) {
                 }
                 const bool act = lane < cnt;
                 const uint32_t out_end = __shfl_sync(LZF_FULL_MASK, o_k + tot, cnt - 1);
-                const uint32_t in_end = __shfl_sync(LZF_FULL_MASK, my_p + 3 + lit, cnt - 1);
 
                 // ---- literals: every lane copies its own run into the staging ring
                 if (act) {
@@ -376,6 +402,12 @@ extern "C" int lzf_launch_decode(const lzf::DecodeArgs* args, int num_sms, cudaS
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, decode_blocks_kernel, kDecodeWarpsPerCta * 32, dyn);
     if (e != cudaSuccess) return (int)e;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
+#ifndef LZF_SIMT_EMU
+    if (const char* e = getenv("LZF_B200_DEC_CTAS_PER_SM")) {     // tuning knob: cap the resident CTAs per SM
+        const int v = atoi(e);
+        if (v >= 1 && v < ctas_per_sm) ctas_per_sm = v;
+    }
+#endif
     unsigned grid = (unsigned)(num_sms * ctas_per_sm);
     const unsigned need = (args->nblocks + kDecodeWarpsPerCta - 1) / kDecodeWarpsPerCta;
     if (grid > need) grid = need;
