@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--decomp-gib", type=float, default=4.0, help="config-2 plaintext GiB per GPU")
     ap.add_argument("--comp-gib", type=float, default=16.0, help="config-3 plaintext GiB per GPU")
     ap.add_argument("--no-compress", action="store_true", help="skip the config-3 compress section")
+    ap.add_argument("--no-decompress-e2e", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-xxh", action="store_true", help="experiment: skip the fused XXH32 epilogue")

@@ -11,8 +11,11 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 // ------------------------------------------------------------------------------------------------
@@ -55,26 +58,32 @@ struct lzf_slot {
     Buf d_comp;                         // compressed-block scratch (frame compress)
     Buf d_io_in, d_io_out;              // staging of host-buffer calls
 };
-constexpr int kSlots = 3;
+constexpr int kSlots = 4;
 
 struct lzf_ctx {
     int device = 0;
     int num_sms = 0;
-    uint64_t launches = 0;
+    std::atomic<uint64_t> launches{0};
+    std::mutex err_mu;
     std::string err;
     lzf_slot slots[kSlots];
-    lzf_slot* cur = nullptr;            // slot the current call works in
-    // payload per pipeline chunk of the host-buffer frame calls.  A chunk is one kernel launch, and one
-    // warp owns one block, so a chunk must still hold enough blocks to fill the GPU (148 SMs x tens of
-    // warps): ~1 GiB of 64 KiB blocks for decode; compress (4 MiB blocks, ~1800 resident warps) needs more.
-    uint64_t chunk_bytes = 1ull << 30;
-    uint64_t compress_chunk_bytes = 8ull << 30;
+    // payload per pipeline chunk of the host-buffer frame calls.  A chunk is one kernel launch and one
+    // warp owns one block, so the chunks in flight together must hold enough blocks to fill the GPU
+    // (148 SMs x tens of warps): up to kSlots chunks run concurrently, one host thread + stream each.
+    uint64_t chunk_bytes = 512ull << 20;            // decompress: compressed + plaintext bytes
+    uint64_t compress_chunk_bytes = 2ull << 30;     // compress: plaintext bytes (4 MiB blocks need many in flight)
 };
+
+// slot of the calling thread: worker threads of the host-buffer pipelines bind their own, every other
+// call works in slot 0
+static thread_local lzf_slot* tls_slot = nullptr;
+static inline lzf_slot* cur_slot(lzf_ctx* c) { return tls_slot ? tls_slot : &c->slots[0]; }
 
 namespace {
 
 int fail(lzf_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
     if (c) {
+        std::lock_guard<std::mutex> lock(c->err_mu);
         c->err = what;
         if (e != cudaSuccess) { c->err += ": "; c->err += cudaGetErrorString(e); }
     }
@@ -142,7 +151,6 @@ extern "C" int lzf_create(int device, lzf_ctx** out) {
              cudaEventCreateWithFlags(&sl.ev_join, cudaEventDisableTiming) == cudaSuccess &&
              cudaMalloc((void**)&sl.d_counter, 256) == cudaSuccess;
     }
-    c->cur = &c->slots[0];
     if (const char* e = getenv("LZF_B200_CHUNK_BYTES")) {       // tuning / test knob
         const unsigned long long v = strtoull(e, nullptr, 10);
         if (v) c->chunk_bytes = c->compress_chunk_bytes = v;
@@ -173,7 +181,7 @@ extern "C" void lzf_destroy(lzf_ctx* c) {
 }
 
 extern "C" const char* lzf_last_error(const lzf_ctx* c) { return c ? c->err.c_str() : "null ctx"; }
-extern "C" uint64_t lzf_launch_count(const lzf_ctx* c) { return c ? c->launches : 0; }
+extern "C" uint64_t lzf_launch_count(const lzf_ctx* c) { return c ? c->launches.load() : 0; }
 extern "C" size_t lzf_compress_bound(size_t n) { return n + n / 255 + 16; }
 
 // ------------------------------------------------------------------------------------------------
@@ -198,15 +206,15 @@ int compress_blocks_impl(lzf_ctx* c, const uint8_t* d_in, const uint64_t* d_in_o
     a.hashlog = hashlog; a.table_kind = table_kind;
     a.out = d_out; a.out_off = d_out_off; a.out_cap = d_out_cap; a.out_len = d_out_len; a.status = d_status;
     a.xxh_plain = d_xxh_plain; a.xxh_stored = d_xxh_stored;
-    a.work_counter = c->cur->d_counter;
+    a.work_counter = cur_slot(c)->d_counter;
     a.max_block_len = max_block_len;
     const size_t nslots = table_kind == LZF_TABLE_U16 ? ((size_t)2 << hashlog) : ((size_t)1 << hashlog);
     if (nslots * 4 > 32 * 1024) {
-        const int rc = ensure_dev(c, c->cur->d_tables, lzf_encode_global_table_warps(c->num_sms) * nslots * 4);
+        const int rc = ensure_dev(c, cur_slot(c)->d_tables, lzf_encode_global_table_warps(c->num_sms) * nslots * 4);
         if (rc) return rc;
-        a.global_tables = (uint8_t*)c->cur->d_tables.p;
+        a.global_tables = (uint8_t*)cur_slot(c)->d_tables.p;
     }
-    LZF_CU(c, cudaMemsetAsync(c->cur->d_counter, 0, 4, s));
+    LZF_CU(c, cudaMemsetAsync(cur_slot(c)->d_counter, 0, 4, s));
     LZF_LAUNCHED(c, lzf_launch_encode(&a, c->num_sms, s), 1);
     return LZF_SUCCESS;
 }
@@ -226,8 +234,8 @@ int decompress_blocks_impl(lzf_ctx* c, const uint8_t* d_in, const uint64_t* d_in
     a.prefix = d_prefix; a.prefix_off = d_prefix_off; a.prefix_len = d_prefix_len;
     a.out = d_out; a.out_off = d_out_off; a.out_cap = d_out_cap; a.out_limit = d_out_limit;
     a.out_len = d_out_len; a.status = d_status; a.xxh_plain = d_xxh_plain;
-    a.work_counter = c->cur->d_counter + 16;
-    LZF_CU(c, cudaMemsetAsync(c->cur->d_counter + 16, 0, 4, s));
+    a.work_counter = cur_slot(c)->d_counter + 16;
+    LZF_CU(c, cudaMemsetAsync(cur_slot(c)->d_counter + 16, 0, 4, s));
     LZF_LAUNCHED(c, lzf_launch_decode(&a, c->num_sms, s), 1);
     return LZF_SUCCESS;
 }
@@ -291,20 +299,20 @@ extern "C" int lzf_xxh32_update(lzf_ctx* c, lzf_xxh32_state* st, const uint8_t* 
     const size_t dev_bytes = (head_full ? 16 : 0) + body;
     if (dev_bytes) {
         int rc;
-        if ((rc = ensure_dev(c, c->cur->d_io_in, dev_bytes + 64))) return rc;
-        if ((rc = ensure_dev(c, c->cur->d_desc, 4096))) return rc;
-        if ((rc = ensure_host(c, c->cur->h_desc, 4096))) return rc;
-        uint8_t* din = (uint8_t*)c->cur->d_io_in.p;
-        cudaStream_t s = c->cur->stream;
-        memcpy(c->cur->h_desc.p, st->acc, 16);
-        if (head_full) memcpy((uint8_t*)c->cur->h_desc.p + 16, st->buf, 16);
-        LZF_CU(c, cudaMemcpyAsync(c->cur->d_desc.p, c->cur->h_desc.p, 32, cudaMemcpyHostToDevice, s));
-        if (head_full) LZF_CU(c, cudaMemcpyAsync(din, (uint8_t*)c->cur->d_desc.p + 16, 16, cudaMemcpyDeviceToDevice, s));
+        if ((rc = ensure_dev(c, cur_slot(c)->d_io_in, dev_bytes + 64))) return rc;
+        if ((rc = ensure_dev(c, cur_slot(c)->d_desc, 4096))) return rc;
+        if ((rc = ensure_host(c, cur_slot(c)->h_desc, 4096))) return rc;
+        uint8_t* din = (uint8_t*)cur_slot(c)->d_io_in.p;
+        cudaStream_t s = cur_slot(c)->stream;
+        memcpy(cur_slot(c)->h_desc.p, st->acc, 16);
+        if (head_full) memcpy((uint8_t*)cur_slot(c)->h_desc.p + 16, st->buf, 16);
+        LZF_CU(c, cudaMemcpyAsync(cur_slot(c)->d_desc.p, cur_slot(c)->h_desc.p, 32, cudaMemcpyHostToDevice, s));
+        if (head_full) LZF_CU(c, cudaMemcpyAsync(din, (uint8_t*)cur_slot(c)->d_desc.p + 16, 16, cudaMemcpyDeviceToDevice, s));
         if (body) LZF_CU(c, cudaMemcpyAsync(din + (head_full ? 16 : 0), data + head, body, cudaMemcpyHostToDevice, s));
-        LZF_LAUNCHED(c, lzf_launch_xxh32_stripes(din, dev_bytes / 16, (uint32_t*)c->cur->d_desc.p, s), 1);
-        LZF_CU(c, cudaMemcpyAsync(c->cur->h_desc.p, c->cur->d_desc.p, 16, cudaMemcpyDeviceToHost, s));
+        LZF_LAUNCHED(c, lzf_launch_xxh32_stripes(din, dev_bytes / 16, (uint32_t*)cur_slot(c)->d_desc.p, s), 1);
+        LZF_CU(c, cudaMemcpyAsync(cur_slot(c)->h_desc.p, cur_slot(c)->d_desc.p, 16, cudaMemcpyDeviceToHost, s));
         LZF_CU(c, cudaStreamSynchronize(s));
-        memcpy(st->acc, c->cur->h_desc.p, 16);
+        memcpy(st->acc, cur_slot(c)->h_desc.p, 16);
     }
     if (head_full) st->buflen = 0;
     memcpy(st->buf, data + head + body, tail);
@@ -344,21 +352,21 @@ extern "C" int lzf_raw_compress_into(lzf_ctx* c, const uint8_t* in, size_t n, ui
     LZF_CU(c, cudaSetDevice(c->device));
     const size_t capc = cap > 0xffffffffull ? 0xffffffffull : cap;
     int rc;
-    if ((rc = ensure_dev(c, c->cur->d_io_in, n + 64))) return rc;
-    if ((rc = ensure_dev(c, c->cur->d_io_out, capc + 64))) return rc;
-    if ((rc = ensure_dev(c, c->cur->d_desc, 4096))) return rc;
-    if ((rc = ensure_host(c, c->cur->h_desc, 4096))) return rc;
-    uint8_t* h = (uint8_t*)c->cur->h_desc.p;
-    uint8_t* d = (uint8_t*)c->cur->d_desc.p;
+    if ((rc = ensure_dev(c, cur_slot(c)->d_io_in, n + 64))) return rc;
+    if ((rc = ensure_dev(c, cur_slot(c)->d_io_out, capc + 64))) return rc;
+    if ((rc = ensure_dev(c, cur_slot(c)->d_desc, 4096))) return rc;
+    if ((rc = ensure_host(c, cur_slot(c)->h_desc, 4096))) return rc;
+    uint8_t* h = (uint8_t*)cur_slot(c)->h_desc.p;
+    uint8_t* d = (uint8_t*)cur_slot(c)->d_desc.p;
     // layout: in_off u64 @0, out_off u64 @8, in_len u32 @16, out_cap u32 @20 | results: out_len u32 @64, status i32 @68
     memset(h, 0, 128);
     *(uint32_t*)(h + 16) = (uint32_t)n;
     *(uint32_t*)(h + 20) = (uint32_t)capc;
-    cudaStream_t s = c->cur->stream;
+    cudaStream_t s = cur_slot(c)->stream;
     LZF_CU(c, cudaMemcpyAsync(d, h, 128, cudaMemcpyHostToDevice, s));
-    if (n) LZF_CU(c, cudaMemcpyAsync(c->cur->d_io_in.p, in, n, cudaMemcpyHostToDevice, s));
-    rc = compress_blocks_impl(c, (const uint8_t*)c->cur->d_io_in.p, (const uint64_t*)d, (const uint32_t*)(d + 16), 1, hashlog,
-                              table_kind, (uint32_t)n, (uint8_t*)c->cur->d_io_out.p, (const uint64_t*)(d + 8),
+    if (n) LZF_CU(c, cudaMemcpyAsync(cur_slot(c)->d_io_in.p, in, n, cudaMemcpyHostToDevice, s));
+    rc = compress_blocks_impl(c, (const uint8_t*)cur_slot(c)->d_io_in.p, (const uint64_t*)d, (const uint32_t*)(d + 16), 1, hashlog,
+                              table_kind, (uint32_t)n, (uint8_t*)cur_slot(c)->d_io_out.p, (const uint64_t*)(d + 8),
                               (const uint32_t*)(d + 20), (uint32_t*)(d + 64), (int32_t*)(d + 68), nullptr, nullptr, s);
     if (rc) return rc;
     LZF_CU(c, cudaMemcpyAsync(h + 64, d + 64, 8, cudaMemcpyDeviceToHost, s));
@@ -366,7 +374,7 @@ extern "C" int lzf_raw_compress_into(lzf_ctx* c, const uint8_t* in, size_t n, ui
     const uint32_t olen = *(uint32_t*)(h + 64);
     *status = *(int32_t*)(h + 68);
     if (*status == LZF_OK && olen) {
-        LZF_CU(c, cudaMemcpyAsync(out, c->cur->d_io_out.p, olen, cudaMemcpyDeviceToHost, s));
+        LZF_CU(c, cudaMemcpyAsync(out, cur_slot(c)->d_io_out.p, olen, cudaMemcpyDeviceToHost, s));
         LZF_CU(c, cudaStreamSynchronize(s));
     }
     *written = *status == LZF_OK ? olen : 0;
@@ -383,12 +391,12 @@ extern "C" int lzf_raw_decompress(lzf_ctx* c, const uint8_t* in, size_t n, const
     const size_t capc = out_cap > 0xffffffffull ? 0xffffffffull : out_cap;
     const size_t limc = out_limit > 0xffffffffull ? 0xffffffffull : out_limit;
     int rc;
-    if ((rc = ensure_dev(c, c->cur->d_io_in, n + plen + 128))) return rc;
-    if ((rc = ensure_dev(c, c->cur->d_io_out, capc + 64))) return rc;
-    if ((rc = ensure_dev(c, c->cur->d_desc, 4096))) return rc;
-    if ((rc = ensure_host(c, c->cur->h_desc, 4096))) return rc;
-    uint8_t* h = (uint8_t*)c->cur->h_desc.p;
-    uint8_t* d = (uint8_t*)c->cur->d_desc.p;
+    if ((rc = ensure_dev(c, cur_slot(c)->d_io_in, n + plen + 128))) return rc;
+    if ((rc = ensure_dev(c, cur_slot(c)->d_io_out, capc + 64))) return rc;
+    if ((rc = ensure_dev(c, cur_slot(c)->d_desc, 4096))) return rc;
+    if ((rc = ensure_host(c, cur_slot(c)->h_desc, 4096))) return rc;
+    uint8_t* h = (uint8_t*)cur_slot(c)->h_desc.p;
+    uint8_t* d = (uint8_t*)cur_slot(c)->d_desc.p;
     const size_t poff = (n + 63) / 64 * 64;
     // in_off @0, out_off @8, prefix_off @16, in_len @24, out_cap @28, out_limit @32, prefix_len @36 | out_len @64, status @68
     memset(h, 0, 128);
@@ -397,13 +405,13 @@ extern "C" int lzf_raw_decompress(lzf_ctx* c, const uint8_t* in, size_t n, const
     *(uint32_t*)(h + 28) = (uint32_t)capc;
     *(uint32_t*)(h + 32) = (uint32_t)limc;
     *(uint32_t*)(h + 36) = (uint32_t)plen;
-    cudaStream_t s = c->cur->stream;
+    cudaStream_t s = cur_slot(c)->stream;
     LZF_CU(c, cudaMemcpyAsync(d, h, 128, cudaMemcpyHostToDevice, s));
-    uint8_t* din = (uint8_t*)c->cur->d_io_in.p;
+    uint8_t* din = (uint8_t*)cur_slot(c)->d_io_in.p;
     if (n) LZF_CU(c, cudaMemcpyAsync(din, in, n, cudaMemcpyHostToDevice, s));
     if (plen) LZF_CU(c, cudaMemcpyAsync(din + poff, prefix, plen, cudaMemcpyHostToDevice, s));
     rc = decompress_blocks_impl(c, din, (const uint64_t*)d, (const uint32_t*)(d + 24), 1, plen ? din : nullptr,
-                                (const uint64_t*)(d + 16), (const uint32_t*)(d + 36), (uint8_t*)c->cur->d_io_out.p,
+                                (const uint64_t*)(d + 16), (const uint32_t*)(d + 36), (uint8_t*)cur_slot(c)->d_io_out.p,
                                 (const uint64_t*)(d + 8), (const uint32_t*)(d + 28), (const uint32_t*)(d + 32),
                                 (uint32_t*)(d + 64), (int32_t*)(d + 68), nullptr, s);
     if (rc) return rc;
@@ -413,7 +421,7 @@ extern "C" int lzf_raw_decompress(lzf_ctx* c, const uint8_t* in, size_t n, const
     *status = *(int32_t*)(h + 68);
     const size_t ncopy = olen < capc ? olen : capc;
     if (ncopy) {
-        LZF_CU(c, cudaMemcpyAsync(out, c->cur->d_io_out.p, ncopy, cudaMemcpyDeviceToHost, s));
+        LZF_CU(c, cudaMemcpyAsync(out, cur_slot(c)->d_io_out.p, ncopy, cudaMemcpyDeviceToHost, s));
         LZF_CU(c, cudaStreamSynchronize(s));
     }
     *out_len = olen;
@@ -518,13 +526,13 @@ int frames_compress_core(lzf_ctx* c, const lzf_settings* s, const uint8_t* d_in,
     const size_t r_host_lo = r_flen, r_host_hi = ra.used;   // only frame_len + frame_status travel back
 
     int rc;
-    if ((rc = ensure_host(c, c->cur->h_desc, da.used))) return rc;
-    if ((rc = ensure_dev(c, c->cur->d_desc, da.used))) return rc;
-    if ((rc = ensure_dev(c, c->cur->d_res, ra.used))) return rc;
-    if ((rc = ensure_host(c, c->cur->h_res, ra.used))) return rc;
-    uint8_t* h = (uint8_t*)c->cur->h_desc.p;
-    uint8_t* d = (uint8_t*)c->cur->d_desc.p;
-    uint8_t* r = (uint8_t*)c->cur->d_res.p;
+    if ((rc = ensure_host(c, cur_slot(c)->h_desc, da.used))) return rc;
+    if ((rc = ensure_dev(c, cur_slot(c)->d_desc, da.used))) return rc;
+    if ((rc = ensure_dev(c, cur_slot(c)->d_res, ra.used))) return rc;
+    if ((rc = ensure_host(c, cur_slot(c)->h_res, ra.used))) return rc;
+    uint8_t* h = (uint8_t*)cur_slot(c)->h_desc.p;
+    uint8_t* d = (uint8_t*)cur_slot(c)->d_desc.p;
+    uint8_t* r = (uint8_t*)cur_slot(c)->d_res.p;
 
     uint32_t* first = (uint32_t*)(h + o_first); uint32_t* nblk = (uint32_t*)(h + o_nblk);
     uint8_t* hdrs = h + o_hdr;
@@ -556,25 +564,25 @@ int frames_compress_core(lzf_ctx* c, const lzf_settings* s, const uint8_t* d_in,
             if (l > max_block_len) max_block_len = l;
         }
     }
-    if ((rc = ensure_dev(c, c->cur->d_comp, comp_total + 64))) return rc;
+    if ((rc = ensure_dev(c, cur_slot(c)->d_comp, comp_total + 64))) return rc;
 
     LZF_CU(c, cudaMemcpyAsync(d, h, da.used, cudaMemcpyHostToDevice, st));
     // content checksum of each frame's plaintext (compress.rs:172,233-235,279-281) on the side stream
     if (s->content_checksum) {
-        LZF_CU(c, cudaEventRecord(c->cur->ev_fork, st));
-        LZF_CU(c, cudaStreamWaitEvent(c->cur->side, c->cur->ev_fork, 0));
+        LZF_CU(c, cudaEventRecord(cur_slot(c)->ev_fork, st));
+        LZF_CU(c, cudaStreamWaitEvent(cur_slot(c)->side, cur_slot(c)->ev_fork, 0));
         LZF_LAUNCHED(c, lzf_launch_xxh32_ranges(d_in, (const uint64_t*)(d + o_hoff), (const uint64_t*)(d + o_hlen), nframes,
-                                               (uint32_t*)(r + r_chash), c->cur->side), 1);
-        LZF_CU(c, cudaEventRecord(c->cur->ev_join, c->cur->side));
+                                               (uint32_t*)(r + r_chash), cur_slot(c)->side), 1);
+        LZF_CU(c, cudaEventRecord(cur_slot(c)->ev_join, cur_slot(c)->side));
     }
     if (nblocks) {
         rc = compress_blocks_impl(c, d_in, (const uint64_t*)(d + o_bin_off), (const uint32_t*)(d + o_bin_len), nblocks,
-                                  hashlog, LZF_TABLE_U32, max_block_len, (uint8_t*)c->cur->d_comp.p,
+                                  hashlog, LZF_TABLE_U32, max_block_len, (uint8_t*)cur_slot(c)->d_comp.p,
                                   (const uint64_t*)(d + o_bc_off), nullptr, (uint32_t*)(r + r_clen), (int32_t*)(r + r_bst),
                                   nullptr, s->block_checksums ? (uint32_t*)(r + r_xs) : nullptr, st);
         if (rc) return rc;
     }
-    if (s->content_checksum) LZF_CU(c, cudaStreamWaitEvent(st, c->cur->ev_join, 0));
+    if (s->content_checksum) LZF_CU(c, cudaStreamWaitEvent(st, cur_slot(c)->ev_join, 0));
     lzf::LayoutArgs la;
     memset(&la, 0, sizeof(la));
     la.nframes = nframes;
@@ -593,13 +601,13 @@ int frames_compress_core(lzf_ctx* c, const lzf_settings* s, const uint8_t* d_in,
         memset(&aa, 0, sizeof(aa));
         aa.nblocks = nblocks;
         aa.in = d_in; aa.blk_in_off = (const uint64_t*)(d + o_bin_off); aa.blk_in_len = (const uint32_t*)(d + o_bin_len);
-        aa.comp = (const uint8_t*)c->cur->d_comp.p; aa.blk_comp_off = (const uint64_t*)(d + o_bc_off);
+        aa.comp = (const uint8_t*)cur_slot(c)->d_comp.p; aa.blk_comp_off = (const uint64_t*)(d + o_bc_off);
         aa.blk_comp_len = (const uint32_t*)(r + r_clen); aa.blk_status = (const int32_t*)(r + r_bst);
         aa.blk_xxh_stored = s->block_checksums ? (const uint32_t*)(r + r_xs) : nullptr;
         aa.blk_dst = (const uint64_t*)(r + r_dst); aa.out = d_out;
         LZF_LAUNCHED(c, lzf_launch_assemble(&aa, max_block_len, st), 1);
     }
-    uint8_t* hr = (uint8_t*)c->cur->h_res.p;
+    uint8_t* hr = (uint8_t*)cur_slot(c)->h_res.p;
     LZF_CU(c, cudaMemcpyAsync(hr + r_host_lo, r + r_host_lo, r_host_hi - r_host_lo, cudaMemcpyDeviceToHost, st));
     LZF_CU(c, cudaStreamSynchronize(st));
     const uint64_t* flen = (const uint64_t*)(hr + r_flen);
@@ -636,10 +644,10 @@ int frames_decompress_core(lzf_ctx* c, const uint8_t* d_in, const uint64_t* in_o
     const size_t o_first = da.take((size_t)nframes * 4), o_nblk = da.take((size_t)nframes * 4);
     const size_t o_hoff = da.take((size_t)nframes * 8), o_hlen = da.take((size_t)nframes * 8);
     const size_t frame_desc_bytes = da.used;
-    if ((rc = ensure_host(c, c->cur->h_desc, da.used))) return rc;
-    if ((rc = ensure_dev(c, c->cur->d_desc, da.used))) return rc;
-    uint8_t* h = (uint8_t*)c->cur->h_desc.p;
-    uint8_t* d = (uint8_t*)c->cur->d_desc.p;
+    if ((rc = ensure_host(c, cur_slot(c)->h_desc, da.used))) return rc;
+    if ((rc = ensure_dev(c, cur_slot(c)->d_desc, da.used))) return rc;
+    uint8_t* h = (uint8_t*)cur_slot(c)->h_desc.p;
+    uint8_t* d = (uint8_t*)cur_slot(c)->d_desc.p;
     memcpy(h + o_ioff, in_off, (size_t)nframes * 8);
     memcpy(h + o_ilen, in_len, (size_t)nframes * 8);
     memcpy(h + o_ooff, out_off, (size_t)nframes * 8);
@@ -647,20 +655,20 @@ int frames_decompress_core(lzf_ctx* c, const uint8_t* d_in, const uint64_t* in_o
 
     Arena ra;
     const size_t r_walk = ra.take((size_t)nframes * sizeof(lzf::WalkFrame));
-    if ((rc = ensure_dev(c, c->cur->d_res, ra.used))) return rc;
-    if ((rc = ensure_host(c, c->cur->h_res, ra.used))) return rc;
+    if ((rc = ensure_dev(c, cur_slot(c)->d_res, ra.used))) return rc;
+    if ((rc = ensure_host(c, cur_slot(c)->h_res, ra.used))) return rc;
     LZF_CU(c, cudaMemcpyAsync(d, h, o_first, cudaMemcpyHostToDevice, st));
     lzf::WalkArgs wa;
     memset(&wa, 0, sizeof(wa));
     wa.nframes = nframes; wa.mode = 0;
     wa.in = d_in; wa.in_off = (const uint64_t*)(d + o_ioff); wa.in_len = (const uint64_t*)(d + o_ilen);
-    wa.frames = (lzf::WalkFrame*)((uint8_t*)c->cur->d_res.p + r_walk);
+    wa.frames = (lzf::WalkFrame*)((uint8_t*)cur_slot(c)->d_res.p + r_walk);
     LZF_LAUNCHED(c, lzf_launch_walk(&wa, st), 1);
     std::vector<lzf::WalkFrame> wf(nframes);
-    LZF_CU(c, cudaMemcpyAsync(c->cur->h_res.p, (uint8_t*)c->cur->d_res.p + r_walk, (size_t)nframes * sizeof(lzf::WalkFrame),
+    LZF_CU(c, cudaMemcpyAsync(cur_slot(c)->h_res.p, (uint8_t*)cur_slot(c)->d_res.p + r_walk, (size_t)nframes * sizeof(lzf::WalkFrame),
                               cudaMemcpyDeviceToHost, st));
     LZF_CU(c, cudaStreamSynchronize(st));
-    memcpy(wf.data(), c->cur->h_res.p, (size_t)nframes * sizeof(lzf::WalkFrame));
+    memcpy(wf.data(), cur_slot(c)->h_res.p, (size_t)nframes * sizeof(lzf::WalkFrame));
 
     uint64_t nblocks64 = 0;
     bool any_dependent = false;
@@ -691,17 +699,17 @@ int frames_decompress_core(lzf_ctx* c, const uint8_t* d_in, const uint64_t* in_o
     const size_t r_bxxh = rb.take((size_t)nblocks * 4), r_bcks = rb.take((size_t)nblocks * 4);
     const size_t r_bend = rb.take((size_t)nblocks * 8);
     const size_t r_chash = rb.take((size_t)nframes * 4);
-    if (ba.used > c->cur->d_desc.cap) {
+    if (ba.used > cur_slot(c)->d_desc.cap) {
         // growing d_desc would drop the frame arrays: re-upload them afterwards
-        if ((rc = ensure_dev(c, c->cur->d_desc, ba.used))) return rc;
-        d = (uint8_t*)c->cur->d_desc.p;
+        if ((rc = ensure_dev(c, cur_slot(c)->d_desc, ba.used))) return rc;
+        d = (uint8_t*)cur_slot(c)->d_desc.p;
         LZF_CU(c, cudaMemcpyAsync(d, h, o_first, cudaMemcpyHostToDevice, st));
         wa.in_off = (const uint64_t*)(d + o_ioff); wa.in_len = (const uint64_t*)(d + o_ilen);
     }
-    if ((rc = ensure_dev(c, c->cur->d_res, rb.used))) return rc;
-    if ((rc = ensure_host(c, c->cur->h_res, rb.used))) return rc;
-    uint8_t* r = (uint8_t*)c->cur->d_res.p;
-    uint8_t* hr = (uint8_t*)c->cur->h_res.p;
+    if ((rc = ensure_dev(c, cur_slot(c)->d_res, rb.used))) return rc;
+    if ((rc = ensure_host(c, cur_slot(c)->h_res, rb.used))) return rc;
+    uint8_t* r = (uint8_t*)cur_slot(c)->d_res.p;
+    uint8_t* hr = (uint8_t*)cur_slot(c)->h_res.p;
     LZF_CU(c, cudaMemcpyAsync(d + o_first, h + o_first, o_hoff - o_first, cudaMemcpyHostToDevice, st));
 
     bool any_block_checksums = false;
@@ -821,8 +829,8 @@ int frames_decompress_core(lzf_ctx* c, const uint8_t* d_in, const uint64_t* in_o
                 o += b_olen[b];
             }
         }
-        if ((rc = ensure_dev(c, c->cur->d_comp, xa.used))) return rc;     // scratch free on this path
-        uint8_t* x = (uint8_t*)c->cur->d_comp.p;
+        if ((rc = ensure_dev(c, cur_slot(c)->d_comp, xa.used))) return rc;     // scratch free on this path
+        uint8_t* x = (uint8_t*)cur_slot(c)->d_comp.p;
         LZF_CU(c, cudaMemcpyAsync(x, xh.data(), xa.used, cudaMemcpyHostToDevice, st));
         rc = decompress_blocks_impl(c, d_in, (const uint64_t*)(x + x_in_off), (const uint32_t*)(x + x_word), nredo,
                                     nullptr, nullptr, nullptr, d_out, (const uint64_t*)(x + x_out_off),
@@ -882,7 +890,7 @@ extern "C" int lzf_frames_compress_device(lzf_ctx* c, const lzf_settings* s, con
                                           int32_t* status) {
     if (!c) return LZF_ERR_INVALID_ARG;
     LZF_CU(c, cudaSetDevice(c->device));
-    return frames_compress_core(c, s, d_in, in_off, in_len, nframes, d_out, out_off, out_cap, out_len, status, c->cur->stream);
+    return frames_compress_core(c, s, d_in, in_off, in_len, nframes, d_out, out_off, out_cap, out_len, status, cur_slot(c)->stream);
 }
 
 namespace {
@@ -900,35 +908,70 @@ std::vector<uint32_t> plan_chunks(const uint64_t* len, uint32_t n, uint64_t targ
     return start;
 }
 
-struct CompressChunk {      // per-slot state of the host-buffer compress pipeline
-    uint32_t f0 = 0, f1 = 0;
-    HostLayout li, lo;
-    std::vector<uint64_t> dcap;
-};
+// Runs `work(i)` for every chunk on up to kSlots host threads, each bound to its own pipeline slot
+// (stream + scratch).  Every worker is synchronous on its own stream; the overlap of the H2D copy of
+// one chunk with the kernels of another and the D2H copy of a third comes from the streams running
+// side by side, and kernels of different chunks share the SMs.
+template <typename F>
+int run_chunks(lzf_ctx* c, uint32_t nchunks, F work) {
+    if (nchunks == 0) return LZF_SUCCESS;
+    std::atomic<uint32_t> next{0};
+    std::atomic<int> rc_all{LZF_SUCCESS};
+    auto worker = [&](int k) {
+        cudaSetDevice(c->device);
+        tls_slot = &c->slots[k];
+        for (;;) {
+            const uint32_t i = next.fetch_add(1);
+            if (i >= nchunks || rc_all.load() != LZF_SUCCESS) break;
+            const int rc = work(i, c->slots[k]);
+            if (rc != LZF_SUCCESS) rc_all.store(rc);
+        }
+        cudaStreamSynchronize(c->slots[k].stream);
+        tls_slot = nullptr;
+    };
+#ifdef LZF_SIMT_EMU
+    const uint32_t nworkers = 1;                 // the CPU SIMT test harness is single-threaded
+#else
+    const uint32_t nworkers = nchunks < (uint32_t)kSlots ? nchunks : (uint32_t)kSlots;
+#endif
+    std::vector<std::thread> threads;
+    for (uint32_t k = 1; k < nworkers; k++) threads.emplace_back(worker, (int)k);
+    worker(0);
+    for (auto& t : threads) t.join();
+    return rc_all.load();
+}
 
-int compress_chunk_upload(lzf_ctx* c, lzf_slot& sl, CompressChunk& ch, const lzf_settings* s, const uint8_t* in,
-                          const uint64_t* in_off, const uint64_t* in_len, const uint64_t* out_off, const uint64_t* out_cap) {
-    const uint32_t n = ch.f1 - ch.f0;
-    ch.dcap.resize(n);
+int compress_chunk(lzf_ctx* c, lzf_slot& sl, const lzf_settings* s, uint32_t f0, uint32_t f1, const uint8_t* in,
+                   const uint64_t* in_off, const uint64_t* in_len, uint8_t* out, const uint64_t* out_off,
+                   const uint64_t* out_cap, uint64_t* out_len, int32_t* status) {
+    const uint32_t n = f1 - f0;
+    std::vector<uint64_t> dcap(n);
     for (uint32_t f = 0; f < n; f++) {
-        const uint64_t need = lzf_frame_bound(s, in_len[ch.f0 + f]);
-        ch.dcap[f] = out_cap[ch.f0 + f] < need ? out_cap[ch.f0 + f] : need;
+        const uint64_t need = lzf_frame_bound(s, in_len[f0 + f]);
+        dcap[f] = out_cap[f0 + f] < need ? out_cap[f0 + f] : need;
     }
-    ch.li = plan_layout(in_off + ch.f0, in_len + ch.f0, n);
-    ch.lo = plan_layout(out_off + ch.f0, ch.dcap.data(), n);
-    lzf_slot* saved = c->cur;
-    c->cur = &sl;
+    const HostLayout li = plan_layout(in_off + f0, in_len + f0, n);
+    const HostLayout lo = plan_layout(out_off + f0, dcap.data(), n);
     int rc;
-    if ((rc = ensure_dev(c, sl.d_io_in, ch.li.span + 256)) || (rc = ensure_dev(c, sl.d_io_out, ch.lo.span + 256))) { c->cur = saved; return rc; }
-    c->cur = saved;
+    if ((rc = ensure_dev(c, sl.d_io_in, li.span + 256))) return rc;
+    if ((rc = ensure_dev(c, sl.d_io_out, lo.span + 256))) return rc;
     uint8_t* din = (uint8_t*)sl.d_io_in.p;
-    if (ch.li.dense) {
-        if (ch.li.span) LZF_CU(c, cudaMemcpyAsync(din, in + ch.li.base, ch.li.span, cudaMemcpyHostToDevice, sl.stream));
+    const uint8_t* dout = (const uint8_t*)sl.d_io_out.p;
+    if (li.dense) {
+        if (li.span) LZF_CU(c, cudaMemcpyAsync(din, in + li.base, li.span, cudaMemcpyHostToDevice, sl.stream));
     } else {
         for (uint32_t f = 0; f < n; f++)
-            if (in_len[ch.f0 + f])
-                LZF_CU(c, cudaMemcpyAsync(din + ch.li.dev_off[f], in + in_off[ch.f0 + f], in_len[ch.f0 + f], cudaMemcpyHostToDevice, sl.stream));
+            if (in_len[f0 + f])
+                LZF_CU(c, cudaMemcpyAsync(din + li.dev_off[f], in + in_off[f0 + f], in_len[f0 + f], cudaMemcpyHostToDevice, sl.stream));
     }
+    rc = frames_compress_core(c, s, din, li.dev_off.data(), in_len + f0, n, (uint8_t*)sl.d_io_out.p, lo.dev_off.data(),
+                              dcap.data(), out_len + f0, status + f0, sl.stream);
+    if (rc) return rc;
+    // compressed frames are much shorter than their capacity: copy each frame's bytes
+    for (uint32_t f = f0; f < f1; f++)
+        if (status[f] == LZF_F_OK && out_len[f])
+            LZF_CU(c, cudaMemcpyAsync(out + out_off[f], dout + lo.dev_off[f - f0], out_len[f], cudaMemcpyDeviceToHost, sl.stream));
+    LZF_CU(c, cudaStreamSynchronize(sl.stream));
     return LZF_SUCCESS;
 }
 
@@ -942,39 +985,9 @@ extern "C" int lzf_frames_compress(lzf_ctx* c, const lzf_settings* s, const uint
         return fail(c, LZF_ERR_INVALID_ARG, "null pointer");
     LZF_CU(c, cudaSetDevice(c->device));
     const std::vector<uint32_t> chunks = plan_chunks(in_len, nframes, c->compress_chunk_bytes);
-    const uint32_t nchunks = (uint32_t)chunks.size() - 1;
-    CompressChunk st[kSlots];
-    int rc = LZF_SUCCESS;
-    // software pipeline: upload(i+1) is queued before the host blocks in the kernels of chunk i,
-    // and the download of chunk i stays in flight while chunk i+1 computes
-    if (nchunks) {
-        st[0].f0 = chunks[0]; st[0].f1 = chunks[1];
-        rc = compress_chunk_upload(c, c->slots[0], st[0], s, in, in_off, in_len, out_off, out_cap);
-    }
-    for (uint32_t i = 0; i < nchunks && rc == LZF_SUCCESS; i++) {
-        lzf_slot& sl = c->slots[i % kSlots];
-        CompressChunk& ch = st[i % kSlots];
-        if (i + 1 < nchunks) {
-            lzf_slot& nx = c->slots[(i + 1) % kSlots];
-            LZF_CU(c, cudaStreamSynchronize(nx.stream));          // its previous download (chunk i-2) is long done
-            CompressChunk& nc = st[(i + 1) % kSlots];
-            nc.f0 = chunks[i + 1]; nc.f1 = chunks[i + 2];
-            if ((rc = compress_chunk_upload(c, nx, nc, s, in, in_off, in_len, out_off, out_cap))) break;
-        }
-        c->cur = &sl;
-        rc = frames_compress_core(c, s, (const uint8_t*)sl.d_io_in.p, ch.li.dev_off.data(), in_len + ch.f0, ch.f1 - ch.f0,
-                                  (uint8_t*)sl.d_io_out.p, ch.lo.dev_off.data(), ch.dcap.data(), out_len + ch.f0,
-                                  status + ch.f0, sl.stream);
-        if (rc) break;
-        // compressed frames are much shorter than their capacity: copy each frame's bytes
-        const uint8_t* dout = (const uint8_t*)sl.d_io_out.p;
-        for (uint32_t f = ch.f0; f < ch.f1; f++)
-            if (status[f] == LZF_F_OK && out_len[f])
-                LZF_CU(c, cudaMemcpyAsync(out + out_off[f], dout + ch.lo.dev_off[f - ch.f0], out_len[f], cudaMemcpyDeviceToHost, sl.stream));
-    }
-    for (int i = 0; i < kSlots; i++) cudaStreamSynchronize(c->slots[i].stream);
-    c->cur = &c->slots[0];
-    return rc;
+    return run_chunks(c, (uint32_t)chunks.size() - 1, [&](uint32_t i, lzf_slot& sl) {
+        return compress_chunk(c, sl, s, chunks[i], chunks[i + 1], in, in_off, in_len, out, out_off, out_cap, out_len, status);
+    });
 }
 
 extern "C" int lzf_frame_compress(lzf_ctx* c, const lzf_settings* s, const uint8_t* in, size_t n,
@@ -993,42 +1006,50 @@ extern "C" int lzf_frames_decompress_device(lzf_ctx* c, const uint8_t* d_in, con
     if (!c) return LZF_ERR_INVALID_ARG;
     LZF_CU(c, cudaSetDevice(c->device));
     DecodeOut ex{nullptr, detail};
-    return frames_decompress_core(c, d_in, in_off, in_len, nframes, d_out, out_off, out_cap, out_len, status, ex, c->cur->stream);
+    return frames_decompress_core(c, d_in, in_off, in_len, nframes, d_out, out_off, out_cap, out_len, status, ex, cur_slot(c)->stream);
 }
 
 namespace {
 
-struct DecompressChunk {
-    uint32_t f0 = 0, f1 = 0;
-    HostLayout li, lo;
-    std::vector<uint64_t> dcap;
-};
-
-int decompress_chunk_upload(lzf_ctx* c, lzf_slot& sl, DecompressChunk& ch, const uint8_t* in, const uint64_t* in_off,
-                            const uint64_t* in_len, const uint64_t* out_off, const uint64_t* out_cap) {
-    const uint32_t n = ch.f1 - ch.f0;
-    ch.dcap.resize(n);
+int decompress_chunk(lzf_ctx* c, lzf_slot& sl, uint32_t f0, uint32_t f1, const uint8_t* in, const uint64_t* in_off,
+                     const uint64_t* in_len, uint8_t* out, const uint64_t* out_off, const uint64_t* out_cap,
+                     uint64_t* out_len, int32_t* status, int32_t* detail, uint64_t* consumed) {
+    const uint32_t n = f1 - f0;
+    std::vector<uint64_t> dcap(n);
     for (uint32_t f = 0; f < n; f++) {
         // a frame of C bytes decodes to at most ~C/5 blocks of <= 4 MiB; the device copy of the output
         // is bounded by what the caller can take anyway
-        const uint64_t worst = (in_len[ch.f0 + f] / 5 + 1) * (4ull << 20);
-        ch.dcap[f] = out_cap[ch.f0 + f] < worst ? out_cap[ch.f0 + f] : worst;
+        const uint64_t worst = (in_len[f0 + f] / 5 + 1) * (4ull << 20);
+        dcap[f] = out_cap[f0 + f] < worst ? out_cap[f0 + f] : worst;
     }
-    ch.li = plan_layout(in_off + ch.f0, in_len + ch.f0, n);
-    ch.lo = plan_layout(out_off + ch.f0, ch.dcap.data(), n);
-    lzf_slot* saved = c->cur;
-    c->cur = &sl;
+    const HostLayout li = plan_layout(in_off + f0, in_len + f0, n);
+    const HostLayout lo = plan_layout(out_off + f0, dcap.data(), n);
     int rc;
-    if ((rc = ensure_dev(c, sl.d_io_in, ch.li.span + 256)) || (rc = ensure_dev(c, sl.d_io_out, ch.lo.span + 256))) { c->cur = saved; return rc; }
-    c->cur = saved;
+    if ((rc = ensure_dev(c, sl.d_io_in, li.span + 256))) return rc;
+    if ((rc = ensure_dev(c, sl.d_io_out, lo.span + 256))) return rc;
     uint8_t* din = (uint8_t*)sl.d_io_in.p;
-    if (ch.li.dense) {
-        if (ch.li.span) LZF_CU(c, cudaMemcpyAsync(din, in + ch.li.base, ch.li.span, cudaMemcpyHostToDevice, sl.stream));
+    const uint8_t* dout = (const uint8_t*)sl.d_io_out.p;
+    if (li.dense) {
+        if (li.span) LZF_CU(c, cudaMemcpyAsync(din, in + li.base, li.span, cudaMemcpyHostToDevice, sl.stream));
     } else {
         for (uint32_t f = 0; f < n; f++)
-            if (in_len[ch.f0 + f])
-                LZF_CU(c, cudaMemcpyAsync(din + ch.li.dev_off[f], in + in_off[ch.f0 + f], in_len[ch.f0 + f], cudaMemcpyHostToDevice, sl.stream));
+            if (in_len[f0 + f])
+                LZF_CU(c, cudaMemcpyAsync(din + li.dev_off[f], in + in_off[f0 + f], in_len[f0 + f], cudaMemcpyHostToDevice, sl.stream));
     }
+    DecodeOut ex{consumed ? consumed + f0 : nullptr, detail ? detail + f0 : nullptr};
+    rc = frames_decompress_core(c, din, li.dev_off.data(), in_len + f0, n, (uint8_t*)sl.d_io_out.p, lo.dev_off.data(),
+                                dcap.data(), out_len + f0, status + f0, ex, sl.stream);
+    if (rc) return rc;
+    bool full = lo.dense;      // every frame filled its capacity exactly: one copy moves the whole run
+    for (uint32_t f = f0; f < f1 && full; f++) full = out_len[f] == dcap[f - f0];
+    if (full) {
+        if (lo.span) LZF_CU(c, cudaMemcpyAsync(out + lo.base, dout, lo.span, cudaMemcpyDeviceToHost, sl.stream));
+    } else {
+        for (uint32_t f = f0; f < f1; f++)
+            if (out_len[f])
+                LZF_CU(c, cudaMemcpyAsync(out + out_off[f], dout + lo.dev_off[f - f0], out_len[f], cudaMemcpyDeviceToHost, sl.stream));
+    }
+    LZF_CU(c, cudaStreamSynchronize(sl.stream));
     return LZF_SUCCESS;
 }
 
@@ -1038,50 +1059,17 @@ int frames_decompress_host(lzf_ctx* c, const uint8_t* in, const uint64_t* in_off
     if (nframes && (!in_off || !in_len || !out_off || !out_cap || !out_len || !status))
         return fail(c, LZF_ERR_INVALID_ARG, "null pointer");
     LZF_CU(c, cudaSetDevice(c->device));
-    // chunk by output capacity (the larger side of a decode)
+    // chunk by compressed + plaintext bytes
     std::vector<uint64_t> weight(nframes);
     for (uint32_t f = 0; f < nframes; f++) {
         const uint64_t worst = (in_len[f] / 5 + 1) * (4ull << 20);
         weight[f] = in_len[f] + (out_cap[f] < worst ? out_cap[f] : worst);
     }
     const std::vector<uint32_t> chunks = plan_chunks(weight.data(), nframes, c->chunk_bytes);
-    const uint32_t nchunks = (uint32_t)chunks.size() - 1;
-    DecompressChunk st[kSlots];
-    int rc = LZF_SUCCESS;
-    if (nchunks) {
-        st[0].f0 = chunks[0]; st[0].f1 = chunks[1];
-        rc = decompress_chunk_upload(c, c->slots[0], st[0], in, in_off, in_len, out_off, out_cap);
-    }
-    for (uint32_t i = 0; i < nchunks && rc == LZF_SUCCESS; i++) {
-        lzf_slot& sl = c->slots[i % kSlots];
-        DecompressChunk& ch = st[i % kSlots];
-        if (i + 1 < nchunks) {
-            lzf_slot& nx = c->slots[(i + 1) % kSlots];
-            LZF_CU(c, cudaStreamSynchronize(nx.stream));
-            DecompressChunk& nc = st[(i + 1) % kSlots];
-            nc.f0 = chunks[i + 1]; nc.f1 = chunks[i + 2];
-            if ((rc = decompress_chunk_upload(c, nx, nc, in, in_off, in_len, out_off, out_cap))) break;
-        }
-        c->cur = &sl;
-        DecodeOut ex{consumed ? consumed + ch.f0 : nullptr, detail ? detail + ch.f0 : nullptr};
-        rc = frames_decompress_core(c, (const uint8_t*)sl.d_io_in.p, ch.li.dev_off.data(), in_len + ch.f0, ch.f1 - ch.f0,
-                                    (uint8_t*)sl.d_io_out.p, ch.lo.dev_off.data(), ch.dcap.data(), out_len + ch.f0,
-                                    status + ch.f0, ex, sl.stream);
-        if (rc) break;
-        const uint8_t* dout = (const uint8_t*)sl.d_io_out.p;
-        bool full = ch.lo.dense;      // every frame filled its capacity exactly: one copy moves the whole run
-        for (uint32_t f = ch.f0; f < ch.f1 && full; f++) full = out_len[f] == ch.dcap[f - ch.f0];
-        if (full) {
-            if (ch.lo.span) LZF_CU(c, cudaMemcpyAsync(out + ch.lo.base, dout, ch.lo.span, cudaMemcpyDeviceToHost, sl.stream));
-        } else {
-            for (uint32_t f = ch.f0; f < ch.f1; f++)
-                if (out_len[f])
-                    LZF_CU(c, cudaMemcpyAsync(out + out_off[f], dout + ch.lo.dev_off[f - ch.f0], out_len[f], cudaMemcpyDeviceToHost, sl.stream));
-        }
-    }
-    for (int i = 0; i < kSlots; i++) cudaStreamSynchronize(c->slots[i].stream);
-    c->cur = &c->slots[0];
-    return rc;
+    return run_chunks(c, (uint32_t)chunks.size() - 1, [&](uint32_t i, lzf_slot& sl) {
+        return decompress_chunk(c, sl, chunks[i], chunks[i + 1], in, in_off, in_len, out, out_off, out_cap, out_len, status,
+                                detail, consumed);
+    });
 }
 }  // namespace
 
