@@ -82,7 +82,8 @@ __device__ __forceinline__ uint32_t ld4(const uint8_t* in, uint32_t pos) {
 // One LZ4 sequence (write_group :150-163, or the literal-only tail :182-189 when `final`).
 // Returns false when the bounded writer would refuse it (NoPartialWrites, compress.rs:298-301).
 __device__ __forceinline__ bool emit_sequence(uint8_t* out, uint64_t& opos, uint64_t cap, const uint8_t* in,
-                                              uint32_t lit_start, uint32_t L, uint32_t offset, uint32_t extra, bool final) {
+                                              uint32_t lit_start, uint32_t L, uint32_t offset, uint32_t extra, bool final,
+                                              bool lits_in_regs, uint32_t v32, uint32_t first_lit_lane) {
     const unsigned lane = lane_id();
     const uint32_t ll = lsic_len(L), ml = final ? 0u : lsic_len(extra);
     const uint64_t total = 1ull + ll + L + (final ? 0u : 2u + ml);
@@ -91,11 +92,14 @@ __device__ __forceinline__ bool emit_sequence(uint8_t* out, uint64_t& opos, uint
     const uint8_t token = (uint8_t)(((L < 15 ? L : 15) << 4) | (final ? 0u : (extra < 15 ? extra : 15)));
     if (total <= 32) {
         // one byte per lane: token | lsic(L) | literals | offset | lsic(extra)
+        const uint32_t t = lane - 1 - ll;                         // literal index of this lane (when in range)
+        uint32_t litb = 0;
+        if (lits_in_regs) litb = __shfl_sync(LZF_FULL_MASK, v32, first_lit_lane + t) & 0xffu;   // lane of in[lit_start + t]
         if (lane < total) {
             uint8_t v;
             if (lane == 0) v = token;
             else if (lane < 1 + ll) v = (lane == ll) ? (uint8_t)((L - 15) % 255) : 0xff;
-            else if (lane < 1 + ll + L) v = __ldg(in + lit_start + (lane - 1 - ll));
+            else if (lane < 1 + ll + L) v = lits_in_regs ? (uint8_t)litb : __ldg(in + lit_start + t);
             else if (lane < 1 + ll + L + 2) v = (uint8_t)(offset >> (8 * (lane - 1 - ll - L)));
             else v = (lane == total - 1) ? (uint8_t)((extra - 15) % 255) : 0xff;
             o[lane] = v;
@@ -189,8 +193,64 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
                 const uint32_t same = __match_any_sync(LZF_FULL_MASK, h);
                 // table candidate: addressable (:200-201) and >= MINMATCH equal bytes (:206)
                 bool t_ok = false;
-                if (!is_end && p != 0 && p - tcand <= 0xffffu) t_ok = ld4(in, tcand) == v32;
+                // FAST-PATH SUMMARY (consecutive batches): each lane also fetches 16 bytes after and 4 bytes
+                // before its table candidate in the same round trip, and compares them with the bytes of its
+                // own position, which sit in the v32 registers of lanes +4, +8, +12 and -4.  If the lane later
+                // wins, its forward match length (up to 16) and backtrack (up to 4) are already known and the
+                // whole sequence is resolved with shuffles only — no further memory round trip.
+                //   fsum: bits 0..4 forward match length 4..16, bits 5..7 backtrack 0..4,
+                //         bit 8 forward summary valid, bit 9 backward summary valid
+                uint32_t fsum = 0;
+                uint32_t v_c1 = 0, v_c2 = 0, v_c3 = 0, v_cm1 = 0;
+                bool v_hasb = false, v_pre = false;
+                if (!is_end && p != 0 && p - tcand <= 0xffffu) {
+                    if (consecutive && tcand + 16 <= len) {
+                        const bool hasb = tcand >= 4;
+                        const uint32_t s0 = hasb ? tcand - 4 : tcand;
+                        const uintptr_t ad = reinterpret_cast<uintptr_t>(in + s0);
+                        const uint32_t* w = reinterpret_cast<const uint32_t*>(ad & ~uintptr_t(3));
+                        const unsigned sh = (unsigned)(ad & 3u) * 8u;
+                        const uint32_t nw = hasb ? 5u : 4u;                       // unaligned words wanted from s0
+                        uint32_t W[6];
+#pragma unroll
+                        for (int i = 0; i < 6; i++) W[i] = ((uint32_t)i < nw || ((uint32_t)i == nw && sh != 0)) ? __ldg(w + i) : 0u;
+                        uint32_t U[5];
+#pragma unroll
+                        for (int i = 0; i < 5; i++) U[i] = __funnelshift_r(W[i], W[i + 1], sh);
+                        const uint32_t cm1 = U[0];
+                        const uint32_t c0 = hasb ? U[1] : U[0], c1 = hasb ? U[2] : U[1], c2 = hasb ? U[3] : U[2], c3 = hasb ? U[4] : U[3];
+                        t_ok = c0 == v32;
+                        // park the candidate words for the comparison after the shuffles
+                        v_c1 = c1; v_c2 = c2; v_c3 = c3; v_cm1 = cm1; v_hasb = hasb; v_pre = true;
+                    } else {
+                        t_ok = ld4(in, tcand) == v32;
+                    }
+                }
                 const uint32_t base = __shfl_sync(LZF_FULL_MASK, p, 0);
+                if (consecutive) {
+                    const uint32_t a1 = __shfl_down_sync(LZF_FULL_MASK, v32, 4);
+                    const uint32_t a2 = __shfl_down_sync(LZF_FULL_MASK, v32, 8);
+                    const uint32_t a3 = __shfl_down_sync(LZF_FULL_MASK, v32, 12);
+                    const uint32_t am1 = __shfl_up_sync(LZF_FULL_MASK, v32, 4);
+                    if (v_pre && t_ok) {
+                        // forward: bytes p+4 .. p+15 live in lanes +4, +8, +12 (they must exist and hold data)
+                        if (lane + 12 < 32 && !((endmask >> (lane + 12)) & 1u)) {
+                            const uint32_t x1 = a1 ^ v_c1, x2 = a2 ^ v_c2, x3 = a3 ^ v_c3;
+                            uint32_t fm;
+                            if (x1) fm = 4 + ((uint32_t)(__ffs((int)x1) - 1) >> 3);
+                            else if (x2) fm = 8 + ((uint32_t)(__ffs((int)x2) - 1) >> 3);
+                            else if (x3) fm = 12 + ((uint32_t)(__ffs((int)x3) - 1) >> 3);
+                            else fm = 16;
+                            fsum |= fm | 0x100u;
+                        }
+                        // backward: bytes p-4 .. p-1 live in lane -4
+                        if (lane >= 4 && v_hasb) {
+                            const uint32_t xb = am1 ^ v_cm1;
+                            const uint32_t nb = xb ? (uint32_t)__clz((int)xb) >> 3 : 4u;
+                            fsum |= (nb << 5) | 0x200u;
+                        }
+                    }
+                }
 
                 uint32_t ins = 0;       // lanes whose probe (or cursor-2 insert) has happened, in order
                 uint32_t s = 0;         // first lane of the current run inside this batch
@@ -213,7 +273,7 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
                     const uint32_t w = __ffs(trig) - 1;
                     if ((endmask >> w) & 1u) {
                         // final literal-only sequence  :178-190
-                        if (!emit_sequence(out, opos, cap, in, lit_start, len - lit_start, 0, 0, true)) status = LZF_WRITER_FULL;
+                        if (!emit_sequence(out, opos, cap, in, lit_start, len - lit_start, 0, 0, true, false, 0, 0)) status = LZF_WRITER_FULL;
                         done = true;
                         committed = true;                                     // the table is never read again
                         break;
@@ -222,10 +282,26 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
                     const uint32_t cur = __shfl_sync(LZF_FULL_MASK, p, w);
                     const uint32_t cnd = __shfl_sync(LZF_FULL_MASK, cand, w);
 
-                    // ---- extension: lanes 0..23 look 96 bytes ahead (count_matching_bytes :117-145 over
-                    // input[cur..len-5]), lanes 24..31 look 32 bytes behind (backtrack :211-214)
                     const uint32_t limit = len - 5 - cur;                     // bytes of current_batch :195
                     const uint32_t max_back = min(cur - lit_start, cnd);
+                    uint32_t matching = 0, backtrack = 0;
+                    // ---- fast extension: the winner's own summary, unless it came from an in-batch candidate
+                    // or the match / backtrack runs past what the summary covers
+                    bool fast = false;
+                    {
+                        const uint32_t wsum = __shfl_sync(LZF_FULL_MASK, inb ? 0u : fsum, w);
+                        const uint32_t fm = wsum & 31u, nb = (wsum >> 5) & 7u;
+                        const bool f_ok = (wsum & 0x100u) && (fm < 16 || limit <= 16);
+                        const bool b_ok = max_back == 0 || ((wsum & 0x200u) && (nb < 4 || max_back <= 4));
+                        if (f_ok && b_ok) {
+                            fast = true;
+                            matching = min(fm, limit);
+                            backtrack = min(nb, max_back);
+                        }
+                    }
+                    if (!fast) {
+                    // ---- general extension: lanes 0..23 look 96 bytes ahead (count_matching_bytes :117-145 over
+                    // input[cur..len-5]), lanes 24..31 look 32 bytes behind (backtrack :211-214)
                     uint32_t cnt = 4;                                         // bytes this lane's word contributes
                     if (lane < 24) {
                         const uint32_t f = 4 + 4 * lane;
@@ -249,7 +325,6 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
                         } else cnt = 0;
                     }
                     const uint32_t stop = __ballot_sync(LZF_FULL_MASK, cnt != 4u);
-                    uint32_t matching;
                     {
                         const uint32_t fstop = stop & 0x00ffffffu;
                         if (fstop) {
@@ -279,7 +354,6 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
                             }
                         }
                     }
-                    uint32_t backtrack;
                     {
                         const uint32_t bstop = stop >> 24;
                         if (bstop) {
@@ -297,11 +371,15 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
                             }
                         }
                     }
+                    }   // !fast
                     const uint32_t extra = matching - 4 + backtrack;          // :206,214
                     const uint32_t cursor = cur + matching;                   // :215
 
                     // ---- write_group  :150-163,235-236
-                    if (!emit_sequence(out, opos, cap, in, lit_start, cur - backtrack - lit_start, cur - cnd, extra, false)) {
+                    // literal bytes of a run that started inside this batch are the low bytes of the lanes' v32
+                    const bool lits_in_regs = consecutive && lit_start >= base;
+                    if (!emit_sequence(out, opos, cap, in, lit_start, cur - backtrack - lit_start, cur - cnd, extra, false,
+                                       lits_in_regs, v32, lit_start - base)) {
                         status = LZF_WRITER_FULL;
                         done = true;
                         committed = true;
