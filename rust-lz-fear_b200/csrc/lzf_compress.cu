@@ -81,13 +81,13 @@ __device__ __forceinline__ uint32_t ld4(const uint8_t* in, uint32_t pos) {
 
 // One LZ4 sequence (write_group :150-163, or the literal-only tail :182-189 when `final`).
 // Returns false when the bounded writer would refuse it (NoPartialWrites, compress.rs:298-301).
-__device__ __forceinline__ bool emit_sequence(uint8_t* out, uint64_t& opos, uint64_t cap, const uint8_t* in,
+__device__ __forceinline__ bool emit_sequence(uint8_t* out, uint32_t& opos, uint32_t cap, const uint8_t* in,
                                               uint32_t lit_start, uint32_t L, uint32_t offset, uint32_t extra, bool final,
                                               bool lits_in_regs, uint32_t v32, uint32_t first_lit_lane) {
     const unsigned lane = lane_id();
     const uint32_t ll = lsic_len(L), ml = final ? 0u : lsic_len(extra);
     const uint64_t total = 1ull + ll + L + (final ? 0u : 2u + ml);
-    if (opos + total > cap) return false;
+    if ((uint64_t)opos + total > cap) return false;
     uint8_t* o = out + opos;
     const uint8_t token = (uint8_t)(((L < 15 ? L : 15) << 4) | (final ? 0u : (extra < 15 ? extra : 15)));
     if (total <= 32) {
@@ -113,7 +113,7 @@ __device__ __forceinline__ bool emit_sequence(uint8_t* out, uint64_t& opos, uint
             write_lsic(o + 1 + ll + L + 2, extra);
         }
     }
-    opos += total;
+    opos += (uint32_t)total;
     return true;
 }
 
@@ -150,10 +150,10 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
         const uint32_t len = a.in_len[b];
         const uint8_t* in = a.in + a.in_off[b];
         uint8_t* out = a.out + a.out_off[b];
-        const uint64_t cap = a.out_cap ? (uint64_t)a.out_cap[b] : (uint64_t)len;
+        const uint32_t cap = a.out_cap ? a.out_cap[b] : len;       // NoPartialWrites bound (compress.rs:242)
 
         int status = LZF_OK;
-        uint64_t opos = 0;
+        uint32_t opos = 0;
 
         // assert!(input.len() <= T::payload_size_limit())  :167 ; Slot width must hold every position
         const bool too_big = (kHash4 && len > 0xffffu) || (sizeof(Slot) == 2 && len > 0x10000u) ||
@@ -228,13 +228,18 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
                 }
                 const uint32_t base = __shfl_sync(LZF_FULL_MASK, p, 0);
                 if (consecutive) {
-                    const uint32_t a1 = __shfl_down_sync(LZF_FULL_MASK, v32, 4);
-                    const uint32_t a2 = __shfl_down_sync(LZF_FULL_MASK, v32, 8);
-                    const uint32_t a3 = __shfl_down_sync(LZF_FULL_MASK, v32, 12);
-                    const uint32_t am1 = __shfl_up_sync(LZF_FULL_MASK, v32, 4);
+                    // bytes p+4.., p+8.., p+12.. and p-4..: the neighbours' registers where a neighbour exists and
+                    // holds data, a (cache-resident) load otherwise
+                    uint32_t a1 = __shfl_down_sync(LZF_FULL_MASK, v32, 4);
+                    uint32_t a2 = __shfl_down_sync(LZF_FULL_MASK, v32, 8);
+                    uint32_t a3 = __shfl_down_sync(LZF_FULL_MASK, v32, 12);
+                    uint32_t am1 = __shfl_up_sync(LZF_FULL_MASK, v32, 4);
                     if (v_pre && t_ok) {
-                        // forward: bytes p+4 .. p+15 live in lanes +4, +8, +12 (they must exist and hold data)
-                        if (lane + 12 < 32 && !((endmask >> (lane + 12)) & 1u)) {
+                        const uint32_t live = ~endmask;                          // lanes that loaded their v32
+                        if (p + 16 <= len) {                                     // bytes p .. p+15 are inside the block
+                            if (lane + 4 >= 32 || !((live >> (lane + 4)) & 1u)) a1 = ld4(in, p + 4);
+                            if (lane + 8 >= 32 || !((live >> (lane + 8)) & 1u)) a2 = ld4(in, p + 8);
+                            if (lane + 12 >= 32 || !((live >> (lane + 12)) & 1u)) a3 = ld4(in, p + 12);
                             const uint32_t x1 = a1 ^ v_c1, x2 = a2 ^ v_c2, x3 = a3 ^ v_c3;
                             uint32_t fm;
                             if (x1) fm = 4 + ((uint32_t)(__ffs((int)x1) - 1) >> 3);
@@ -243,8 +248,8 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
                             else fm = 16;
                             fsum |= fm | 0x100u;
                         }
-                        // backward: bytes p-4 .. p-1 live in lane -4
-                        if (lane >= 4 && v_hasb) {
+                        if (v_hasb && p >= 4) {
+                            if (lane < 4) am1 = ld4(in, p - 4);
                             const uint32_t xb = am1 ^ v_cm1;
                             const uint32_t nb = xb ? (uint32_t)__clz((int)xb) >> 3 : 4u;
                             fsum |= (nb << 5) | 0x200u;
@@ -297,6 +302,26 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
                             fast = true;
                             matching = min(fm, limit);
                             backtrack = min(nb, max_back);
+                        }
+                    }
+                    if (fast) {
+                        // ---- HOT PATH: a short sequence that starts and ends inside this batch — token, <= 14
+                        // literals (from registers) and the offset are written with one byte per lane
+                        const uint32_t L = cur - backtrack - lit_start;
+                        const uint32_t extra = matching - 4 + backtrack;
+                        const uint32_t cursor = cur + matching;
+                        if (L < 15 && extra < 15 && lit_start >= base && cursor - base < 32 && cap - opos >= 17 && cap >= opos) {
+                            const uint32_t litb = __shfl_sync(LZF_FULL_MASK, v32, lit_start - base + lane - 1) & 0xffu;
+                            const uint32_t offset = cur - cnd;
+                            const uint32_t v = lane == 0 ? ((L << 4) | extra) : (lane <= L ? litb : (offset >> (8 * (lane - 1 - L))));
+                            if (lane < L + 3) out[opos + lane] = (uint8_t)v;
+                            opos += L + 3;
+                            lit_start = cursor;
+                            j = 0;
+                            const uint32_t l2 = cursor - 2 - base;                // table.replace(cursor - 2) :218
+                            if (!((endmask >> l2) & 1u)) ins |= 1u << l2;
+                            s = cursor - base;
+                            continue;
                         }
                     }
                     if (!fast) {
@@ -424,7 +449,7 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
 
         __syncwarp();
         if (lane == 0) {
-            a.out_len[b] = (status == LZF_OK) ? (uint32_t)opos : 0u;
+            a.out_len[b] = (status == LZF_OK) ? opos : 0u;
             a.status[b] = status;
         }
         // XXH32 of the plaintext / of the stored bytes (compressed, or the plaintext when stored raw):
