@@ -29,6 +29,8 @@
 // when every position fits u16).
 #include "lzf_kernels.cuh"
 
+#include <type_traits>
+
 namespace lzf {
 
 // offset of the j-th probe of a literal run from the run start: the closed form of
@@ -117,25 +119,77 @@ __device__ __forceinline__ bool emit_sequence(uint8_t* out, uint32_t& opos, uint
     return true;
 }
 
+// ---- the per-warp hash table ----------------------------------------------------------------------
+// Slot = uint32_t / uint16_t: the position itself (u16 only when every position of the block fits).
+// Packed17: blocks up to 16 MiB keep 17 bits per slot — a u16 array plus a bit array, 8.5 KiB instead
+// of 16 KiB, so twice as many blocks are resident per SM.  A candidate only matters while it is at
+// most 65 535 bytes behind the probe (:200-201), so positions are kept modulo 2^17 and every 64 KiB
+// of progress a sweep re-encodes the slots that have fallen out of the window as "65 536 behind the
+// sweep point" — they stay out of reach until the next sweep, exactly like the stale u32 positions
+// of the reference.  Distances 1..65 535 are therefore always exact and anything else is rejected.
+template <typename Slot>
+struct PlainTable {
+    Slot* t;
+    __device__ __forceinline__ uint32_t dist(uint32_t h, uint32_t p) const { return p - (uint32_t)t[h]; }
+    __device__ __forceinline__ void put(uint32_t h, uint32_t p) { t[h] = (Slot)p; }
+};
+struct Packed17Table {
+    uint16_t* lo;
+    uint32_t* hi;          // one bit per slot
+    __device__ __forceinline__ uint32_t get(uint32_t h) const { return (uint32_t)lo[h] | (((hi[h >> 5] >> (h & 31u)) & 1u) << 16); }
+    __device__ __forceinline__ uint32_t dist(uint32_t h, uint32_t p) const { return (p - get(h)) & 0x1ffffu; }
+    __device__ __forceinline__ void put(uint32_t h, uint32_t p) {
+        lo[h] = (uint16_t)p;
+        if ((p >> 16) & 1u) atomicOr(&hi[h >> 5], 1u << (h & 31u));
+        else atomicAnd(&hi[h >> 5], ~(1u << (h & 31u)));
+    }
+    // all 32 lanes: slots whose position is more than 65 535 behind `at` become "65 536 behind `at`"
+    __device__ __forceinline__ void sweep(uint32_t nslots, uint32_t at) {
+        const unsigned lane = lane_id();
+        const uint32_t dead = (at - 65536u) & 0x1ffffu;
+        for (uint32_t i = lane; i < nslots; i += 32) {
+            uint32_t e = get(i);
+            const uint32_t age = (at - e) & 0x1ffffu;
+            if (age > 0xffffu || age == 0) { e = dead; lo[i] = (uint16_t)e; }
+            const uint32_t word = __ballot_sync(LZF_FULL_MASK, (e >> 16) & 1u);
+            if (lane == 0) hi[i >> 5] = word;
+        }
+        __syncwarp();
+    }
+};
+constexpr uint32_t kPacked17MaxLen = 16u << 20;
+
 #ifndef LZF_ENC_WARPS
 #define LZF_ENC_WARPS 4
 #endif
 constexpr int kEncodeWarpsPerCta = LZF_ENC_WARPS;
 constexpr int kGlobalTableCtasPerSm = 4;   // bounds the global table scratch
 
-template <typename Slot, bool kHash4>
-__global__ void __launch_bounds__(kEncodeWarpsPerCta * 32)
+// kTab: 0 = u32 slots, 1 = u16 slots (positions fit 16 bits), 2 = packed 17-bit slots
+template <int kTab, bool kHash4, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32)
 encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
     LZF_DYN_SMEM(smem_raw);
     __shared__ HashQueue hashq;
+    constexpr bool kPacked = kTab == 2;
+    using Slot = typename std::conditional<kTab == 0, uint32_t, uint16_t>::type;
+    constexpr int kEncodeWarpsPerCta = kWarps;
     const unsigned lane = lane_id();
     const unsigned warp_in_cta = threadIdx.x >> 5;
-    Slot* table;
+    const size_t table_bytes = kPacked ? (size_t)nslots * 2 + nslots / 8 : (size_t)nslots * sizeof(Slot);
+    uint8_t* table_mem;
     if (smem_tables) {
-        table = reinterpret_cast<Slot*>(smem_raw) + (size_t)warp_in_cta * nslots;
+        table_mem = smem_raw + (size_t)warp_in_cta * table_bytes;
     } else {
         const size_t gw = (size_t)blockIdx.x * kEncodeWarpsPerCta + warp_in_cta;
-        table = reinterpret_cast<Slot*>(a.global_tables) + gw * nslots;
+        table_mem = a.global_tables + gw * table_bytes;
+    }
+    typename std::conditional<kPacked, Packed17Table, PlainTable<Slot>>::type table;
+    if constexpr (kPacked) {
+        table.lo = reinterpret_cast<uint16_t*>(table_mem);
+        table.hi = reinterpret_cast<uint32_t*>(table_mem + (size_t)nslots * 2);
+    } else {
+        table.t = reinterpret_cast<Slot*>(table_mem);
     }
     const uint32_t hashlog = a.hashlog;
     const uint32_t lower_mask = (1u << lane) - 1u;
@@ -156,18 +210,19 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
         uint32_t opos = 0;
 
         // assert!(input.len() <= T::payload_size_limit())  :167 ; Slot width must hold every position
-        const bool too_big = (kHash4 && len > 0xffffu) || (sizeof(Slot) == 2 && len > 0x10000u) ||
+        const bool too_big = (kHash4 && len > 0xffffu) || (kTab == 1 && len > 0x10000u) || (kPacked && len > kPacked17MaxLen) ||
                              (a.max_block_len && len > a.max_block_len);
         if (too_big) {
             status = LZF_PANIC;
         } else if (len) {
             // fresh zeroed table (U32Table::default :32-36 / template_table.clone() compress.rs:270)
             {
-                uint4* t4 = reinterpret_cast<uint4*>(table);
-                const uint32_t nvec = nslots * (uint32_t)sizeof(Slot) / 16;
+                uint4* t4 = reinterpret_cast<uint4*>(table_mem);
+                const uint32_t nvec = (uint32_t)(table_bytes / 16);
                 for (uint32_t i = lane; i < nvec; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
             }
             __syncwarp();
+            uint32_t last_sweep = 0;    // packed tables: every slot is exact for probes below last_sweep + 65536
 
             uint32_t lit_start = 0;     // start of the current literal run
             uint32_t j = 0;             // probes already done in the current run
@@ -179,8 +234,15 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
                 const bool is_end = p64 >= len || len - (uint32_t)p64 < 12;    // :178
                 const uint32_t p = (uint32_t)p64;
                 const uint32_t endmask = __ballot_sync(LZF_FULL_MASK, is_end);
+                if constexpr (kPacked) {
+                    const uint32_t p_hi = __shfl_sync(LZF_FULL_MASK, p64 < len ? (uint32_t)p64 : len, 31);
+                    if (p_hi - last_sweep >= 65536u) {
+                        last_sweep = __shfl_sync(LZF_FULL_MASK, (uint32_t)p64, 0);
+                        table.sweep(nslots, last_sweep);
+                    }
+                }
                 uint32_t v32 = 0, h = 0xffff0000u | lane;                     // unique key for idle lanes
-                uint32_t tcand = 0;
+                uint32_t tcand = 0, tdist = 0;
                 if (!is_end) {
                     const uintptr_t ad = reinterpret_cast<uintptr_t>(in + p);
                     const uint32_t* w = reinterpret_cast<const uint32_t*>(ad & ~uintptr_t(3));
@@ -188,7 +250,8 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
                     const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1);          // 12 bytes remain: both words are inside the block
                     v32 = __funnelshift_r(w0, w1, sh);
                     h = kHash4 ? hash4(v32, hashlog) : hash5(v32, (w1 >> sh) & 0xffu, hashlog);
-                    tcand = table[h];                                         // table.replace :196 (read half)
+                    tdist = table.dist(h, p);                                 // table.replace :196 (read half)
+                    tcand = p - tdist;
                 }
                 const uint32_t same = __match_any_sync(LZF_FULL_MASK, h);
                 // table candidate: addressable (:200-201) and >= MINMATCH equal bytes (:206)
@@ -203,7 +266,8 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
                 uint32_t fsum = 0;
                 uint32_t v_c1 = 0, v_c2 = 0, v_c3 = 0, v_cm1 = 0;
                 bool v_hasb = false, v_pre = false;
-                if (!is_end && p != 0 && p - tcand <= 0xffffu) {
+                // addressable (:200-201): 1 <= distance <= 0xFFFF (distance 0 only ever means "p == 0", :200)
+                if (!is_end && tdist - 1u < 0xffffu) {
                     if (consecutive && tcand + 16 <= len) {
                         const bool hasb = tcand >= 4;
                         const uint32_t s0 = hasb ? tcand - 4 : tcand;
@@ -425,14 +489,14 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
                     // the match left the batch: commit, then insert cursor - 2 behind everything committed
                     {
                         const uint32_t later = same & ins & ~lower_mask & ~(1u << lane);
-                        if (((ins >> lane) & 1u) && later == 0) table[h] = (Slot)p;
+                        if (((ins >> lane) & 1u) && later == 0) table.put(h, p);
                         __syncwarp();
                         if (lane == 0) {
                             uint32_t h2;
                             if (kHash4) h2 = hash4(ld4(in, q2), hashlog);
                             else if (len - q2 >= 8) h2 = hash5(ld4(in, q2), in[q2 + 4], hashlog);
                             else h2 = 0;                                      // :43 unwrap_or(0) -> hash of 0
-                            table[h2] = (Slot)q2;
+                            table.put(h2, q2);
                         }
                         committed = true;
                     }
@@ -441,7 +505,7 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
                 if (!committed) {
                     // last inserted lane of each slot wins (mem::swap order, :64-71)
                     const uint32_t later = same & ins & ~lower_mask & ~(1u << lane);
-                    if (((ins >> lane) & 1u) && later == 0) table[h] = (Slot)p;
+                    if (((ins >> lane) & 1u) && later == 0) table.put(h, p);
                 }
                 __syncwarp();
             }
@@ -466,42 +530,51 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
 }  // namespace lzf
 
 // Host-side launcher.  Returns a cudaError_t as int.
+namespace lzf {
+template <int kTab, bool kHash4, int kWarps>
+static int launch_encode_variant(const EncodeArgs* args, int num_sms, uint32_t nslots, size_t table_bytes, bool smem_tables,
+                                 cudaStream_t stream) {
+    auto kern = encode_blocks_kernel<kTab, kHash4, kWarps>;
+    cudaError_t e;
+    int ctas_per_sm = 1;
+    const size_t dyn = smem_tables ? table_bytes * kWarps : 0;
+    if (dyn > 48 * 1024) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return (int)e;
+    }
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kWarps * 32, dyn);
+    if (e != cudaSuccess) return (int)e;
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    if (!smem_tables && ctas_per_sm > kGlobalTableCtasPerSm) ctas_per_sm = kGlobalTableCtasPerSm;
+    unsigned grid = (unsigned)(num_sms * ctas_per_sm);
+    const unsigned need = (args->nblocks + kWarps - 1) / kWarps;
+    if (grid > need) grid = need;
+    LZF_LAUNCH(kern, grid, kWarps * 32, dyn, stream, *args, nslots, smem_tables ? 1 : 0);
+    return (int)cudaGetLastError();
+}
+}  // namespace lzf
+
 extern "C" int lzf_launch_encode(const lzf::EncodeArgs* args, int num_sms, cudaStream_t stream) {
     using namespace lzf;
     if (args->nblocks == 0) return 0;
     const uint32_t hashlog = args->hashlog;
     const bool hash4 = args->table_kind == LZF_TABLE_U16;
     const uint32_t nslots = hash4 ? (2u << hashlog) : (1u << hashlog);
-    // u16 slots are exact whenever every position fits 16 bits
+    // u16 slots are exact whenever every position fits 16 bits; blocks up to 16 MiB use packed 17-bit slots
     const bool slot16 = hash4 || (args->max_block_len != 0 && args->max_block_len <= 65536u);
-    const size_t table_bytes = (size_t)nslots * (slot16 ? 2 : 4);
+    const bool packed = !slot16 && args->max_block_len != 0 && args->max_block_len <= kPacked17MaxLen;
+    const size_t table_bytes = slot16 ? (size_t)nslots * 2 : packed ? (size_t)nslots * 2 + nslots / 8 : (size_t)nslots * 4;
     // per-warp tables up to 32 KiB live in shared memory; larger ones (hashlog >= 14 extension) in a
     // ctx-owned global scratch that stays L2-resident
     const bool smem_tables = table_bytes <= 32 * 1024;
     if (!smem_tables && args->global_tables == nullptr) return (int)cudaErrorInvalidValue;
-    void (*kern)(EncodeArgs, uint32_t, int);
-    if (hash4) kern = encode_blocks_kernel<uint16_t, true>;
-    else if (slot16) kern = encode_blocks_kernel<uint16_t, false>;
-    else kern = encode_blocks_kernel<uint32_t, false>;
-    cudaError_t e;
-    int ctas_per_sm = 1;
-    const size_t dyn = smem_tables ? table_bytes * kEncodeWarpsPerCta : 0;
-    if (dyn > 48 * 1024) {
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-        if (e != cudaSuccess) return (int)e;
-    }
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kEncodeWarpsPerCta * 32, dyn);
-    if (e != cudaSuccess) return (int)e;
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
-    if (!smem_tables && ctas_per_sm > kGlobalTableCtasPerSm) ctas_per_sm = kGlobalTableCtasPerSm;
-    unsigned grid = (unsigned)(num_sms * ctas_per_sm);
-    const unsigned need = (args->nblocks + kEncodeWarpsPerCta - 1) / kEncodeWarpsPerCta;
-    if (grid > need) grid = need;
-    LZF_LAUNCH(kern, grid, kEncodeWarpsPerCta * 32, dyn, stream, *args, nslots, smem_tables ? 1 : 0);
-    return (int)cudaGetLastError();
+    if (hash4) return launch_encode_variant<1, true, kEncodeWarpsPerCta>(args, num_sms, nslots, table_bytes, smem_tables, stream);
+    if (slot16) return launch_encode_variant<1, false, 8>(args, num_sms, nslots, table_bytes, smem_tables, stream);
+    if (packed) return launch_encode_variant<2, false, 8>(args, num_sms, nslots, table_bytes, smem_tables, stream);
+    return launch_encode_variant<0, false, kEncodeWarpsPerCta>(args, num_sms, nslots, table_bytes, smem_tables, stream);
 }
 
 // Number of warps a global-table launch may start (sizing of the scratch).
 extern "C" size_t lzf_encode_global_table_warps(int num_sms) {
-    return (size_t)num_sms * lzf::kGlobalTableCtasPerSm * lzf::kEncodeWarpsPerCta;
+    return (size_t)num_sms * lzf::kGlobalTableCtasPerSm * 8;
 }

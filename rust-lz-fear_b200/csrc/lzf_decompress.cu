@@ -41,7 +41,7 @@ struct __align__(16) DecodeWarpSmem {
     uint8_t win[kWin];            // staged compressed bytes
     uint8_t step[kWin + 32];      // step[p] = encoded size of the LSIC-free sequence whose token is win[p]; 0 = not fast
     uint8_t stage[kStage];        // output staging ring
-    uint16_t plist[32];           // token positions of the current step
+    uint32_t plist[32];           // token positions of the current step (walk32: shared-memory addresses of step[p])
     uint64_t mbar;
     uint64_t pad;
 };
@@ -210,6 +210,254 @@ __device__ __forceinline__ uint32_t flush_stage(const uint8_t* stage, uint8_t* o
     return upto;
 }
 
+// The serial part of the decoder: follow step[] from `pp` for at most 32 sequences, recording where each
+// token sits.  Five instructions per sequence (load, test, branch, store, add); written in PTX because
+// the compiler's version of this loop carries three redundant induction variables.
+//   pp      in/out: shared-memory address of step[p]
+//   plist   shared-memory address of the position list (u32 x 32)
+// returns the number of sequences walked.
+#ifndef LZF_SIMT_EMU
+__device__ __noinline__ uint32_t walk32(uint32_t& pp, uint32_t plist) {
+    uint32_t cnt;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        ".reg .u32 d;\n\t"
+        "ld.shared.u8 d, [%1];\n\t"
+        "setp.eq.u32 q, d, 0;\n\t"
+        "@q bra.uni WALK_DONE_0;\n\t"
+        "st.shared.u32 [%2+0], %1;\n\t"
+        "add.u32 %1, %1, d;\n\t"
+        "ld.shared.u8 d, [%1];\n\t"
+        "setp.eq.u32 q, d, 0;\n\t"
+        "@q bra.uni WALK_DONE_1;\n\t"
+        "st.shared.u32 [%2+4], %1;\n\t"
+        "add.u32 %1, %1, d;\n\t"
+        "ld.shared.u8 d, [%1];\n\t"
+        "setp.eq.u32 q, d, 0;\n\t"
+        "@q bra.uni WALK_DONE_2;\n\t"
+        "st.shared.u32 [%2+8], %1;\n\t"
+        "add.u32 %1, %1, d;\n\t"
+        "ld.shared.u8 d, [%1];\n\t"
+        "setp.eq.u32 q, d, 0;\n\t"
+        "@q bra.uni WALK_DONE_3;\n\t"
+        "st.shared.u32 [%2+12], %1;\n\t"
+        "add.u32 %1, %1, d;\n\t"
+        "ld.shared.u8 d, [%1];\n\t"
+        "setp.eq.u32 q, d, 0;\n\t"
+        "@q bra.uni WALK_DONE_4;\n\t"
+        "st.shared.u32 [%2+16], %1;\n\t"
+        "add.u32 %1, %1, d;\n\t"
+        "ld.shared.u8 d, [%1];\n\t"
+        "setp.eq.u32 q, d, 0;\n\t"
+        "@q bra.uni WALK_DONE_5;\n\t"
+        "st.shared.u32 [%2+20], %1;\n\t"
+        "add.u32 %1, %1, d;\n\t"
+        "ld.shared.u8 d, [%1];\n\t"
+        "setp.eq.u32 q, d, 0;\n\t"
+        "@q bra.uni WALK_DONE_6;\n\t"
+        "st.shared.u32 [%2+24], %1;\n\t"
+        "add.u32 %1, %1, d;\n\t"
+        "ld.shared.u8 d, [%1];\n\t"
+        "setp.eq.u32 q, d, 0;\n\t"
+        "@q bra.uni WALK_DONE_7;\n\t"
+        "st.shared.u32 [%2+28], %1;\n\t"
+        "add.u32 %1, %1, d;\n\t"
+        "ld.shared.u8 d, [%1];\n\t"
+        "setp.eq.u32 q, d, 0;\n\t"
+        "@q bra.uni WALK_DONE_8;\n\t"
+        "st.shared.u32 [%2+32], %1;\n\t"
+        "add.u32 %1, %1, d;\n\t"
+        "ld.shared.u8 d, [%1];\n\t"
+        "setp.eq.u32 q, d, 0;\n\t"
+        "@q bra.uni WALK_DONE_9;\n\t"
+        "st.shared.u32 [%2+36], %1;\n\t"
+        "add.u32 %1, %1, d;\n\t"
+        "ld.shared.u8 d, [%1];\n\t"
+        "setp.eq.u32 q, d, 0;\n\t"
+        "@q bra.uni WALK_DONE_10;\n\t"
+        "st.shared.u32 [%2+40], %1;\n\t"
+        "add.u32 %1, %1, d;\n\t"
+        "ld.shared.u8 d, [%1];\n\t"
+        "setp.eq.u32 q, d, 0;\n\t"
+        "@q bra.uni WALK_DONE_11;\n\t"
+        "st.shared.u32 [%2+44], %1;\n\t"
+        "add.u32 %1, %1, d;\n\t"
+        "ld.shared.u8 d, [%1];\n\t"
+        "setp.eq.u32 q, d, 0;\n\t"
+        "@q bra.uni WALK_DONE_12;\n\t"
+        "st.shared.u32 [%2+48], %1;\n\t"
+        "add.u32 %1, %1, d;\n\t"
+        "ld.shared.u8 d, [%1];\n\t"
+        "setp.eq.u32 q, d, 0;\n\t"
+        "@q bra.uni WALK_DONE_13;\n\t"
+        "st.shared.u32 [%2+52], %1;\n\t"
+        "add.u32 %1, %1, d;\n\t"
+        "ld.shared.u8 d, [%1];\n\t"
+        "setp.eq.u32 q, d, 0;\n\t"
+        "@q bra.uni WALK_DONE_14;\n\t"
+        "st.shared.u32 [%2+56], %1;\n\t"
+        "add.u32 %1, %1, d;\n\t"
+        "ld.shared.u8 d, [%1];\n\t"
+        "setp.eq.u32 q, d, 0;\n\t"
+        "@q bra.uni WALK_DONE_15;\n\t"
+        "st.shared.u32 [%2+60], %1;\n\t"
+        "add.u32 %1, %1, d;\n\t"
+        "ld.shared.u8 d, [%1];\n\t"
+        "setp.eq.u32 q, d, 0;\n\t"
+        "@q bra.uni WALK_DONE_16;\n\t"
+        "st.shared.u32 [%2+64], %1;\n\t"
+        "add.u32 %1, %1, d;\n\t"
+        "ld.shared.u8 d, [%1];\n\t"
+        "setp.eq.u32 q, d, 0;\n\t"
+        "@q bra.uni WALK_DONE_17;\n\t"
+        "st.shared.u32 [%2+68], %1;\n\t"
+        "add.u32 %1, %1, d;\n\t"
+        "ld.shared.u8 d, [%1];\n\t"
+        "setp.eq.u32 q, d, 0;\n\t"
+        "@q bra.uni WALK_DONE_18;\n\t"
+        "st.shared.u32 [%2+72], %1;\n\t"
+        "add.u32 %1, %1, d;\n\t"
+        "ld.shared.u8 d, [%1];\n\t"
+        "setp.eq.u32 q, d, 0;\n\t"
+        "@q bra.uni WALK_DONE_19;\n\t"
+        "st.shared.u32 [%2+76], %1;\n\t"
+        "add.u32 %1, %1, d;\n\t"
+        "ld.shared.u8 d, [%1];\n\t"
+        "setp.eq.u32 q, d, 0;\n\t"
+        "@q bra.uni WALK_DONE_20;\n\t"
+        "st.shared.u32 [%2+80], %1;\n\t"
+        "add.u32 %1, %1, d;\n\t"
+        "ld.shared.u8 d, [%1];\n\t"
+        "setp.eq.u32 q, d, 0;\n\t"
+        "@q bra.uni WALK_DONE_21;\n\t"
+        "st.shared.u32 [%2+84], %1;\n\t"
+        "add.u32 %1, %1, d;\n\t"
+        "ld.shared.u8 d, [%1];\n\t"
+        "setp.eq.u32 q, d, 0;\n\t"
+        "@q bra.uni WALK_DONE_22;\n\t"
+        "st.shared.u32 [%2+88], %1;\n\t"
+        "add.u32 %1, %1, d;\n\t"
+        "ld.shared.u8 d, [%1];\n\t"
+        "setp.eq.u32 q, d, 0;\n\t"
+        "@q bra.uni WALK_DONE_23;\n\t"
+        "st.shared.u32 [%2+92], %1;\n\t"
+        "add.u32 %1, %1, d;\n\t"
+        "ld.shared.u8 d, [%1];\n\t"
+        "setp.eq.u32 q, d, 0;\n\t"
+        "@q bra.uni WALK_DONE_24;\n\t"
+        "st.shared.u32 [%2+96], %1;\n\t"
+        "add.u32 %1, %1, d;\n\t"
+        "ld.shared.u8 d, [%1];\n\t"
+        "setp.eq.u32 q, d, 0;\n\t"
+        "@q bra.uni WALK_DONE_25;\n\t"
+        "st.shared.u32 [%2+100], %1;\n\t"
+        "add.u32 %1, %1, d;\n\t"
+        "ld.shared.u8 d, [%1];\n\t"
+        "setp.eq.u32 q, d, 0;\n\t"
+        "@q bra.uni WALK_DONE_26;\n\t"
+        "st.shared.u32 [%2+104], %1;\n\t"
+        "add.u32 %1, %1, d;\n\t"
+        "ld.shared.u8 d, [%1];\n\t"
+        "setp.eq.u32 q, d, 0;\n\t"
+        "@q bra.uni WALK_DONE_27;\n\t"
+        "st.shared.u32 [%2+108], %1;\n\t"
+        "add.u32 %1, %1, d;\n\t"
+        "ld.shared.u8 d, [%1];\n\t"
+        "setp.eq.u32 q, d, 0;\n\t"
+        "@q bra.uni WALK_DONE_28;\n\t"
+        "st.shared.u32 [%2+112], %1;\n\t"
+        "add.u32 %1, %1, d;\n\t"
+        "ld.shared.u8 d, [%1];\n\t"
+        "setp.eq.u32 q, d, 0;\n\t"
+        "@q bra.uni WALK_DONE_29;\n\t"
+        "st.shared.u32 [%2+116], %1;\n\t"
+        "add.u32 %1, %1, d;\n\t"
+        "ld.shared.u8 d, [%1];\n\t"
+        "setp.eq.u32 q, d, 0;\n\t"
+        "@q bra.uni WALK_DONE_30;\n\t"
+        "st.shared.u32 [%2+120], %1;\n\t"
+        "add.u32 %1, %1, d;\n\t"
+        "ld.shared.u8 d, [%1];\n\t"
+        "setp.eq.u32 q, d, 0;\n\t"
+        "@q bra.uni WALK_DONE_31;\n\t"
+        "st.shared.u32 [%2+124], %1;\n\t"
+        "add.u32 %1, %1, d;\n\t"
+        "mov.u32 %0, 32;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_0: mov.u32 %0, 0;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_1: mov.u32 %0, 1;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_2: mov.u32 %0, 2;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_3: mov.u32 %0, 3;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_4: mov.u32 %0, 4;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_5: mov.u32 %0, 5;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_6: mov.u32 %0, 6;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_7: mov.u32 %0, 7;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_8: mov.u32 %0, 8;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_9: mov.u32 %0, 9;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_10: mov.u32 %0, 10;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_11: mov.u32 %0, 11;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_12: mov.u32 %0, 12;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_13: mov.u32 %0, 13;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_14: mov.u32 %0, 14;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_15: mov.u32 %0, 15;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_16: mov.u32 %0, 16;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_17: mov.u32 %0, 17;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_18: mov.u32 %0, 18;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_19: mov.u32 %0, 19;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_20: mov.u32 %0, 20;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_21: mov.u32 %0, 21;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_22: mov.u32 %0, 22;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_23: mov.u32 %0, 23;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_24: mov.u32 %0, 24;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_25: mov.u32 %0, 25;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_26: mov.u32 %0, 26;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_27: mov.u32 %0, 27;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_28: mov.u32 %0, 28;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_29: mov.u32 %0, 29;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_30: mov.u32 %0, 30;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_31: mov.u32 %0, 31;\n\t"
+        "bra.uni WALK_END;\n\t"
+        "WALK_END:\n\t"
+        "}"
+        : "=r"(cnt), "+r"(pp)
+        : "r"(plist)
+        : "memory");
+    return cnt;
+}
+#endif
+
 __global__ void __launch_bounds__(kDecodeWarpsPerCta * 32, LZF_DEC_MINCTAS)
 decode_blocks_kernel(DecodeArgs a) {
     LZF_DYN_SMEM(smem_raw);
@@ -285,18 +533,28 @@ decode_blocks_kernel(DecodeArgs a) {
                 // ---- walk: up to 32 LSIC-free sequences that lie completely inside the window.  This is
                 // the only serial part of the decoder: one shared-memory byte per sequence.
                 uint32_t cnt = 0;
+#ifndef LZF_SIMT_EMU
+                const uint32_t step_sa = smem_addr(sm.step);
                 if (s.olen + 32u * 32u <= bound) {
-#pragma unroll 8
+                    uint32_t pp = step_sa + p;
+                    cnt = walk32(pp, smem_addr(sm.plist));
+                    p = pp - step_sa;
+                }
+                __syncwarp();
+                const uint32_t my_p = sm.plist[lane] - step_sa;
+#else
+                if (s.olen + 32u * 32u <= bound) {
                     for (int k = 0; k < 32; k++) {
                         const uint32_t d = sm.step[p];
                         if (d == 0) break;
-                        sm.plist[k] = (uint16_t)p;
+                        sm.plist[k] = p;
                         p += d;
                         cnt = k + 1;
                     }
                 }
                 __syncwarp();
                 const uint32_t my_p = sm.plist[lane];
+#endif
                 // ---- per-lane decode of the sequence headers, output positions by warp scan
                 uint32_t lit = 0, ml = 0, off = 1, tot = 0;
                 if (lane < cnt) {
@@ -322,7 +580,14 @@ decode_blocks_kernel(DecodeArgs a) {
                 uint32_t in_end = p;
                 if (fb) {
                     const uint32_t keep = (uint32_t)(__ffs(fb) - 1);
-                    if (keep < cnt) { cnt = keep; in_end = sm.plist[keep]; }     // the next sequence starts where the kept ones end
+                    if (keep < cnt) {                                           // the next sequence starts where the kept ones end
+                        cnt = keep;
+#ifndef LZF_SIMT_EMU
+                        in_end = sm.plist[keep] - step_sa;
+#else
+                        in_end = sm.plist[keep];
+#endif
+                    }
                 }
                 if (cnt == 0) {
                     flushed = flush_stage(sm.stage, s.out, sbase, flushed, (uint32_t)s.olen, true);

@@ -31,6 +31,19 @@ def test_raw_compress_large_hashlog(gpu, oracle):
         parity.check_raw_compress(gpu, oracle, inputs, hashlog=hashlog)
 
 
+def test_packed17_table_window_edges(gpu, oracle):
+    """Repeats at distances around 64 KiB / 128 KiB / multiples inside 4 MiB blocks (packed 17-bit table + sweeps)."""
+    rng = np.random.default_rng(17)
+    a = rng.integers(0, 256, 3000, dtype=np.uint8).tobytes()
+    inputs = []
+    for dist in (65535, 65536, 65537, 131071, 131072, 131073, 196608, 262143, 262144, 1 << 20, (1 << 21) + 1):
+        filler = W.text(dist - len(a), dist).numpy().tobytes()
+        inputs.append(a + filler + a + W.lowent(5000, dist).numpy().tobytes())
+    inputs += [W.text(4 << 20, 99).numpy().tobytes(), bytes(4 << 20), W.random_bytes(1 << 20, 5).numpy().tobytes() * 4,
+               W.text(17 << 20, 98).numpy().tobytes()]           # the last one is beyond 16 MiB: plain u32 table
+    parity.check_raw_compress(gpu, oracle, inputs, caps=False)
+
+
 def test_decode_kats(gpu, oracle, vectors):
     parity.check_raw_decompress(gpu, oracle, [(bytes(k["input"]), None) for k in vectors["decode_kats"]])
     assert gpu.ctx.raw_decompress(bytes([0x11, 97, 1, 0, 0x22, 98, 99, 2, 0]))[:2] == (0, b"aaaaaabcbcbcbc")

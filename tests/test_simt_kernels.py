@@ -194,3 +194,18 @@ def test_batched_frames_pipeline_and_hash_queue(simt_lib_path, oracle, monkeypat
     finally:
         ctx.close()
         _native._lib, _native._lib_path = saved
+
+
+def test_packed17_table_window_edges(emu, oracle):
+    """Blocks > 64 KiB use the packed 17-bit table: repeats at distances around 64 KiB and 128 KiB
+    (where a modulo-2^17 position would alias) must be accepted / rejected exactly like the reference."""
+    from lz_fear_b200 import workloads as W
+    rng = np.random.default_rng(17)
+    a = rng.integers(0, 256, 3000, dtype=np.uint8).tobytes()
+    inputs = []
+    for dist in (65535, 65536, 65537, 131071, 131072, 131073, 196608, 70000):
+        filler = W.text(dist - len(a), dist).numpy().tobytes()
+        inputs.append(a + filler + a + W.lowent(5000, dist).numpy().tobytes())
+    inputs.append(W.text(400000, 99).numpy().tobytes())
+    inputs.append(bytes(300000))
+    parity.check_raw_compress(emu, oracle, inputs, caps=False)
