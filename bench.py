@@ -397,9 +397,18 @@ def main():
         # round trip property at full size: decode what we just wrote and compare on the device
         back = torch.empty_like(data)
         cap3 = len3.clone()
-        ctx.decompress_blocks(cbuf, off3, clen, nb3, back, off3, cap3, cap3, torch.zeros_like(clen), cst, None, stream=stream)
+        olen3 = torch.zeros_like(clen)
+        ctx.decompress_blocks(cbuf, off3, clen, nb3, back, off3, cap3, cap3, olen3, cst, cxx, stream=stream)
         torch.cuda.synchronize()
         assert int(cst.abs().sum().item()) == 0 and torch.equal(back, data), "compress -> decompress round trip failed"
+        # the same decode, timed: a realistic token mix (text, 4 MiB blocks) next to the synthetic config 2
+        e0.record()
+        for _ in range(K):
+            ctx.decompress_blocks(cbuf, off3, clen, nb3, back, off3, cap3, cap3, olen3, cst, cxx, stream=stream)
+        e1.record()
+        torch.cuda.synchronize()
+        comp_section["roundtrip_decompress"] = {"value": nb3 * BLOCK3 * K / GiB / (e0.elapsed_time(e1) / 1e3), "unit": "GiB/s",
+                                                "note": "decode of the blocks just written (text, 4 MiB blocks, XXH32 fused), this rank"}
         del back
 
         if not args.no_e2e:
