@@ -368,7 +368,7 @@ def main():
         cxx = torch.zeros(nb3, dtype=torch.int32, device=dev)
 
         def step_compress():
-            ctx.compress_blocks(data, off3, len3, nb3, cbuf, off3, None, clen, cst, cxx, None, stream=stream)
+            ctx.compress_blocks(data, off3, len3, nb3, cbuf, off3, None, clen, cst, cxx, None, stream=stream, max_block_len=BLOCK3)
 
         for _ in range(Wm):
             step_compress()

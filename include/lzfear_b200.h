@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define LZF_ABI_VERSION 1
+#define LZF_ABI_VERSION 2
 
 /* ---- call-level return codes ---- */
 enum {
@@ -121,11 +121,15 @@ uint64_t lzf_launch_count(const lzf_ctx* ctx);
  *                  bytes if LZF_OK, else the plaintext (block checksum, compress.rs:259-263)
  *   hashlog        0 or 12 = reference (src/raw/compress/mod.rs:15); 13..16 = larger-table extension
  *   table_kind     LZF_TABLE_U32 (framed path, compress.rs:202) or LZF_TABLE_U16 (src/lib.rs:26-27)
+ *   max_block_len  a promise that no d_in_len[b] exceeds it (the frame's block_size, compress.rs:50,227), or 0 for
+ *                  "unknown".  Up to 16 MiB it lets the kernel keep 17-bit table slots (twice as many blocks
+ *                  resident per SM); the output is the same either way.  A block that breaks the promise gets
+ *                  LZF_PANIC.
  * Output bytes are identical to the reference's for the same input.
  * ------------------------------------------------------------------------------------------ */
 int lzf_compress_blocks(lzf_ctx* ctx,
                         const uint8_t* d_in, const uint64_t* d_in_off, const uint32_t* d_in_len,
-                        uint32_t nblocks, uint32_t hashlog, uint32_t table_kind,
+                        uint32_t nblocks, uint32_t hashlog, uint32_t table_kind, uint32_t max_block_len,
                         uint8_t* d_out, const uint64_t* d_out_off, const uint32_t* d_out_cap,
                         uint32_t* d_out_len, int32_t* d_status,
                         uint32_t* d_xxh_plain, uint32_t* d_xxh_stored, void* stream);

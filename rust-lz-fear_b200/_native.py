@@ -24,7 +24,7 @@ F_INVALID_BLOCK_SIZE, F_WRITE_ERROR, F_PANIC = 20, 21, 22
 P_UNIMPLEMENTED_BLOCKSIZE, P_UNSUPPORTED_VERSION, P_RESERVED_FLAG_BITS, P_RESERVED_BD_BITS = 1, 2, 3, 4
 TABLE_U32, TABLE_U16 = 0, 1
 INCOMPRESSIBLE = 0x80000000
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class NativeLibraryError(RuntimeError):
@@ -68,7 +68,7 @@ _PROTOTYPES = {
     "lzf_destroy": (None, [_P]),
     "lzf_last_error": (C.c_char_p, [_P]),
     "lzf_launch_count": (C.c_uint64, [_P]),
-    "lzf_compress_blocks": (C.c_int, [_P, _P, _P, _P, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "lzf_compress_blocks": (C.c_int, [_P, _P, _P, _P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "lzf_decompress_blocks": (C.c_int, [_P, _P, _P, _P, C.c_uint32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "lzf_xxh32_ranges": (C.c_int, [_P, _P, _P, _P, C.c_uint32, _P, _P]),
     "lzf_raw_compress_into": (C.c_int, [_P, _P, C.c_size_t, C.c_uint32, C.c_uint32, _P, C.c_size_t,
@@ -321,9 +321,10 @@ class Context:
 
     # ---- batched blocks, device pointers, asynchronous on `stream` ------------------------------
     def compress_blocks(self, d_in, d_in_off, d_in_len, nblocks, d_out, d_out_off, d_out_cap, d_out_len, d_status,
-                        d_xxh_plain=None, d_xxh_stored=None, hashlog=12, table=TABLE_U32, stream=0):
+                        d_xxh_plain=None, d_xxh_stored=None, hashlog=12, table=TABLE_U32, stream=0, max_block_len=0):
         self._check(self._lib.lzf_compress_blocks(self._h, _ptr(d_in), _ptr(d_in_off), _ptr(d_in_len), int(nblocks),
-                                                  int(hashlog), int(table), _ptr(d_out), _ptr(d_out_off), _ptr(d_out_cap),
+                                                  int(hashlog), int(table), int(max_block_len), _ptr(d_out), _ptr(d_out_off),
+                                                  _ptr(d_out_cap),
                                                   _ptr(d_out_len), _ptr(d_status), _ptr(d_xxh_plain), _ptr(d_xxh_stored),
                                                   _P(int(stream)) if stream else None))
 

@@ -57,6 +57,7 @@ struct lzf_slot {
     Buf d_res, h_res;                   // result arenas (device / pinned host)
     Buf d_comp;                         // compressed-block scratch (frame compress)
     Buf d_io_in, d_io_out;              // staging of host-buffer calls
+    Buf d_dict, d_aux;                  // dictionary copy / dependent-block descriptors and window scratch
 };
 constexpr int kSlots = 4;
 
@@ -167,7 +168,7 @@ extern "C" void lzf_destroy(lzf_ctx* c) {
         lzf_slot& sl = c->slots[i];
         if (sl.stream) cudaStreamSynchronize(sl.stream);
         if (sl.side) cudaStreamSynchronize(sl.side);
-        Buf* dev[] = {&sl.d_tables, &sl.d_desc, &sl.d_res, &sl.d_comp, &sl.d_io_in, &sl.d_io_out};
+        Buf* dev[] = {&sl.d_tables, &sl.d_desc, &sl.d_res, &sl.d_comp, &sl.d_io_in, &sl.d_io_out, &sl.d_dict, &sl.d_aux};
         for (Buf* b : dev) if (b->p) cudaFree(b->p);
         Buf* host[] = {&sl.h_desc, &sl.h_res};
         for (Buf* b : host) if (b->p) cudaFreeHost(b->p);
@@ -223,17 +224,19 @@ int decompress_blocks_impl(lzf_ctx* c, const uint8_t* d_in, const uint64_t* d_in
                            uint32_t nblocks, const uint8_t* d_prefix, const uint64_t* d_prefix_off,
                            const uint32_t* d_prefix_len, uint8_t* d_out, const uint64_t* d_out_off,
                            const uint32_t* d_out_cap, const uint32_t* d_out_limit, uint32_t* d_out_len,
-                           int32_t* d_status, uint32_t* d_xxh_plain, cudaStream_t s) {
+                           int32_t* d_status, uint32_t* d_xxh_plain, cudaStream_t s,
+                           bool prefix_abs = false, const int32_t* d_wait_for = nullptr, uint32_t* d_done = nullptr) {
     if (nblocks == 0) return LZF_SUCCESS;
     if (!d_in || !d_in_off || !d_in_len || !d_out || !d_out_off || !d_out_cap || !d_out_limit || !d_out_len || !d_status)
         return fail(c, LZF_ERR_INVALID_ARG, "null pointer");
-    if (d_prefix && (!d_prefix_off || !d_prefix_len)) return fail(c, LZF_ERR_INVALID_ARG, "prefix triple incomplete");
+    if ((d_prefix || prefix_abs) && (!d_prefix_off || !d_prefix_len)) return fail(c, LZF_ERR_INVALID_ARG, "prefix triple incomplete");
     lzf::DecodeArgs a;
     memset(&a, 0, sizeof(a));
     a.in = d_in; a.in_off = d_in_off; a.in_len = d_in_len; a.nblocks = nblocks;
     a.prefix = d_prefix; a.prefix_off = d_prefix_off; a.prefix_len = d_prefix_len;
     a.out = d_out; a.out_off = d_out_off; a.out_cap = d_out_cap; a.out_limit = d_out_limit;
     a.out_len = d_out_len; a.status = d_status; a.xxh_plain = d_xxh_plain;
+    a.prefix_abs = prefix_abs ? 1 : 0; a.wait_for = d_wait_for; a.done = d_done;
     a.work_counter = cur_slot(c)->d_counter + 16;
     LZF_CU(c, cudaMemsetAsync(cur_slot(c)->d_counter + 16, 0, 4, s));
     LZF_LAUNCHED(c, lzf_launch_decode(&a, c->num_sms, s), 1);
@@ -243,13 +246,13 @@ int decompress_blocks_impl(lzf_ctx* c, const uint8_t* d_in, const uint64_t* d_in
 }  // namespace
 
 extern "C" int lzf_compress_blocks(lzf_ctx* c, const uint8_t* d_in, const uint64_t* d_in_off, const uint32_t* d_in_len,
-                                   uint32_t nblocks, uint32_t hashlog, uint32_t table_kind,
+                                   uint32_t nblocks, uint32_t hashlog, uint32_t table_kind, uint32_t max_block_len,
                                    uint8_t* d_out, const uint64_t* d_out_off, const uint32_t* d_out_cap,
                                    uint32_t* d_out_len, int32_t* d_status,
                                    uint32_t* d_xxh_plain, uint32_t* d_xxh_stored, void* stream) {
     if (!c) return LZF_ERR_INVALID_ARG;
     LZF_CU(c, cudaSetDevice(c->device));
-    return compress_blocks_impl(c, d_in, d_in_off, d_in_len, nblocks, hashlog, table_kind, 0, d_out, d_out_off,
+    return compress_blocks_impl(c, d_in, d_in_off, d_in_len, nblocks, hashlog, table_kind, max_block_len, d_out, d_out_off,
                                 d_out_cap, d_out_len, d_status, d_xxh_plain, d_xxh_stored, (cudaStream_t)stream);
 }
 
@@ -626,7 +629,8 @@ struct DecodeOut {          // optional extra per-frame results
 
 int frames_decompress_core(lzf_ctx* c, const uint8_t* d_in, const uint64_t* in_off, const uint64_t* in_len,
                            uint32_t nframes, uint8_t* d_out, const uint64_t* out_off, const uint64_t* out_cap,
-                           uint64_t* out_len, int32_t* status, DecodeOut extra, cudaStream_t st) {
+                           uint64_t* out_len, int32_t* status, DecodeOut extra, cudaStream_t st,
+                           const uint8_t* d_dict = nullptr, uint64_t dlen = 0) {
     if (nframes && (!in_off || !in_len || !out_off || !out_cap || !out_len || !status))
         return fail(c, LZF_ERR_INVALID_ARG, "null pointer");
     for (uint32_t f = 0; f < nframes; f++) {
@@ -677,7 +681,7 @@ int frames_decompress_core(lzf_ctx* c, const uint8_t* d_in, const uint64_t* in_o
         if (!(wf[f].flags & lzf::kFlagIndependent)) any_dependent = true;
         nblocks64 += wf[f].nblocks;
     }
-    if (any_dependent) return fail(c, LZF_ERR_UNSUPPORTED, "dependent-block frames are not on the GPU path yet");
+    if (dlen > 0xffffffffull) return fail(c, LZF_ERR_UNSUPPORTED, "dictionary larger than 4 GiB");
     if (nblocks64 > 0x7fffffffull) return fail(c, LZF_ERR_UNSUPPORTED, "too many blocks in one call");
     const uint32_t nblocks = (uint32_t)nblocks64;
 
@@ -729,10 +733,47 @@ int frames_decompress_core(lzf_ctx* c, const uint8_t* d_in, const uint64_t* in_o
         if (any_block_checksums)    // decompress.rs:228-235: hash of the stored payload
             LZF_LAUNCHED(c, lzf_launch_xxh32_ranges(d_in, (const uint64_t*)(d + o_bin_off), (const uint64_t*)(d + o_bplen),
                                                    nblocks, (uint32_t*)(r + r_bxxh), st), 1);
+        // history of every block (src/framed/decompress.rs:238-248): the dictionary for independent blocks
+        // and for the first block of a dependent frame; for block i > 0 of a dependent frame the 64 KiB of
+        // output right in front of its own slot — exact whenever the blocks before it were full, which
+        // pass 1 assumes and the resolution below verifies
+        const bool use_hist = any_dependent || dlen > 0;
+        const uint64_t* d_pf_off = nullptr; const uint32_t* d_pf_len = nullptr; const int32_t* d_wait = nullptr; uint32_t* d_done = nullptr;
+        std::vector<uint8_t> hx;
+        if (use_hist) {
+            Arena xa;
+            const size_t x_pf = xa.take((size_t)nblocks * 8), x_pl = xa.take((size_t)nblocks * 4), x_wait = xa.take((size_t)nblocks * 4);
+            const size_t x_done = xa.take((size_t)nblocks * 4);
+            hx.assign(xa.used, 0);
+            uint64_t* pf = (uint64_t*)(hx.data() + x_pf); uint32_t* pl = (uint32_t*)(hx.data() + x_pl); int32_t* wt = (int32_t*)(hx.data() + x_wait);
+            for (uint32_t f = 0; f < nframes; f++) {
+                const bool dep = wf[f].header_status == LZF_F_OK && !(wf[f].flags & lzf::kFlagIndependent);
+                const uint64_t bms = wf[f].block_maxsize;
+                for (uint32_t i = 0; i < wf[f].nblocks; i++) {
+                    const uint32_t b = first[f] + i;
+                    const uint64_t rel = (uint64_t)i * bms;
+                    wt[b] = -1;
+                    if (dep && i > 0 && rel <= out_cap[f]) {
+                        const uint64_t wlen = rel < LZF_WINDOW_SIZE ? rel : LZF_WINDOW_SIZE;
+                        pf[b] = (uint64_t)(uintptr_t)(d_out + out_off[f] + rel - wlen);
+                        pl[b] = (uint32_t)wlen;
+                        wt[b] = (int32_t)(b - 1);
+                    } else if ((!dep || i == 0) && dlen) {
+                        pf[b] = (uint64_t)(uintptr_t)d_dict;
+                        pl[b] = (uint32_t)dlen;
+                    }
+                }
+            }
+            if ((rc = ensure_dev(c, cur_slot(c)->d_aux, xa.used))) return rc;
+            uint8_t* x = (uint8_t*)cur_slot(c)->d_aux.p;
+            LZF_CU(c, cudaMemcpyAsync(x, hx.data(), xa.used, cudaMemcpyHostToDevice, st));
+            d_pf_off = (const uint64_t*)(x + x_pf); d_pf_len = (const uint32_t*)(x + x_pl);
+            if (any_dependent) { d_wait = (const int32_t*)(x + x_wait); d_done = (uint32_t*)(x + x_done); }
+        }
         rc = decompress_blocks_impl(c, d_in, (const uint64_t*)(d + o_bin_off), (const uint32_t*)(d + o_bword), nblocks,
-                                    nullptr, nullptr, nullptr, d_out, (const uint64_t*)(d + o_boff),
+                                    nullptr, d_pf_off, d_pf_len, d_out, (const uint64_t*)(d + o_boff),
                                     (const uint32_t*)(d + o_bcap), (const uint32_t*)(d + o_blim), (uint32_t*)(r + r_olen),
-                                    (int32_t*)(r + r_bst), nullptr, st);
+                                    (int32_t*)(r + r_bst), nullptr, st, use_hist, d_wait, d_done);
         if (rc) return rc;
         LZF_CU(c, cudaMemcpyAsync(hr + r_olen, r + r_olen, r_bxxh - r_olen, cudaMemcpyDeviceToHost, st));
         if (any_block_checksums) {
@@ -742,8 +783,8 @@ int frames_decompress_core(lzf_ctx* c, const uint8_t* d_in, const uint64_t* in_o
         LZF_CU(c, cudaMemcpyAsync(hr + r_bend, d + o_bend, (size_t)nblocks * 8, cudaMemcpyDeviceToHost, st));
         LZF_CU(c, cudaStreamSynchronize(st));
     }
-    const uint32_t* b_olen = (const uint32_t*)(hr + r_olen);
-    const int32_t* b_st = (const int32_t*)(hr + r_bst);
+    uint32_t* b_olen = (uint32_t*)(hr + r_olen);
+    int32_t* b_st = (int32_t*)(hr + r_bst);
     const uint32_t* b_xxh = (const uint32_t*)(hr + r_bxxh);
     const uint32_t* b_cks = (const uint32_t*)(hr + r_bcks);
     const uint64_t* b_end = (const uint64_t*)(hr + r_bend);
@@ -757,8 +798,40 @@ int frames_decompress_core(lzf_ctx* c, const uint8_t* d_in, const uint64_t* in_o
     uint64_t* hlen = (uint64_t*)(h + o_hlen);
     bool any_hash = false;
     std::vector<uint8_t> want_hash(nframes, 0);
-    std::vector<uint32_t> redo_frames;              // frames needing exact placement
+    std::vector<uint32_t> redo_frames;              // independent frames needing exact placement
     std::vector<uint32_t> delivered(nframes, 0);    // blocks whose plaintext the caller receives
+    std::vector<uint64_t> p_in_off;                 // host copies of the payload descriptors (filled on demand)
+    std::vector<uint32_t> p_word;
+    auto fetch_payload_descriptors = [&]() -> int {
+        if (!p_in_off.empty() || nblocks == 0) return LZF_SUCCESS;
+        p_in_off.resize(nblocks);
+        p_word.resize(nblocks);
+        LZF_CU(c, cudaMemcpyAsync(p_in_off.data(), d + o_bin_off, (size_t)nblocks * 8, cudaMemcpyDeviceToHost, st));
+        LZF_CU(c, cudaMemcpyAsync(p_word.data(), d + o_bword, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, st));
+        LZF_CU(c, cudaStreamSynchronize(st));
+        return LZF_SUCCESS;
+    };
+    // One block, decoded synchronously at an exact position with an exact window (slow, exact path of
+    // dependent frames with short non-final blocks).
+    auto decode_one = [&](uint32_t b, const uint8_t* pfx, uint32_t plen, uint64_t out_pos, uint32_t cap1, uint32_t lim1) -> int {
+        int rc1;
+        if ((rc1 = ensure_dev(c, cur_slot(c)->d_comp, 4096))) return rc1;
+        uint8_t* x = (uint8_t*)cur_slot(c)->d_comp.p;
+        uint8_t hb[128];
+        memset(hb, 0, sizeof(hb));
+        *(uint64_t*)(hb + 0) = p_in_off[b]; *(uint64_t*)(hb + 8) = out_pos; *(uint64_t*)(hb + 16) = (uint64_t)(uintptr_t)pfx;
+        *(uint32_t*)(hb + 24) = p_word[b]; *(uint32_t*)(hb + 28) = cap1; *(uint32_t*)(hb + 32) = lim1; *(uint32_t*)(hb + 36) = plen;
+        LZF_CU(c, cudaMemcpyAsync(x, hb, 128, cudaMemcpyHostToDevice, st));
+        rc1 = decompress_blocks_impl(c, d_in, (const uint64_t*)x, (const uint32_t*)(x + 24), 1, nullptr, (const uint64_t*)(x + 16),
+                                     (const uint32_t*)(x + 36), d_out, (const uint64_t*)(x + 8), (const uint32_t*)(x + 28),
+                                     (const uint32_t*)(x + 32), (uint32_t*)(x + 64), (int32_t*)(x + 68), nullptr, st, true);
+        if (rc1) return rc1;
+        LZF_CU(c, cudaMemcpyAsync(hb + 64, x + 64, 8, cudaMemcpyDeviceToHost, st));
+        LZF_CU(c, cudaStreamSynchronize(st));
+        b_olen[b] = *(uint32_t*)(hb + 64);
+        b_st[b] = *(int32_t*)(hb + 68);
+        return LZF_SUCCESS;
+    };
     for (uint32_t f = 0; f < nframes; f++) {
         hoff[f] = out_off[f]; hlen[f] = 0;
         const lzf::WalkFrame& w = wf[f];
@@ -769,23 +842,48 @@ int frames_decompress_core(lzf_ctx* c, const uint8_t* d_in, const uint64_t* in_o
         }
         const uint64_t bms = w.block_maxsize;
         const bool bc = (w.flags & lzf::kFlagBlockChecksums) != 0;
+        const bool dep = !(w.flags & lzf::kFlagIndependent);
         const uint64_t capf = out_cap[f];
         uint64_t o = 0;
         int fs = LZF_F_OK, det = 0;
         uint64_t consumed = w.consumed;
         bool early_stop = false, irregular = false;
+        bool exact = false;          // dependent frame: from here on blocks are (re)decoded one by one, exactly placed
         uint32_t i = 0;
         for (; i < w.nblocks; i++) {
             const uint32_t b = first[f] + i;
             if (bc && b_xxh[b] != b_cks[b]) { fs = LZF_F_BLOCK_CHECKSUM_FAIL; break; }                     // :228-235
+            if (exact) {
+                // window = last 64 KiB of dictionary ++ output so far (decompress.rs:253-269)
+                if ((rc = fetch_payload_descriptors())) return rc;
+                const uint8_t* pfx;
+                uint32_t plen;
+                if (o >= LZF_WINDOW_SIZE) { pfx = d_out + out_off[f] + o - LZF_WINDOW_SIZE; plen = LZF_WINDOW_SIZE; }
+                else if (o == 0) { pfx = d_dict; plen = (uint32_t)dlen; }
+                else {
+                    const uint64_t from_dict = dlen < LZF_WINDOW_SIZE - o ? dlen : LZF_WINDOW_SIZE - o;
+                    if ((rc = ensure_dev(c, cur_slot(c)->d_aux, 2 * LZF_WINDOW_SIZE))) return rc;
+                    uint8_t* wb = (uint8_t*)cur_slot(c)->d_aux.p;
+                    if (from_dict) LZF_CU(c, cudaMemcpyAsync(wb, d_dict + dlen - from_dict, from_dict, cudaMemcpyDeviceToDevice, st));
+                    LZF_CU(c, cudaMemcpyAsync(wb + from_dict, d_out + out_off[f], o, cudaMemcpyDeviceToDevice, st));
+                    pfx = wb; plen = (uint32_t)(from_dict + o);
+                }
+                const uint64_t room = capf - o;
+                if ((rc = decode_one(b, pfx, plen, out_off[f] + o, (uint32_t)(room < bms ? room : bms), (uint32_t)bms))) return rc;
+            }
             const int bst = b_st[b];
             if (bst >= LZF_UNEXPECTED_END && bst <= LZF_INVALID_DEDUP_OFFSET) { fs = LZF_F_CODEC_ERROR; det = bst; break; }   // :247-248
             const uint64_t ol = b_olen[b];
             if (ol > bms) { fs = LZF_F_BLOCK_SIZE_OVERFLOW; break; }                                        // :272-274
             if (o + ol > capf) { fs = LZF_F_WRITE_ERROR; break; }
-            const uint64_t rel = (uint64_t)i * bms;
-            const uint64_t slot_cap = rel < capf ? (bms < capf - rel ? bms : capf - rel) : 0;
-            if (ol && (o != rel || ol > slot_cap)) irregular = true;
+            if (!exact) {
+                const uint64_t rel = (uint64_t)i * bms;
+                const uint64_t slot_cap = rel < capf ? (bms < capf - rel ? bms : capf - rel) : 0;
+                if (ol && (o != rel || ol > slot_cap)) irregular = true;
+                // a dependent frame stops being regular at the first short block: everything after it saw the
+                // wrong window in pass 1 and is decoded again, one block at a time
+                if (dep && ol != bms) exact = true;
+            }
             o += ol;
             if (ol == 0) { early_stop = true; consumed = b_end[b]; i++; break; }   // read_to_end sees Ok(0): decompress.rs:54-61,286
         }
@@ -797,24 +895,19 @@ int frames_decompress_core(lzf_ctx* c, const uint8_t* d_in, const uint64_t* in_o
         status[f] = fs;
         out_len[f] = o;
         hlen[f] = o;
-        if (irregular) redo_frames.push_back(f);
+        if (irregular && !dep) redo_frames.push_back(f);
         if (extra.detail) extra.detail[f] = det;
         if (extra.consumed) extra.consumed[f] = consumed;
     }
-    bool synced = true;
     if (!redo_frames.empty()) {
         uint32_t nredo = 0;
         for (uint32_t f : redo_frames) nredo += delivered[f];
-        // host copies of the payload descriptors of pass 1
-        std::vector<uint64_t> p_in_off(nblocks);
-        std::vector<uint32_t> p_word(nblocks);
-        LZF_CU(c, cudaMemcpyAsync(p_in_off.data(), d + o_bin_off, (size_t)nblocks * 8, cudaMemcpyDeviceToHost, st));
-        LZF_CU(c, cudaMemcpyAsync(p_word.data(), d + o_bword, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, st));
-        LZF_CU(c, cudaStreamSynchronize(st));
+        if ((rc = fetch_payload_descriptors())) return rc;
         Arena xa;
         const size_t x_in_off = xa.take((size_t)nredo * 8), x_word = xa.take((size_t)nredo * 4);
         const size_t x_out_off = xa.take((size_t)nredo * 8), x_cap = xa.take((size_t)nredo * 4);
         const size_t x_lim = xa.take((size_t)nredo * 4), x_olen = xa.take((size_t)nredo * 4), x_st = xa.take((size_t)nredo * 4);
+        const size_t x_pf = xa.take((size_t)nredo * 8), x_pl = xa.take((size_t)nredo * 4);
         std::vector<uint8_t> xh(xa.used);
         uint32_t k = 0;
         for (uint32_t f : redo_frames) {
@@ -826,6 +919,8 @@ int frames_decompress_core(lzf_ctx* c, const uint8_t* d_in, const uint64_t* in_o
                 ((uint64_t*)(xh.data() + x_out_off))[k] = out_off[f] + o;
                 ((uint32_t*)(xh.data() + x_cap))[k] = b_olen[b];
                 ((uint32_t*)(xh.data() + x_lim))[k] = (uint32_t)wf[f].block_maxsize;
+                ((uint64_t*)(xh.data() + x_pf))[k] = (uint64_t)(uintptr_t)d_dict;
+                ((uint32_t*)(xh.data() + x_pl))[k] = (uint32_t)dlen;
                 o += b_olen[b];
             }
         }
@@ -833,14 +928,12 @@ int frames_decompress_core(lzf_ctx* c, const uint8_t* d_in, const uint64_t* in_o
         uint8_t* x = (uint8_t*)cur_slot(c)->d_comp.p;
         LZF_CU(c, cudaMemcpyAsync(x, xh.data(), xa.used, cudaMemcpyHostToDevice, st));
         rc = decompress_blocks_impl(c, d_in, (const uint64_t*)(x + x_in_off), (const uint32_t*)(x + x_word), nredo,
-                                    nullptr, nullptr, nullptr, d_out, (const uint64_t*)(x + x_out_off),
-                                    (const uint32_t*)(x + x_cap), (const uint32_t*)(x + x_lim), (uint32_t*)(x + x_olen),
-                                    (int32_t*)(x + x_st), nullptr, st);
+                                    nullptr, (const uint64_t*)(x + x_pf), (const uint32_t*)(x + x_pl), d_out,
+                                    (const uint64_t*)(x + x_out_off), (const uint32_t*)(x + x_cap), (const uint32_t*)(x + x_lim),
+                                    (uint32_t*)(x + x_olen), (int32_t*)(x + x_st), nullptr, st, true);
         if (rc) return rc;
         LZF_CU(c, cudaStreamSynchronize(st));    // xh must outlive the copy
-        synced = true;
     }
-    (void)synced;
     if (any_hash) {       // content checksum over the frame's plaintext (decompress.rs:207-211,276-278)
         LZF_CU(c, cudaMemcpyAsync(d + o_hoff, h + o_hoff, frame_desc_bytes - o_hoff, cudaMemcpyHostToDevice, st));
         LZF_LAUNCHED(c, lzf_launch_xxh32_ranges(d_out, (const uint64_t*)(d + o_hoff), (const uint64_t*)(d + o_hlen), nframes,
@@ -1013,7 +1106,8 @@ namespace {
 
 int decompress_chunk(lzf_ctx* c, lzf_slot& sl, uint32_t f0, uint32_t f1, const uint8_t* in, const uint64_t* in_off,
                      const uint64_t* in_len, uint8_t* out, const uint64_t* out_off, const uint64_t* out_cap,
-                     uint64_t* out_len, int32_t* status, int32_t* detail, uint64_t* consumed) {
+                     uint64_t* out_len, int32_t* status, int32_t* detail, uint64_t* consumed,
+                     const uint8_t* dict, uint64_t dlen) {
     const uint32_t n = f1 - f0;
     std::vector<uint64_t> dcap(n);
     for (uint32_t f = 0; f < n; f++) {
@@ -1036,9 +1130,13 @@ int decompress_chunk(lzf_ctx* c, lzf_slot& sl, uint32_t f0, uint32_t f1, const u
             if (in_len[f0 + f])
                 LZF_CU(c, cudaMemcpyAsync(din + li.dev_off[f], in + in_off[f0 + f], in_len[f0 + f], cudaMemcpyHostToDevice, sl.stream));
     }
+    if (dlen) {
+        if ((rc = ensure_dev(c, sl.d_dict, dlen + 16))) return rc;
+        LZF_CU(c, cudaMemcpyAsync(sl.d_dict.p, dict, dlen, cudaMemcpyHostToDevice, sl.stream));
+    }
     DecodeOut ex{consumed ? consumed + f0 : nullptr, detail ? detail + f0 : nullptr};
     rc = frames_decompress_core(c, din, li.dev_off.data(), in_len + f0, n, (uint8_t*)sl.d_io_out.p, lo.dev_off.data(),
-                                dcap.data(), out_len + f0, status + f0, ex, sl.stream);
+                                dcap.data(), out_len + f0, status + f0, ex, sl.stream, dlen ? (const uint8_t*)sl.d_dict.p : nullptr, dlen);
     if (rc) return rc;
     bool full = lo.dense;      // every frame filled its capacity exactly: one copy moves the whole run
     for (uint32_t f = f0; f < f1 && full; f++) full = out_len[f] == dcap[f - f0];
@@ -1055,7 +1153,8 @@ int decompress_chunk(lzf_ctx* c, lzf_slot& sl, uint32_t f0, uint32_t f1, const u
 
 int frames_decompress_host(lzf_ctx* c, const uint8_t* in, const uint64_t* in_off, const uint64_t* in_len,
                            uint32_t nframes, uint8_t* out, const uint64_t* out_off, const uint64_t* out_cap,
-                           uint64_t* out_len, int32_t* status, int32_t* detail, uint64_t* consumed) {
+                           uint64_t* out_len, int32_t* status, int32_t* detail, uint64_t* consumed,
+                           const uint8_t* dict = nullptr, uint64_t dlen = 0) {
     if (nframes && (!in_off || !in_len || !out_off || !out_cap || !out_len || !status))
         return fail(c, LZF_ERR_INVALID_ARG, "null pointer");
     LZF_CU(c, cudaSetDevice(c->device));
@@ -1068,7 +1167,7 @@ int frames_decompress_host(lzf_ctx* c, const uint8_t* in, const uint64_t* in_off
     const std::vector<uint32_t> chunks = plan_chunks(weight.data(), nframes, c->chunk_bytes);
     return run_chunks(c, (uint32_t)chunks.size() - 1, [&](uint32_t i, lzf_slot& sl) {
         return decompress_chunk(c, sl, chunks[i], chunks[i + 1], in, in_off, in_len, out, out_off, out_cap, out_len, status,
-                                detail, consumed);
+                                detail, consumed, dict, dlen);
     });
 }
 }  // namespace
@@ -1084,11 +1183,11 @@ extern "C" int lzf_frame_decompress(lzf_ctx* c, const uint8_t* in, size_t n, con
                                     uint8_t* out, size_t cap, size_t* written, size_t* consumed,
                                     int32_t* status, int32_t* detail) {
     if (!c || !written || !status) return LZF_ERR_INVALID_ARG;
-    if (dict && dlen) return fail(c, LZF_ERR_UNSUPPORTED, "dictionaries are not on the GPU path yet");
     const uint64_t in_off = 0, in_len = n, out_off = 0, out_cap = cap;
     uint64_t out_len = 0, cons = 0;
     int32_t det = 0;
-    const int rc = frames_decompress_host(c, in, &in_off, &in_len, 1, out, &out_off, &out_cap, &out_len, status, &det, &cons);
+    const int rc = frames_decompress_host(c, in, &in_off, &in_len, 1, out, &out_off, &out_cap, &out_len, status, &det, &cons,
+                                          dlen ? dict : nullptr, dlen);
     *written = (size_t)out_len;
     if (consumed) *consumed = (size_t)cons;
     if (detail) *detail = det;

@@ -180,8 +180,19 @@ __device__ __forceinline__ uint32_t warp_xxh32_x8(const uint8_t* p, uint64_t n) 
 // CTA hashes the remainder.  Keeps the checksum fused in the block kernel at 1/8 of the issue cost.
 #ifdef LZF_SIMT_EMU
 __device__ __forceinline__ void spin_pause() { simt::yield(); }
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) { return *(const volatile uint32_t*)p; }
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) { *(volatile uint32_t*)p = v; }
 #else
 __device__ __forceinline__ void spin_pause() { __nanosleep(32); }
+// gpu-scope acquire / release on a flag in global memory (the acquire also drops stale L1 lines)
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 #endif
 
 constexpr uint32_t kHashRing = 64;     // entries; a power of two, multiple of 8

@@ -222,233 +222,70 @@ __device__ __noinline__ uint32_t walk32(uint32_t& pp, uint32_t plist) {
     asm volatile(
         "{\n\t"
         ".reg .pred q;\n\t"
-        ".reg .u32 d;\n\t"
+        ".reg .u32 d, pl;\n\t"
+        "mov.u32 %0, 0;\n\t"
+        "mov.u32 pl, %2;\n\t"
+        "WALK_LOOP:\n\t"
         "ld.shared.u8 d, [%1];\n\t"
         "setp.eq.u32 q, d, 0;\n\t"
         "@q bra.uni WALK_DONE_0;\n\t"
-        "st.shared.u32 [%2+0], %1;\n\t"
+        "st.shared.u32 [pl+0], %1;\n\t"
         "add.u32 %1, %1, d;\n\t"
         "ld.shared.u8 d, [%1];\n\t"
         "setp.eq.u32 q, d, 0;\n\t"
         "@q bra.uni WALK_DONE_1;\n\t"
-        "st.shared.u32 [%2+4], %1;\n\t"
+        "st.shared.u32 [pl+4], %1;\n\t"
         "add.u32 %1, %1, d;\n\t"
         "ld.shared.u8 d, [%1];\n\t"
         "setp.eq.u32 q, d, 0;\n\t"
         "@q bra.uni WALK_DONE_2;\n\t"
-        "st.shared.u32 [%2+8], %1;\n\t"
+        "st.shared.u32 [pl+8], %1;\n\t"
         "add.u32 %1, %1, d;\n\t"
         "ld.shared.u8 d, [%1];\n\t"
         "setp.eq.u32 q, d, 0;\n\t"
         "@q bra.uni WALK_DONE_3;\n\t"
-        "st.shared.u32 [%2+12], %1;\n\t"
+        "st.shared.u32 [pl+12], %1;\n\t"
         "add.u32 %1, %1, d;\n\t"
         "ld.shared.u8 d, [%1];\n\t"
         "setp.eq.u32 q, d, 0;\n\t"
         "@q bra.uni WALK_DONE_4;\n\t"
-        "st.shared.u32 [%2+16], %1;\n\t"
+        "st.shared.u32 [pl+16], %1;\n\t"
         "add.u32 %1, %1, d;\n\t"
         "ld.shared.u8 d, [%1];\n\t"
         "setp.eq.u32 q, d, 0;\n\t"
         "@q bra.uni WALK_DONE_5;\n\t"
-        "st.shared.u32 [%2+20], %1;\n\t"
+        "st.shared.u32 [pl+20], %1;\n\t"
         "add.u32 %1, %1, d;\n\t"
         "ld.shared.u8 d, [%1];\n\t"
         "setp.eq.u32 q, d, 0;\n\t"
         "@q bra.uni WALK_DONE_6;\n\t"
-        "st.shared.u32 [%2+24], %1;\n\t"
+        "st.shared.u32 [pl+24], %1;\n\t"
         "add.u32 %1, %1, d;\n\t"
         "ld.shared.u8 d, [%1];\n\t"
         "setp.eq.u32 q, d, 0;\n\t"
         "@q bra.uni WALK_DONE_7;\n\t"
-        "st.shared.u32 [%2+28], %1;\n\t"
+        "st.shared.u32 [pl+28], %1;\n\t"
         "add.u32 %1, %1, d;\n\t"
-        "ld.shared.u8 d, [%1];\n\t"
-        "setp.eq.u32 q, d, 0;\n\t"
-        "@q bra.uni WALK_DONE_8;\n\t"
-        "st.shared.u32 [%2+32], %1;\n\t"
-        "add.u32 %1, %1, d;\n\t"
-        "ld.shared.u8 d, [%1];\n\t"
-        "setp.eq.u32 q, d, 0;\n\t"
-        "@q bra.uni WALK_DONE_9;\n\t"
-        "st.shared.u32 [%2+36], %1;\n\t"
-        "add.u32 %1, %1, d;\n\t"
-        "ld.shared.u8 d, [%1];\n\t"
-        "setp.eq.u32 q, d, 0;\n\t"
-        "@q bra.uni WALK_DONE_10;\n\t"
-        "st.shared.u32 [%2+40], %1;\n\t"
-        "add.u32 %1, %1, d;\n\t"
-        "ld.shared.u8 d, [%1];\n\t"
-        "setp.eq.u32 q, d, 0;\n\t"
-        "@q bra.uni WALK_DONE_11;\n\t"
-        "st.shared.u32 [%2+44], %1;\n\t"
-        "add.u32 %1, %1, d;\n\t"
-        "ld.shared.u8 d, [%1];\n\t"
-        "setp.eq.u32 q, d, 0;\n\t"
-        "@q bra.uni WALK_DONE_12;\n\t"
-        "st.shared.u32 [%2+48], %1;\n\t"
-        "add.u32 %1, %1, d;\n\t"
-        "ld.shared.u8 d, [%1];\n\t"
-        "setp.eq.u32 q, d, 0;\n\t"
-        "@q bra.uni WALK_DONE_13;\n\t"
-        "st.shared.u32 [%2+52], %1;\n\t"
-        "add.u32 %1, %1, d;\n\t"
-        "ld.shared.u8 d, [%1];\n\t"
-        "setp.eq.u32 q, d, 0;\n\t"
-        "@q bra.uni WALK_DONE_14;\n\t"
-        "st.shared.u32 [%2+56], %1;\n\t"
-        "add.u32 %1, %1, d;\n\t"
-        "ld.shared.u8 d, [%1];\n\t"
-        "setp.eq.u32 q, d, 0;\n\t"
-        "@q bra.uni WALK_DONE_15;\n\t"
-        "st.shared.u32 [%2+60], %1;\n\t"
-        "add.u32 %1, %1, d;\n\t"
-        "ld.shared.u8 d, [%1];\n\t"
-        "setp.eq.u32 q, d, 0;\n\t"
-        "@q bra.uni WALK_DONE_16;\n\t"
-        "st.shared.u32 [%2+64], %1;\n\t"
-        "add.u32 %1, %1, d;\n\t"
-        "ld.shared.u8 d, [%1];\n\t"
-        "setp.eq.u32 q, d, 0;\n\t"
-        "@q bra.uni WALK_DONE_17;\n\t"
-        "st.shared.u32 [%2+68], %1;\n\t"
-        "add.u32 %1, %1, d;\n\t"
-        "ld.shared.u8 d, [%1];\n\t"
-        "setp.eq.u32 q, d, 0;\n\t"
-        "@q bra.uni WALK_DONE_18;\n\t"
-        "st.shared.u32 [%2+72], %1;\n\t"
-        "add.u32 %1, %1, d;\n\t"
-        "ld.shared.u8 d, [%1];\n\t"
-        "setp.eq.u32 q, d, 0;\n\t"
-        "@q bra.uni WALK_DONE_19;\n\t"
-        "st.shared.u32 [%2+76], %1;\n\t"
-        "add.u32 %1, %1, d;\n\t"
-        "ld.shared.u8 d, [%1];\n\t"
-        "setp.eq.u32 q, d, 0;\n\t"
-        "@q bra.uni WALK_DONE_20;\n\t"
-        "st.shared.u32 [%2+80], %1;\n\t"
-        "add.u32 %1, %1, d;\n\t"
-        "ld.shared.u8 d, [%1];\n\t"
-        "setp.eq.u32 q, d, 0;\n\t"
-        "@q bra.uni WALK_DONE_21;\n\t"
-        "st.shared.u32 [%2+84], %1;\n\t"
-        "add.u32 %1, %1, d;\n\t"
-        "ld.shared.u8 d, [%1];\n\t"
-        "setp.eq.u32 q, d, 0;\n\t"
-        "@q bra.uni WALK_DONE_22;\n\t"
-        "st.shared.u32 [%2+88], %1;\n\t"
-        "add.u32 %1, %1, d;\n\t"
-        "ld.shared.u8 d, [%1];\n\t"
-        "setp.eq.u32 q, d, 0;\n\t"
-        "@q bra.uni WALK_DONE_23;\n\t"
-        "st.shared.u32 [%2+92], %1;\n\t"
-        "add.u32 %1, %1, d;\n\t"
-        "ld.shared.u8 d, [%1];\n\t"
-        "setp.eq.u32 q, d, 0;\n\t"
-        "@q bra.uni WALK_DONE_24;\n\t"
-        "st.shared.u32 [%2+96], %1;\n\t"
-        "add.u32 %1, %1, d;\n\t"
-        "ld.shared.u8 d, [%1];\n\t"
-        "setp.eq.u32 q, d, 0;\n\t"
-        "@q bra.uni WALK_DONE_25;\n\t"
-        "st.shared.u32 [%2+100], %1;\n\t"
-        "add.u32 %1, %1, d;\n\t"
-        "ld.shared.u8 d, [%1];\n\t"
-        "setp.eq.u32 q, d, 0;\n\t"
-        "@q bra.uni WALK_DONE_26;\n\t"
-        "st.shared.u32 [%2+104], %1;\n\t"
-        "add.u32 %1, %1, d;\n\t"
-        "ld.shared.u8 d, [%1];\n\t"
-        "setp.eq.u32 q, d, 0;\n\t"
-        "@q bra.uni WALK_DONE_27;\n\t"
-        "st.shared.u32 [%2+108], %1;\n\t"
-        "add.u32 %1, %1, d;\n\t"
-        "ld.shared.u8 d, [%1];\n\t"
-        "setp.eq.u32 q, d, 0;\n\t"
-        "@q bra.uni WALK_DONE_28;\n\t"
-        "st.shared.u32 [%2+112], %1;\n\t"
-        "add.u32 %1, %1, d;\n\t"
-        "ld.shared.u8 d, [%1];\n\t"
-        "setp.eq.u32 q, d, 0;\n\t"
-        "@q bra.uni WALK_DONE_29;\n\t"
-        "st.shared.u32 [%2+116], %1;\n\t"
-        "add.u32 %1, %1, d;\n\t"
-        "ld.shared.u8 d, [%1];\n\t"
-        "setp.eq.u32 q, d, 0;\n\t"
-        "@q bra.uni WALK_DONE_30;\n\t"
-        "st.shared.u32 [%2+120], %1;\n\t"
-        "add.u32 %1, %1, d;\n\t"
-        "ld.shared.u8 d, [%1];\n\t"
-        "setp.eq.u32 q, d, 0;\n\t"
-        "@q bra.uni WALK_DONE_31;\n\t"
-        "st.shared.u32 [%2+124], %1;\n\t"
-        "add.u32 %1, %1, d;\n\t"
-        "mov.u32 %0, 32;\n\t"
+        "add.u32 pl, pl, 32;\n\t"
+        "add.u32 %0, %0, 8;\n\t"
+        "setp.lt.u32 q, %0, 32;\n\t"
+        "@q bra.uni WALK_LOOP;\n\t"
         "bra.uni WALK_END;\n\t"
-        "WALK_DONE_0: mov.u32 %0, 0;\n\t"
+        "WALK_DONE_1: add.u32 %0, %0, 1;\n\t"
         "bra.uni WALK_END;\n\t"
-        "WALK_DONE_1: mov.u32 %0, 1;\n\t"
+        "WALK_DONE_2: add.u32 %0, %0, 2;\n\t"
         "bra.uni WALK_END;\n\t"
-        "WALK_DONE_2: mov.u32 %0, 2;\n\t"
+        "WALK_DONE_3: add.u32 %0, %0, 3;\n\t"
         "bra.uni WALK_END;\n\t"
-        "WALK_DONE_3: mov.u32 %0, 3;\n\t"
+        "WALK_DONE_4: add.u32 %0, %0, 4;\n\t"
         "bra.uni WALK_END;\n\t"
-        "WALK_DONE_4: mov.u32 %0, 4;\n\t"
+        "WALK_DONE_5: add.u32 %0, %0, 5;\n\t"
         "bra.uni WALK_END;\n\t"
-        "WALK_DONE_5: mov.u32 %0, 5;\n\t"
+        "WALK_DONE_6: add.u32 %0, %0, 6;\n\t"
         "bra.uni WALK_END;\n\t"
-        "WALK_DONE_6: mov.u32 %0, 6;\n\t"
+        "WALK_DONE_7: add.u32 %0, %0, 7;\n\t"
         "bra.uni WALK_END;\n\t"
-        "WALK_DONE_7: mov.u32 %0, 7;\n\t"
-        "bra.uni WALK_END;\n\t"
-        "WALK_DONE_8: mov.u32 %0, 8;\n\t"
-        "bra.uni WALK_END;\n\t"
-        "WALK_DONE_9: mov.u32 %0, 9;\n\t"
-        "bra.uni WALK_END;\n\t"
-        "WALK_DONE_10: mov.u32 %0, 10;\n\t"
-        "bra.uni WALK_END;\n\t"
-        "WALK_DONE_11: mov.u32 %0, 11;\n\t"
-        "bra.uni WALK_END;\n\t"
-        "WALK_DONE_12: mov.u32 %0, 12;\n\t"
-        "bra.uni WALK_END;\n\t"
-        "WALK_DONE_13: mov.u32 %0, 13;\n\t"
-        "bra.uni WALK_END;\n\t"
-        "WALK_DONE_14: mov.u32 %0, 14;\n\t"
-        "bra.uni WALK_END;\n\t"
-        "WALK_DONE_15: mov.u32 %0, 15;\n\t"
-        "bra.uni WALK_END;\n\t"
-        "WALK_DONE_16: mov.u32 %0, 16;\n\t"
-        "bra.uni WALK_END;\n\t"
-        "WALK_DONE_17: mov.u32 %0, 17;\n\t"
-        "bra.uni WALK_END;\n\t"
-        "WALK_DONE_18: mov.u32 %0, 18;\n\t"
-        "bra.uni WALK_END;\n\t"
-        "WALK_DONE_19: mov.u32 %0, 19;\n\t"
-        "bra.uni WALK_END;\n\t"
-        "WALK_DONE_20: mov.u32 %0, 20;\n\t"
-        "bra.uni WALK_END;\n\t"
-        "WALK_DONE_21: mov.u32 %0, 21;\n\t"
-        "bra.uni WALK_END;\n\t"
-        "WALK_DONE_22: mov.u32 %0, 22;\n\t"
-        "bra.uni WALK_END;\n\t"
-        "WALK_DONE_23: mov.u32 %0, 23;\n\t"
-        "bra.uni WALK_END;\n\t"
-        "WALK_DONE_24: mov.u32 %0, 24;\n\t"
-        "bra.uni WALK_END;\n\t"
-        "WALK_DONE_25: mov.u32 %0, 25;\n\t"
-        "bra.uni WALK_END;\n\t"
-        "WALK_DONE_26: mov.u32 %0, 26;\n\t"
-        "bra.uni WALK_END;\n\t"
-        "WALK_DONE_27: mov.u32 %0, 27;\n\t"
-        "bra.uni WALK_END;\n\t"
-        "WALK_DONE_28: mov.u32 %0, 28;\n\t"
-        "bra.uni WALK_END;\n\t"
-        "WALK_DONE_29: mov.u32 %0, 29;\n\t"
-        "bra.uni WALK_END;\n\t"
-        "WALK_DONE_30: mov.u32 %0, 30;\n\t"
-        "bra.uni WALK_END;\n\t"
-        "WALK_DONE_31: mov.u32 %0, 31;\n\t"
-        "bra.uni WALK_END;\n\t"
+        "WALK_DONE_0:\n\t"
         "WALK_END:\n\t"
         "}"
         : "=r"(cnt), "+r"(pp)
@@ -481,8 +318,22 @@ decode_blocks_kernel(DecodeArgs a) {
         s.out = a.out + a.out_off[b];
         s.cap = a.out_cap[b];
         s.limit = a.out_limit[b];
-        s.plen = a.prefix ? a.prefix_len[b] : 0;
-        s.prefix_end = a.prefix ? a.prefix + a.prefix_off[b] + s.plen : nullptr;
+        const bool has_prefix = a.prefix != nullptr || a.prefix_abs;
+        s.plen = has_prefix ? a.prefix_len[b] : 0;
+        s.prefix_end = !has_prefix ? nullptr
+                       : a.prefix_abs ? reinterpret_cast<const uint8_t*>((uintptr_t)a.prefix_off[b]) + s.plen
+                                      : a.prefix + a.prefix_off[b] + s.plen;
+        if (a.wait_for) {
+            // dependent block (src/framed/decompress.rs:238-269): its window is the output of the block
+            // before it; the dynamic queue hands blocks out in ascending order, so the predecessor is
+            // already running (or done) on some warp
+            const int32_t w = a.wait_for[b];
+            if (w >= 0) {
+                if (lane == 0) while (ld_acquire_gpu(a.done + w) == 0) spin_pause();
+                __syncwarp();
+                __threadfence();
+            }
+        }
         s.pos = 0; s.olen = 0; s.status = LZF_OK; s.dry = false; s.finished = false;
 
         if (len_word & LZF_INCOMPRESSIBLE) {
@@ -645,6 +496,11 @@ decode_blocks_kernel(DecodeArgs a) {
         if (lane == 0) {
             a.out_len[b] = (uint32_t)(s.olen > 0xffffffffull ? 0xffffffffull : s.olen);
             a.status[b] = s.status;
+        }
+        if (a.done) {
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) st_release_gpu(a.done + b, 1u);
         }
         if (a.xxh_plain) {
             // XXH32 of the decoded bytes: queued so that 8 blocks are hashed per warp pass

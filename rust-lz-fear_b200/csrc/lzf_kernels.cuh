@@ -18,6 +18,10 @@ struct DecodeArgs {
     uint8_t* out; const uint64_t* out_off; const uint32_t* out_cap; const uint32_t* out_limit;
     uint32_t* out_len; int32_t* status; uint32_t* xxh_plain;
     uint32_t* work_counter;
+    // internal (frame layer): dependent blocks.  prefix_abs: prefix_off[] holds absolute device addresses
+    // (history of a dependent block = the previous blocks' output in front of its own).  wait_for[b] >= 0:
+    // block b may only start once block wait_for[b] (always a lower index) has set done[wait_for[b]].
+    int prefix_abs; const int32_t* wait_for; uint32_t* done;
 };
 struct LayoutArgs {
     uint32_t nframes;

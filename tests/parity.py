@@ -145,7 +145,7 @@ def check_frames(backend, oracle, inputs, settings_list=FRAME_SETTINGS):
             assert st == 0 and plain == data and cons == ocons == len(frame)
 
 
-def check_frame_decode_errors(backend, oracle, frames, dependent_ok=False):
+def check_frame_decode_errors(backend, oracle, frames, dependent_ok=True, dictionary=b""):
     """Arbitrary / mutated frames: status, detail and the plaintext decoded before the failure."""
     n_ok = 0
     for blob in frames:
@@ -157,8 +157,8 @@ def check_frame_decode_errors(backend, oracle, frames, dependent_ok=False):
             if not (info.flags & 0x20) and not dependent_ok:
                 continue           # dependent-block frames: not on the GPU path yet
         cap = 1 << 22
-        orc, odet, oplain, ocons = oracle.frame_decompress(blob, cap=cap)
-        st, det, plain, cons = backend.ctx.frame_decompress(blob, cap=cap)
+        orc, odet, oplain, ocons = oracle.frame_decompress(blob, dictionary=dictionary, cap=cap)
+        st, det, plain, cons = backend.ctx.frame_decompress(blob, dictionary=dictionary, cap=cap)
         assert (st, det) == (orc, odet), "frame status %s vs oracle %s (len %d)" % ((st, det), (orc, odet), len(blob))
         assert plain == oplain, "plaintext before failure differs (status %d)" % st
         if st == 0:

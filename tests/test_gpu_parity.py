@@ -214,3 +214,21 @@ def test_streaming_xxh32_and_host_mirror(gpu, oracle):
     L.raw.decompress_raw(oracle.compress_block(data)[1], b"", buf, 1 << 30)
     assert bytes(buf) == data
     L.raw.set_default_context(None)
+
+
+def test_dependent_and_dictionary_frames(gpu, oracle, issue15_input, corpora, liblz4):
+    """Decode side of SURVEY §8(f) rank 2: dependent-block frames (block i waits for block i-1 inside the
+    kernel), dictionaries, C-written linked frames, and the block-at-a-time exact path."""
+    import test_simt_kernels as T
+    from test_oracle import lz4f_compress
+    T.test_dependent_block_frames_decode(gpu, oracle, issue15_input)
+    T.test_dictionary_frames_decode(gpu, oracle)
+    T.test_dependent_frames_with_short_blocks(gpu, oracle)
+    data = (W.text(3 << 20, 5).numpy().tobytes() + W.lowent(1 << 20, 6).numpy().tobytes()) * 2
+    for kw in (dict(blockSizeID=4, blockMode=0, contentChecksumFlag=1), dict(blockSizeID=7, blockMode=0, blockChecksumFlag=1),
+               dict(blockSizeID=5, blockMode=0, compressionLevel=4, contentChecksumFlag=1)):
+        frame = lz4f_compress(liblz4, data, **kw)               # blockMode 0 = linked (dependent) blocks
+        st, det, plain, cons = gpu.ctx.frame_decompress(frame, cap=len(data) + 16)
+        assert (st, plain) == (0, data), kw
+    rc, fr = oracle.frame_compress(data, independent_blocks=False, block_size=64 << 10)
+    assert gpu.ctx.frame_decompress(fr, cap=len(data) + 16)[:3] == (0, 0, data)

@@ -209,3 +209,64 @@ def test_packed17_table_window_edges(emu, oracle):
     inputs.append(W.text(400000, 99).numpy().tobytes())
     inputs.append(bytes(300000))
     parity.check_raw_compress(emu, oracle, inputs, caps=False)
+
+
+def _dependent_frames(oracle):
+    from lz_fear_b200 import workloads as W
+    data = W.text(200000, 41).numpy().tobytes() + W.lowent(90000, 42).numpy().tobytes() + W.text(50000, 41).numpy().tobytes()
+    dic = W.text(70000, 43).numpy().tobytes()
+    frames = []
+    for kw in (dict(independent_blocks=False, block_size=64 << 10),
+               dict(independent_blocks=False, block_size=64 << 10, block_checksums=True),
+               dict(independent_blocks=False, block_size=256 << 10, content_checksum=False)):
+        rc, fr = oracle.frame_compress(data, **kw)
+        assert rc == 0
+        frames.append(fr)
+    return data, dic, frames
+
+
+def test_dependent_block_frames_decode(emu, oracle, issue15_input):     # tests/issue-15.rs shape
+    data, dic, frames = _dependent_frames(oracle)
+    for fr in frames:
+        st, det, plain, cons = emu.ctx.frame_decompress(fr, cap=len(data) + 16)
+        assert (st, plain, cons) == (0, data, len(fr))
+    rc, fr = oracle.frame_compress(issue15_input, independent_blocks=False, block_size=64 << 10)
+    assert emu.ctx.frame_decompress(fr, cap=len(issue15_input) + 16)[:3] == (0, 0, issue15_input)
+    # mutated dependent frames: same status / detail / delivered plaintext as the oracle
+    muts = [parity.mutate(frames[1], 900 + k, k=1 + k % 2) for k in range(16)] + [frames[0][:n] for n in (70000, len(frames[0]) - 3)]
+    parity.check_frame_decode_errors(emu, oracle, muts)
+
+
+def test_dictionary_frames_decode(emu, oracle):
+    data, dic, _ = _dependent_frames(oracle)
+    for kw in (dict(block_size=64 << 10), dict(independent_blocks=False, block_size=64 << 10)):
+        rc, fr = oracle.frame_compress(data, dictionary=dic, dictionary_id=7, **kw)
+        assert rc == 0
+        want = oracle.frame_decompress(fr, dictionary=dic, cap=len(data) + 16)
+        assert want[0] == 0 and want[2] == data
+        got = emu.ctx.frame_decompress(fr, dictionary=dic, cap=len(data) + 16)
+        assert got == want
+        # the wrong (short) dictionary fails exactly like the reference
+        assert emu.ctx.frame_decompress(fr, dictionary=dic[:100], cap=len(data) + 16)[:3] == \
+            oracle.frame_decompress(fr, dictionary=dic[:100], cap=len(data) + 16)[:3]
+
+
+def test_dependent_frames_with_short_blocks(emu, oracle):
+    """hand-crafted dependent frames whose non-final blocks are short: the exact, block-at-a-time path"""
+    import struct
+    hdr = bytes([0x04, 0x22, 0x4D, 0x18, 0x40, 0x40, 0xC0])         # version 1, dependent, no checksums, 64 KiB
+    assert oracle.parse_header(hdr)[0] == 0
+    a = bytes([0x80]) + b"abcdefgh"                                  # 8 literals
+    b = bytes([0x00, 8, 0, 0x40]) + b"wxyz"                          # match 4 @ offset 8 (reaches block 1), 4 literals
+    c = bytes([0x04, 12, 0, 0x10, 0x21])                             # match 8 @ offset 12, 1 literal
+    bad = bytes([0x00, 40, 0, 0x10, 0x21])                           # offset beyond the window
+    big = oracle.compress_block(bytes(65536))[1]
+    W = lambda blk: struct.pack("<I", len(blk)) + blk
+    frames = [hdr + W(a) + W(b) + W(c) + struct.pack("<I", 0),
+              hdr + W(a) + W(b) + W(bad) + struct.pack("<I", 0),
+              hdr + W(a) + W(big) + W(b) + W(c) + struct.pack("<I", 0),
+              hdr + W(a) + W(b) + struct.pack("<I", 3 | 0x80000000) + b"RAW" + W(c) + struct.pack("<I", 0)]
+    parity.check_frame_decode_errors(emu, oracle, frames)
+    dic = b"0123456789" * 10
+    far = bytes([0x00, 30, 0, 0x10, 0x21])                           # offset 30 at o=0: into the dictionary
+    parity.check_frame_decode_errors(emu, oracle, [hdr + W(far) + W(b) + W(c) + struct.pack("<I", 0)], dictionary=dic)
