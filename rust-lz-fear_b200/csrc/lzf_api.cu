@@ -210,7 +210,7 @@ int compress_blocks_impl(lzf_ctx* c, const uint8_t* d_in, const uint64_t* d_in_o
     a.work_counter = cur_slot(c)->d_counter;
     a.max_block_len = max_block_len;
     const size_t nslots = table_kind == LZF_TABLE_U16 ? ((size_t)2 << hashlog) : ((size_t)1 << hashlog);
-    if (nslots * 4 > 32 * 1024) {
+    if (nslots * 2 > 16 * 1024) {      // any layout that may not fit shared memory (lzf_launch_encode decides)
         const int rc = ensure_dev(c, cur_slot(c)->d_tables, lzf_encode_global_table_warps(c->num_sms) * nslots * 4);
         if (rc) return rc;
         a.global_tables = (uint8_t*)cur_slot(c)->d_tables.p;

@@ -324,32 +324,62 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
                 uint32_t ins = 0;       // lanes whose probe (or cursor-2 insert) has happened, in order
                 uint32_t s = 0;         // first lane of the current run inside this batch
                 bool committed = false;
+                // Batches in which no two lanes share a table slot (the common case) need no per-sequence
+                // candidate resolution at all: who matches is one ballot per batch, and each further sequence
+                // of the batch is found with scalar bit arithmetic.
+                const bool no_dups = __ballot_sync(LZF_FULL_MASK, (same & ~(1u << lane)) != 0) == 0;
+                const uint32_t okmask = __ballot_sync(LZF_FULL_MASK, t_ok);
+                // winner's candidate distance and extension summary travel in one word
+                const uint32_t packed_w = tdist | (fsum << 16);
                 for (;;) {
-                    // ---- candidates as the serial algorithm would see them: lane k of the current run
-                    // comes after every insert recorded so far AND after the probes s..k-1 of its own run
-                    const uint32_t inb = same & (ins | ~((1u << s) - 1u)) & lower_mask;
-                    const uint32_t src = inb ? (31u - __clz(inb)) : lane;
-                    const uint32_t pj = __shfl_sync(LZF_FULL_MASK, p, src);
-                    const uint32_t vj = __shfl_sync(LZF_FULL_MASK, v32, src);
-                    const uint32_t cand = inb ? pj : tcand;
-                    const bool ok = !is_end && lane >= s && (inb ? (vj == v32 && p - pj <= 0xffffu) : t_ok);
-                    const uint32_t trig = __ballot_sync(LZF_FULL_MASK, (ok || is_end) && lane >= s);
-                    if (trig == 0) {
-                        ins |= ~((1u << s) - 1u);                             // every lane from s on probed and missed
-                        j += 32 - s;
-                        break;
+                    uint32_t trig, w, cur, cnd, wsum;
+                    if (no_dups) {
+                        trig = (okmask | endmask) & ~((1u << s) - 1u);
+                        if (trig == 0) {
+                            ins |= ~((1u << s) - 1u);                         // every lane from s on probed and missed
+                            j += 32 - s;
+                            break;
+                        }
+                        w = __ffs(trig) - 1;
+                        if ((endmask >> w) & 1u) {
+                            // final literal-only sequence  :178-190
+                            if (!emit_sequence(out, opos, cap, in, lit_start, len - lit_start, 0, 0, true, false, 0, 0)) status = LZF_WRITER_FULL;
+                            done = true;
+                            committed = true;                                 // the table is never read again
+                            break;
+                        }
+                        ins |= ((2u << w) - 1u) & ~((1u << s) - 1u);         // probes s..w happened
+                        const uint32_t pw = __shfl_sync(LZF_FULL_MASK, packed_w, w);
+                        cur = consecutive ? base + w : __shfl_sync(LZF_FULL_MASK, p, w);
+                        cnd = cur - (pw & 0xffffu);
+                        wsum = pw >> 16;
+                    } else {
+                        // ---- candidates as the serial algorithm would see them: lane k of the current run
+                        // comes after every insert recorded so far AND after the probes s..k-1 of its own run
+                        const uint32_t inb = same & (ins | ~((1u << s) - 1u)) & lower_mask;
+                        const uint32_t src = inb ? (31u - __clz(inb)) : lane;
+                        const uint32_t pj = __shfl_sync(LZF_FULL_MASK, p, src);
+                        const uint32_t vj = __shfl_sync(LZF_FULL_MASK, v32, src);
+                        const uint32_t cand = inb ? pj : tcand;
+                        const bool ok = !is_end && lane >= s && (inb ? (vj == v32 && p - pj <= 0xffffu) : t_ok);
+                        trig = __ballot_sync(LZF_FULL_MASK, (ok || is_end) && lane >= s);
+                        if (trig == 0) {
+                            ins |= ~((1u << s) - 1u);
+                            j += 32 - s;
+                            break;
+                        }
+                        w = __ffs(trig) - 1;
+                        if ((endmask >> w) & 1u) {
+                            if (!emit_sequence(out, opos, cap, in, lit_start, len - lit_start, 0, 0, true, false, 0, 0)) status = LZF_WRITER_FULL;
+                            done = true;
+                            committed = true;
+                            break;
+                        }
+                        ins |= ((2u << w) - 1u) & ~((1u << s) - 1u);
+                        cur = __shfl_sync(LZF_FULL_MASK, p, w);
+                        cnd = __shfl_sync(LZF_FULL_MASK, cand, w);
+                        wsum = __shfl_sync(LZF_FULL_MASK, inb ? 0u : fsum, w);   // in-batch candidates take the general extension
                     }
-                    const uint32_t w = __ffs(trig) - 1;
-                    if ((endmask >> w) & 1u) {
-                        // final literal-only sequence  :178-190
-                        if (!emit_sequence(out, opos, cap, in, lit_start, len - lit_start, 0, 0, true, false, 0, 0)) status = LZF_WRITER_FULL;
-                        done = true;
-                        committed = true;                                     // the table is never read again
-                        break;
-                    }
-                    ins |= ((2u << w) - 1u) & ~((1u << s) - 1u);             // probes s..w happened
-                    const uint32_t cur = __shfl_sync(LZF_FULL_MASK, p, w);
-                    const uint32_t cnd = __shfl_sync(LZF_FULL_MASK, cand, w);
 
                     const uint32_t limit = len - 5 - cur;                     // bytes of current_batch :195
                     const uint32_t max_back = min(cur - lit_start, cnd);
@@ -358,7 +388,6 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
                     // or the match / backtrack runs past what the summary covers
                     bool fast = false;
                     {
-                        const uint32_t wsum = __shfl_sync(LZF_FULL_MASK, inb ? 0u : fsum, w);
                         const uint32_t fm = wsum & 31u, nb = (wsum >> 5) & 7u;
                         const bool f_ok = (wsum & 0x100u) && (fm < 16 || limit <= 16);
                         const bool b_ok = max_back == 0 || ((wsum & 0x200u) && (nb < 4 || max_back <= 4));
@@ -566,7 +595,8 @@ extern "C" int lzf_launch_encode(const lzf::EncodeArgs* args, int num_sms, cudaS
     const size_t table_bytes = slot16 ? (size_t)nslots * 2 : packed ? (size_t)nslots * 2 + nslots / 8 : (size_t)nslots * 4;
     // per-warp tables up to 32 KiB live in shared memory; larger ones (hashlog >= 14 extension) in a
     // ctx-owned global scratch that stays L2-resident
-    const bool smem_tables = table_bytes <= 32 * 1024;
+    const int warps = (hash4 || (!slot16 && !packed)) ? kEncodeWarpsPerCta : 8;
+    const bool smem_tables = table_bytes <= 32 * 1024 && table_bytes * warps <= 200 * 1024;
     if (!smem_tables && args->global_tables == nullptr) return (int)cudaErrorInvalidValue;
     if (hash4) return launch_encode_variant<1, true, kEncodeWarpsPerCta>(args, num_sms, nslots, table_bytes, smem_tables, stream);
     if (slot16) return launch_encode_variant<1, false, 8>(args, num_sms, nslots, table_bytes, smem_tables, stream);

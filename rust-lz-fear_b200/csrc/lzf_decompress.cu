@@ -384,7 +384,7 @@ decode_blocks_kernel(DecodeArgs a) {
                 // ---- walk: up to 32 LSIC-free sequences that lie completely inside the window.  This is
                 // the only serial part of the decoder: one shared-memory byte per sequence.
                 uint32_t cnt = 0;
-#ifndef LZF_SIMT_EMU
+#if !defined(LZF_SIMT_EMU) && !defined(LZF_DEC_C_WALK)
                 const uint32_t step_sa = smem_addr(sm.step);
                 if (s.olen + 32u * 32u <= bound) {
                     uint32_t pp = step_sa + p;
@@ -395,6 +395,7 @@ decode_blocks_kernel(DecodeArgs a) {
                 const uint32_t my_p = sm.plist[lane] - step_sa;
 #else
                 if (s.olen + 32u * 32u <= bound) {
+#pragma unroll 8
                     for (int k = 0; k < 32; k++) {
                         const uint32_t d = sm.step[p];
                         if (d == 0) break;
@@ -433,7 +434,7 @@ decode_blocks_kernel(DecodeArgs a) {
                     const uint32_t keep = (uint32_t)(__ffs(fb) - 1);
                     if (keep < cnt) {                                           // the next sequence starts where the kept ones end
                         cnt = keep;
-#ifndef LZF_SIMT_EMU
+#if !defined(LZF_SIMT_EMU) && !defined(LZF_DEC_C_WALK)
                         in_end = sm.plist[keep] - step_sa;
 #else
                         in_end = sm.plist[keep];
