@@ -68,7 +68,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -101,6 +101,19 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
                 "samples": len(sm)}
+
+
+def ncu_traffic(kernel, nblocks):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` on exactly this workload, from the
+    committed `ncu --set full` capture (profiles/ncu_traffic.json); None when no capture matches."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        e = t.get(kernel)
+        if e and int(e.get("nblocks", -1)) == int(nblocks):
+            return float(e["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
 
 
 def measured_peak():
@@ -250,13 +263,17 @@ def main():
     def step_decompress():
         ctx.decompress_blocks(comp, in_off, in_len, nb, plain, in_off, cap, cap, olen, st, None if args.no_xxh else xx, stream=stream)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(Wm):
         step_decompress()
     torch.cuda.synchronize()
     assert int(st.abs().sum().item()) == 0 and bool((olen == BLOCK2).all()), "decode failed"
+    t_load = time.perf_counter()
+    while time.perf_counter() - t_load < 0.6:      # keep the GPU under the same load while nvidia-smi gets going
+        step_decompress()
+    torch.cuda.synchronize()
     launches0 = ctx.launch_count
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -271,7 +288,8 @@ def main():
     dec_value = total_plain * K / GiB / (dec_ms / 1e3)
     local_ms = e0.elapsed_time(e1) / K
     dec_roof = {"bound": "hbm", "achieved": (comp_bytes + plain_bytes) / 1e9 / (local_ms / 1e3), "peak": peak_gbs,
-                "unit": "GB/s", "kernel": "decode_blocks_kernel", "peak_source": peak_src, "traffic": None,
+                "unit": "GB/s", "kernel": "decode_blocks_kernel", "peak_source": peak_src,
+                "traffic": ncu_traffic("decode_blocks_kernel", nb),
                 "algorithmic_bytes_per_launch": comp_bytes + plain_bytes}
     dec_roof["frac"] = dec_roof["achieved"] / peak_gbs
 
@@ -387,7 +405,8 @@ def main():
         total3 = sum_over_ranks(nb3 * BLOCK3)
         c_local_ms = e0.elapsed_time(e1) / K
         c_roof = {"bound": "hbm", "achieved": (nb3 * BLOCK3 + c_bytes) / 1e9 / (c_local_ms / 1e3), "peak": peak_gbs,
-                  "unit": "GB/s", "kernel": "encode_blocks_kernel", "peak_source": peak_src, "traffic": None,
+                  "unit": "GB/s", "kernel": "encode_blocks_kernel", "peak_source": peak_src,
+                  "traffic": ncu_traffic("encode_blocks_kernel", nb3),
                   "algorithmic_bytes_per_launch": nb3 * BLOCK3 + c_bytes}
         c_roof["frac"] = c_roof["achieved"] / peak_gbs
         comp_section = {"metric": "LZ4 block compress throughput (config 3: 4 MiB text-like blocks, default CompressionSettings)",

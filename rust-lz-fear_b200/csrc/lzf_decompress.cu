@@ -216,7 +216,7 @@ __device__ __forceinline__ uint32_t flush_stage(const uint8_t* stage, uint8_t* o
 //   pp      in/out: shared-memory address of step[p]
 //   plist   shared-memory address of the position list (u32 x 32)
 // returns the number of sequences walked.
-#ifndef LZF_SIMT_EMU
+#if !defined(LZF_SIMT_EMU) && defined(LZF_DEC_PTX_WALK)   // measured slower than the compiler's loop (322 vs 354 GiB/s): kept for reference
 __device__ __noinline__ uint32_t walk32(uint32_t& pp, uint32_t plist) {
     uint32_t cnt;
     asm volatile(
@@ -384,7 +384,7 @@ decode_blocks_kernel(DecodeArgs a) {
                 // ---- walk: up to 32 LSIC-free sequences that lie completely inside the window.  This is
                 // the only serial part of the decoder: one shared-memory byte per sequence.
                 uint32_t cnt = 0;
-#if !defined(LZF_SIMT_EMU) && !defined(LZF_DEC_C_WALK)
+#if !defined(LZF_SIMT_EMU) && defined(LZF_DEC_PTX_WALK)
                 const uint32_t step_sa = smem_addr(sm.step);
                 if (s.olen + 32u * 32u <= bound) {
                     uint32_t pp = step_sa + p;
@@ -434,7 +434,7 @@ decode_blocks_kernel(DecodeArgs a) {
                     const uint32_t keep = (uint32_t)(__ffs(fb) - 1);
                     if (keep < cnt) {                                           // the next sequence starts where the kept ones end
                         cnt = keep;
-#if !defined(LZF_SIMT_EMU) && !defined(LZF_DEC_C_WALK)
+#if !defined(LZF_SIMT_EMU) && defined(LZF_DEC_PTX_WALK)
                         in_end = sm.plist[keep] - step_sa;
 #else
                         in_end = sm.plist[keep];
