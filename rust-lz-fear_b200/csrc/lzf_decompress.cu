@@ -34,7 +34,6 @@ namespace lzf {
 constexpr int kDecodeWarpsPerCta = 8;
 constexpr uint32_t kWin = LZF_DEC_WIN;     // staged bytes of compressed stream per refill
 constexpr uint32_t kStage = 2048;          // output staging ring (power of two, > 32 * 32 + 16)
-constexpr uint32_t kStageMask = kStage - 1;
 constexpr uint32_t kFastSeqMax = 3 + 14;   // token + 14 literals + offset: no LSIC byte anywhere
 
 struct __align__(16) DecodeWarpSmem {
@@ -181,10 +180,12 @@ __device__ __forceinline__ void slow_sequence(BlockState& s) {
     __syncwarp();
 }
 
-// Writes staged output [from, upto) to global memory.  `whole` = false: upto is rounded down to a
-// 16-byte boundary of the destination address (the remainder stays staged); returns the new
-// flushed position.
-__device__ __forceinline__ uint32_t flush_stage(const uint8_t* stage, uint8_t* out, uint32_t sbase, uint32_t from,
+// Writes staged output [from, upto) to global memory.  Output position x lives at stage[x - sbias];
+// sbias keeps (x - sbias) congruent to the destination address modulo 16, so aligned 16-byte chunks
+// of the stage are aligned 16-byte chunks of the output.  `whole` = false: upto is rounded down to a
+// 16-byte boundary of the destination address (the remainder stays staged); returns the new flushed
+// position.
+__device__ __forceinline__ uint32_t flush_stage(const uint8_t* stage, uint8_t* out, uint32_t sbias, uint32_t from,
                                                 uint32_t upto, bool whole) {
     const unsigned lane = lane_id();
     const uintptr_t oa = reinterpret_cast<uintptr_t>(out);
@@ -197,17 +198,31 @@ __device__ __forceinline__ uint32_t flush_stage(const uint8_t* stage, uint8_t* o
     uint32_t a = from;
     uint32_t head = (uint32_t)((16u - ((oa + a) & 15u)) & 15u);
     if (head > upto - a) head = upto - a;
-    if (lane < head) out[a + lane] = stage[(sbase + a + lane) & kStageMask];
+    if (lane < head) out[a + lane] = stage[a + lane - sbias];
     a += head;
     const uint32_t nvec = (upto - a) >> 4;
     for (uint32_t v = lane; v < nvec; v += 32) {
         const uint32_t p = a + 16 * v;
-        *reinterpret_cast<uint4*>(out + p) = *reinterpret_cast<const uint4*>(stage + ((sbase + p) & kStageMask));
+        *reinterpret_cast<uint4*>(out + p) = *reinterpret_cast<const uint4*>(stage + (p - sbias));
     }
     a += nvec * 16;
     const uint32_t tail = upto - a;     // only when `whole`
-    if (lane < tail) out[a + lane] = stage[(sbase + a + lane) & kStageMask];
+    if (lane < tail) out[a + lane] = stage[a + lane - sbias];
     return upto;
+}
+
+// After a flush: re-base the stage so that the (< 16-byte) carry [flushed, olen) starts at the front.
+__device__ __forceinline__ uint32_t rebase_stage(uint8_t* stage, const uint8_t* out, uint32_t sbias, uint32_t flushed, uint32_t olen) {
+    const unsigned lane = lane_id();
+    const uint32_t nb = flushed - (uint32_t)((reinterpret_cast<uintptr_t>(out) + flushed) & 15u);
+    if (nb != sbias) {
+        const uint32_t carry = olen - flushed;      // < 32
+        uint8_t v = 0;
+        if (lane < carry) v = stage[flushed + lane - sbias];
+        __syncwarp();
+        if (lane < carry) stage[flushed + lane - nb] = v;
+    }
+    return nb;
 }
 
 // The serial part of the decoder: follow step[] from `pp` for at most 32 sequences, recording where each
@@ -349,8 +364,8 @@ decode_blocks_kernel(DecodeArgs a) {
             const uint64_t qn16 = (qn + 15) & ~uint64_t(15);
             uint64_t wq = 0;          // window start (multiple of 16), relative to a0
             uint32_t wlen = 0;        // staged bytes
-            const uint32_t sbase = (uint32_t)(reinterpret_cast<uintptr_t>(s.out) & 15u);
             uint32_t flushed = 0;     // output below this position is in global memory; [flushed, olen) is staged
+            uint32_t sbias = 0u - (uint32_t)(reinterpret_cast<uintptr_t>(s.out) & 15u);   // stage index of position x is x - sbias
             // the fast path works in 32-bit output positions and never exceeds this bound
             const uint64_t bound64 = s.cap < s.limit ? s.cap : s.limit;
             const uint32_t bound = bound64 > 0xfffff000ull ? 0xfffff000u : (uint32_t)bound64;
@@ -442,10 +457,11 @@ decode_blocks_kernel(DecodeArgs a) {
                     }
                 }
                 if (cnt == 0) {
-                    flushed = flush_stage(sm.stage, s.out, sbase, flushed, (uint32_t)s.olen, true);
+                    flushed = flush_stage(sm.stage, s.out, sbias, flushed, (uint32_t)s.olen, true);
                     __syncwarp();
                     slow_sequence(s);
                     flushed = (uint32_t)s.olen;
+                    sbias = flushed - (uint32_t)((reinterpret_cast<uintptr_t>(s.out) + flushed) & 15u);
                     continue;
                 }
                 const bool act = lane < cnt;
@@ -454,8 +470,9 @@ decode_blocks_kernel(DecodeArgs a) {
                 // ---- literals: every lane copies its own run into the staging ring
                 if (act) {
                     const uint8_t* src = sm.win + my_p + 1;
-                    const uint32_t d = sbase + o_k;
-                    for (uint32_t i = 0; i < lit; i++) sm.stage[(d + i) & kStageMask] = src[i];
+                    uint8_t* d = sm.stage + (o_k - sbias);
+#pragma unroll
+                    for (uint32_t i = 0; i < 14; i++) if (i < lit) d[i] = src[i];
                 }
                 __syncwarp();
 
@@ -467,18 +484,18 @@ decode_blocks_kernel(DecodeArgs a) {
                     const uint32_t dst_first = __shfl_sync(LZF_FULL_MASK, dstp, first);
                     const bool ready = ((pending >> lane) & 1u) && (lane == first || srcp + (int64_t)ml <= (int64_t)dst_first);
                     if (ready) {
-                        const uint32_t d = sbase + dstp;
+                        uint8_t* d = sm.stage + (dstp - sbias);
                         if (srcp >= (int64_t)flushed) {
-                            const uint32_t sp = sbase + (uint32_t)srcp;           // staged -> staged (in order: overlap-safe)
-                            for (uint32_t i = 0; i < ml; i++) sm.stage[(d + i) & kStageMask] = sm.stage[(sp + i) & kStageMask];
+                            const uint8_t* sp = sm.stage + ((uint32_t)srcp - sbias);   // staged -> staged (in order: overlap-safe)
+                            for (uint32_t i = 0; i < ml; i++) d[i] = sp[i];
                         } else if (srcp >= 0 && srcp + (int64_t)ml <= (int64_t)flushed) {
                             const uint8_t* g = s.out + srcp;                      // flushed history -> staged
-                            for (uint32_t i = 0; i < ml; i++) sm.stage[(d + i) & kStageMask] = g[i];
+#pragma unroll
+                            for (uint32_t i = 0; i < 18; i++) if (i < ml) d[i] = g[i];
                         } else {
                             for (uint32_t i = 0; i < ml; i++) {                   // straddles the flush point or the prefix
                                 const int64_t x = srcp + i;
-                                sm.stage[(d + i) & kStageMask] =
-                                    x >= (int64_t)flushed ? sm.stage[(sbase + (uint32_t)x) & kStageMask] : hist_byte(s.out, s.prefix_end, x);
+                                d[i] = x >= (int64_t)flushed ? sm.stage[(uint32_t)x - sbias] : hist_byte(s.out, s.prefix_end, x);
                             }
                         }
                     }
@@ -487,10 +504,12 @@ decode_blocks_kernel(DecodeArgs a) {
                 }
                 s.olen = out_end;
                 s.pos += in_end - (uint32_t)(q - wq);
-                flushed = flush_stage(sm.stage, s.out, sbase, flushed, out_end, false);
+                flushed = flush_stage(sm.stage, s.out, sbias, flushed, out_end, false);
+                __syncwarp();
+                sbias = rebase_stage(sm.stage, s.out, sbias, flushed, out_end);
                 __syncwarp();
             }
-            flushed = flush_stage(sm.stage, s.out, sbase, flushed, (uint32_t)s.olen, true);
+            flushed = flush_stage(sm.stage, s.out, sbias, flushed, (uint32_t)s.olen, true);
         }
         if (s.status == LZF_OK && s.olen > s.cap) s.status = LZF_OUTPUT_CAP;
         __syncwarp();
