@@ -194,15 +194,20 @@ int compress_blocks_impl(lzf_ctx* c, const uint8_t* d_in, const uint64_t* d_in_o
                          uint32_t nblocks, uint32_t hashlog, uint32_t table_kind, uint32_t max_block_len,
                          uint8_t* d_out, const uint64_t* d_out_off, const uint32_t* d_out_cap,
                          uint32_t* d_out_len, int32_t* d_status, uint32_t* d_xxh_plain, uint32_t* d_xxh_stored,
-                         cudaStream_t s) {
+                         cudaStream_t s, const lzf::EncodeArgs* chains = nullptr) {
     if (hashlog == 0) hashlog = 12;
     if (hashlog < 8 || hashlog > 16) return fail(c, LZF_ERR_INVALID_ARG, "hashlog must be 0 or 8..16");
     if (table_kind != LZF_TABLE_U32 && table_kind != LZF_TABLE_U16) return fail(c, LZF_ERR_INVALID_ARG, "table_kind");
     if (nblocks == 0) return LZF_SUCCESS;
-    if (!d_in || !d_in_off || !d_in_len || !d_out || !d_out_off || !d_out_len || !d_status)
+    if ((!d_in && !chains) || !d_in_off || !d_in_len || !d_out || !d_out_off || !d_out_len || !d_status)
         return fail(c, LZF_ERR_INVALID_ARG, "null pointer");
     lzf::EncodeArgs a;
     memset(&a, 0, sizeof(a));
+    if (chains) {
+        a.prefix_len = chains->prefix_len; a.abs_base = chains->abs_base; a.prime_len = chains->prime_len;
+        a.chain_first = chains->chain_first; a.chain_count = chains->chain_count; a.nchains = chains->nchains;
+        a.max_pos = chains->max_pos;
+    }
     a.in = d_in; a.in_off = d_in_off; a.in_len = d_in_len; a.nblocks = nblocks;
     a.hashlog = hashlog; a.table_kind = table_kind;
     a.out = d_out; a.out_off = d_out_off; a.out_cap = d_out_cap; a.out_len = d_out_len; a.status = d_status;
@@ -496,8 +501,10 @@ int frames_compress_core(lzf_ctx* c, const lzf_settings* s, const uint8_t* d_in,
         return fail(c, LZF_ERR_INVALID_ARG, "null pointer");
     for (uint32_t f = 0; f < nframes; f++) { out_len[f] = 0; status[f] = LZF_F_OK; }
     if (nframes == 0) return LZF_SUCCESS;
-    if (!s->independent_blocks || (s->dictionary && s->dictionary_len))
-        return fail(c, LZF_ERR_UNSUPPORTED, "dependent blocks / dictionaries are not on the GPU path yet");
+    const bool dependent = !s->independent_blocks;
+    const uint64_t dlen = s->dictionary ? s->dictionary_len : 0;
+    if (dlen > 0x7fffffffull) return fail(c, LZF_ERR_UNSUPPORTED, "dictionary larger than 2 GiB");
+    const bool chained = dependent || dlen > 0;
     uint32_t hashlog = s->hashlog ? s->hashlog : 12;
 
     // settings-level failures are identical for every frame
@@ -521,6 +528,13 @@ int frames_compress_core(lzf_ctx* c, const lzf_settings* s, const uint8_t* d_in,
     const size_t o_hoff = da.take((size_t)nframes * 8), o_hlen = da.take((size_t)nframes * 8);
     const size_t o_bin_off = da.take((size_t)nblocks * 8), o_bin_len = da.take((size_t)nblocks * 4);
     const size_t o_bc_off = da.take((size_t)nblocks * 8);
+    // dependent blocks / dictionary: history length, stream base and priming per block, chains of blocks that
+    // share a table, and the blocks that need a [dictionary | block] staging copy
+    const size_t o_pfx = da.take(chained ? (size_t)nblocks * 4 : 0), o_abs = da.take(chained ? (size_t)nblocks * 4 : 0);
+    const size_t o_prime = da.take(chained ? (size_t)nblocks * 4 : 0);
+    const size_t o_cfirst = da.take(chained ? (size_t)nblocks * 4 : 0), o_ccount = da.take(chained ? (size_t)nblocks * 4 : 0);
+    const size_t o_ssrc = da.take(chained ? (size_t)nblocks * 8 : 0), o_sdst = da.take(chained ? (size_t)nblocks * 8 : 0);
+    const size_t o_slen = da.take(chained ? (size_t)nblocks * 4 : 0);
     Arena ra;   // result arena (device-written)
     const size_t r_clen = ra.take((size_t)nblocks * 4), r_bst = ra.take((size_t)nblocks * 4);
     const size_t r_xs = ra.take((size_t)nblocks * 4), r_dst = ra.take((size_t)nblocks * 8);
@@ -543,6 +557,12 @@ int frames_compress_core(lzf_ctx* c, const lzf_settings* s, const uint8_t* d_in,
     uint64_t* hoff = (uint64_t*)(h + o_hoff); uint64_t* hlen = (uint64_t*)(h + o_hlen);
     uint64_t* bin_off = (uint64_t*)(h + o_bin_off); uint32_t* bin_len = (uint32_t*)(h + o_bin_len);
     uint64_t* bc_off = (uint64_t*)(h + o_bc_off);
+    uint32_t* pfx = (uint32_t*)(h + o_pfx); uint32_t* absb = (uint32_t*)(h + o_abs); uint32_t* prime = (uint32_t*)(h + o_prime);
+    uint32_t* cfirst = (uint32_t*)(h + o_cfirst); uint32_t* ccount = (uint32_t*)(h + o_ccount);
+    uint64_t* ssrc = (uint64_t*)(h + o_ssrc); uint64_t* sdst = (uint64_t*)(h + o_sdst); uint32_t* slen = (uint32_t*)(h + o_slen);
+    uint32_t nchains = 0, nstaged = 0;
+    uint64_t stage_total = 0, max_pos = 0;
+    bool positions_overflow = false;
     uint32_t b = 0;
     uint64_t comp_total = 0;
     uint32_t max_block_len = 0;
@@ -565,9 +585,44 @@ int frames_compress_core(lzf_ctx* c, const lzf_settings* s, const uint8_t* d_in,
             bc_off[b] = comp_total;
             comp_total += ((uint64_t)l + 15) / 16 * 16;
             if (l > max_block_len) max_block_len = l;
+            if (chained) {
+                // in_buffer in front of this block (compress.rs:218-222,265-275): the dictionary for block 0 and for
+                // every independent block; the last 64 KiB of dictionary ++ plaintext for later dependent blocks
+                // (entirely plaintext, because every earlier block is a full block of >= 64 KiB)
+                const bool dict_history = dlen && (i == 0 || !dependent);
+                const uint64_t total_before = dlen + (dependent ? o : 0);
+                const uint64_t hist = dict_history ? dlen : (dependent && i > 0 ? (total_before < LZF_WINDOW_SIZE ? total_before : LZF_WINDOW_SIZE) : 0);
+                const uint64_t base = dict_history || !dependent ? 0 : total_before - hist;   // table.offset (compress.rs:273)
+                pfx[b] = (uint32_t)hist;
+                absb[b] = (uint32_t)base;
+                prime[b] = dict_history ? (uint32_t)dlen : 0;
+                if (base + hist + l > 0xffffffffull) positions_overflow = true;   // "EncoderTable contract violated" :67
+                if (base + hist + l > max_pos) max_pos = base + hist + l;
+                if (!dependent || i == 0) { cfirst[nchains] = b; ccount[nchains] = 1; nchains++; }
+                else ccount[nchains - 1]++;
+                if (dict_history) {
+                    ssrc[nstaged] = bin_off[b]; slen[nstaged] = l; sdst[nstaged] = stage_total;
+                    stage_total += (dlen + l + 31) / 16 * 16;
+                    nstaged++;
+                }
+            }
         }
     }
+    if (positions_overflow) { for (uint32_t f = 0; f < nframes; f++) status[f] = LZF_F_PANIC; return LZF_SUCCESS; }
     if ((rc = ensure_dev(c, cur_slot(c)->d_comp, comp_total + 64))) return rc;
+    // with a dictionary every block address becomes absolute: staged blocks live in their own buffer
+    const uint8_t* enc_base = d_in;
+    if (dlen) {
+        if ((rc = ensure_dev(c, cur_slot(c)->d_dict, dlen + 16))) return rc;
+        if ((rc = ensure_dev(c, cur_slot(c)->d_aux, stage_total + 64))) return rc;
+        LZF_CU(c, cudaMemcpyAsync(cur_slot(c)->d_dict.p, s->dictionary, dlen, cudaMemcpyHostToDevice, st));
+        enc_base = nullptr;
+        uint32_t k = 0;
+        for (uint32_t bb = 0; bb < nblocks; bb++) {
+            if (prime[bb]) { bin_off[bb] = (uint64_t)(uintptr_t)((uint8_t*)cur_slot(c)->d_aux.p + sdst[k] + dlen); k++; }
+            else bin_off[bb] = (uint64_t)(uintptr_t)(d_in + bin_off[bb]);
+        }
+    }
 
     LZF_CU(c, cudaMemcpyAsync(d, h, da.used, cudaMemcpyHostToDevice, st));
     // content checksum of each frame's plaintext (compress.rs:172,233-235,279-281) on the side stream
@@ -579,10 +634,25 @@ int frames_compress_core(lzf_ctx* c, const lzf_settings* s, const uint8_t* d_in,
         LZF_CU(c, cudaEventRecord(cur_slot(c)->ev_join, cur_slot(c)->side));
     }
     if (nblocks) {
-        rc = compress_blocks_impl(c, d_in, (const uint64_t*)(d + o_bin_off), (const uint32_t*)(d + o_bin_len), nblocks,
+        lzf::EncodeArgs ch;
+        memset(&ch, 0, sizeof(ch));
+        if (chained) {
+            if (nstaged) {
+                lzf::StageArgs sa;
+                sa.n = nstaged; sa.dict = (const uint8_t*)cur_slot(c)->d_dict.p; sa.dlen = (uint32_t)dlen;
+                sa.in = d_in; sa.src_off = (const uint64_t*)(d + o_ssrc); sa.len = (const uint32_t*)(d + o_slen);
+                sa.dst = (uint8_t*)cur_slot(c)->d_aux.p; sa.dst_off = (const uint64_t*)(d + o_sdst);
+                LZF_LAUNCHED(c, lzf_launch_stage_dict(&sa, st), 1);
+            }
+            ch.prefix_len = (const uint32_t*)(d + o_pfx); ch.abs_base = (const uint32_t*)(d + o_abs);
+            ch.prime_len = (const uint32_t*)(d + o_prime);
+            ch.chain_first = (const uint32_t*)(d + o_cfirst); ch.chain_count = (const uint32_t*)(d + o_ccount);
+            ch.nchains = nchains; ch.max_pos = max_pos;
+        }
+        rc = compress_blocks_impl(c, enc_base, (const uint64_t*)(d + o_bin_off), (const uint32_t*)(d + o_bin_len), nblocks,
                                   hashlog, LZF_TABLE_U32, max_block_len, (uint8_t*)cur_slot(c)->d_comp.p,
                                   (const uint64_t*)(d + o_bc_off), nullptr, (uint32_t*)(r + r_clen), (int32_t*)(r + r_bst),
-                                  nullptr, s->block_checksums ? (uint32_t*)(r + r_xs) : nullptr, st);
+                                  nullptr, s->block_checksums ? (uint32_t*)(r + r_xs) : nullptr, st, chained ? &ch : nullptr);
         if (rc) return rc;
     }
     if (s->content_checksum) LZF_CU(c, cudaStreamWaitEvent(st, cur_slot(c)->ev_join, 0));
@@ -603,7 +673,7 @@ int frames_compress_core(lzf_ctx* c, const lzf_settings* s, const uint8_t* d_in,
         lzf::AssembleArgs aa;
         memset(&aa, 0, sizeof(aa));
         aa.nblocks = nblocks;
-        aa.in = d_in; aa.blk_in_off = (const uint64_t*)(d + o_bin_off); aa.blk_in_len = (const uint32_t*)(d + o_bin_len);
+        aa.in = enc_base; aa.blk_in_off = (const uint64_t*)(d + o_bin_off); aa.blk_in_len = (const uint32_t*)(d + o_bin_len);
         aa.comp = (const uint8_t*)cur_slot(c)->d_comp.p; aa.blk_comp_off = (const uint64_t*)(d + o_bc_off);
         aa.blk_comp_len = (const uint32_t*)(r + r_clen); aa.blk_status = (const int32_t*)(r + r_bst);
         aa.blk_xxh_stored = s->block_checksums ? (const uint32_t*)(r + r_xs) : nullptr;

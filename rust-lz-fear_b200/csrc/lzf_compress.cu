@@ -195,36 +195,62 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
     const uint32_t lower_mask = (1u << lane) - 1u;
     hash_queue_init(&hashq);
 
+    const uint32_t nchains = a.chain_first ? a.nchains : a.nblocks;
     for (;;) {
-        uint32_t b = 0;
-        if (lane == 0) b = atomicAdd(a.work_counter, 1u);
-        b = __shfl_sync(LZF_FULL_MASK, b, 0);
-        if (b >= a.nblocks) break;
+        uint32_t chain = 0;
+        if (lane == 0) chain = atomicAdd(a.work_counter, 1u);
+        chain = __shfl_sync(LZF_FULL_MASK, chain, 0);
+        if (chain >= nchains) break;
+        const uint32_t b_first = a.chain_first ? a.chain_first[chain] : chain;
+        const uint32_t b_count = a.chain_first ? a.chain_count[chain] : 1u;
+        uint32_t last_sweep = 0;        // packed tables: every slot is exact for stream positions below last_sweep + 65536
 
-        const uint32_t len = a.in_len[b];
-        const uint8_t* in = a.in + a.in_off[b];
+      for (uint32_t bi = 0; bi < b_count; bi++) {
+        const uint32_t b = b_first + bi;
+        const uint32_t own_len = a.in_len[b];
+        const uint32_t cursor0 = a.prefix_len ? a.prefix_len[b] : 0u;         // compress2's `cursor` argument
+        const uint32_t ab = a.abs_base ? a.abs_base[b] : 0u;                  // table.offset (:30,65,72-74)
+        const uint64_t len64 = (uint64_t)cursor0 + own_len;
+        const uint32_t len = (uint32_t)len64;                                 // input.len(): history + block
+        const uint8_t* in = a.in + a.in_off[b] - cursor0;
         uint8_t* out = a.out + a.out_off[b];
-        const uint32_t cap = a.out_cap ? a.out_cap[b] : len;       // NoPartialWrites bound (compress.rs:242)
+        const uint32_t cap = a.out_cap ? a.out_cap[b] : own_len;  // NoPartialWrites bound (compress.rs:242)
 
         int status = LZF_OK;
         uint32_t opos = 0;
 
-        // assert!(input.len() <= T::payload_size_limit())  :167 ; Slot width must hold every position
-        const bool too_big = (kHash4 && len > 0xffffu) || (kTab == 1 && len > 0x10000u) || (kPacked && len > kPacked17MaxLen) ||
-                             (a.max_block_len && len > a.max_block_len);
+        // assert!(input.len() <= T::payload_size_limit())  :167 / "EncoderTable contract violated" :67,92;
+        // the slot width must hold every stream position
+        const bool too_big = len64 + ab > 0xffffffffull || (kHash4 && len64 + ab > 0xffffull) ||
+                             (kTab == 1 && len64 + ab > 0x10000ull) || (kPacked && own_len > kPacked17MaxLen) ||
+                             (a.max_block_len && own_len > a.max_block_len);
         if (too_big) {
             status = LZF_PANIC;
-        } else if (len) {
-            // fresh zeroed table (U32Table::default :32-36 / template_table.clone() compress.rs:270)
-            {
+        } else if (own_len) {
+            if (bi == 0) {
+                // fresh zeroed table (U32Table::default :32-36 / template_table.clone() compress.rs:270)
                 uint4* t4 = reinterpret_cast<uint4*>(table_mem);
                 const uint32_t nvec = (uint32_t)(table_bytes / 16);
                 for (uint32_t i = lane; i < nvec; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
+                __syncwarp();
+                last_sweep = 0;
+                // dictionary priming: template_table.replace(dict, off) for off = 0, 3, 6, ... while 8 bytes
+                // remain (compress.rs:204-214), 32 positions per step, the last insert of a slot wins
+                const uint32_t prime = a.prime_len ? a.prime_len[b] : 0u;
+                for (uint32_t o0 = 0; o0 + 8 <= prime; o0 += 96) {
+                    const uint32_t o = o0 + 3 * lane;
+                    const bool on = o + 8 <= prime;
+                    uint32_t hk = 0xffff0000u | lane;
+                    if (on) hk = kHash4 ? hash4(ld4(in, o), hashlog) : hash5(ld4(in, o), in[o + 4], hashlog);
+                    const uint32_t sm_ = __match_any_sync(LZF_FULL_MASK, hk);
+                    if constexpr (kPacked) {
+                        if (o0 + 96 + ab - last_sweep >= 65536u) { last_sweep = o0 + ab; table.sweep(nslots, last_sweep); }
+                    }
+                    if (on && (sm_ >> lane) == 1u) table.put(hk, o + ab);
+                    __syncwarp();
+                }
             }
-            __syncwarp();
-            uint32_t last_sweep = 0;    // packed tables: every slot is exact for probes below last_sweep + 65536
-
-            uint32_t lit_start = 0;     // start of the current literal run
+            uint32_t lit_start = cursor0;   // start of the current literal run
             uint32_t j = 0;             // probes already done in the current run
             bool done = false;
             while (!done) {                                                   // :171 / :177, 32 probes per trip
@@ -236,8 +262,8 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
                 const uint32_t endmask = __ballot_sync(LZF_FULL_MASK, is_end);
                 if constexpr (kPacked) {
                     const uint32_t p_hi = __shfl_sync(LZF_FULL_MASK, p64 < len ? (uint32_t)p64 : len, 31);
-                    if (p_hi - last_sweep >= 65536u) {
-                        last_sweep = __shfl_sync(LZF_FULL_MASK, (uint32_t)p64, 0);
+                    if (p_hi + ab - last_sweep >= 65536u) {
+                        last_sweep = __shfl_sync(LZF_FULL_MASK, (uint32_t)p64, 0) + ab;
                         table.sweep(nslots, last_sweep);
                     }
                 }
@@ -250,7 +276,7 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
                     const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1);          // 12 bytes remain: both words are inside the block
                     v32 = __funnelshift_r(w0, w1, sh);
                     h = kHash4 ? hash4(v32, hashlog) : hash5(v32, (w1 >> sh) & 0xffu, hashlog);
-                    tdist = table.dist(h, p);                                 // table.replace :196 (read half)
+                    tdist = table.dist(h, p + ab);                            // table.replace :196 (read half)
                     tcand = p - tdist;
                 }
                 const uint32_t same = __match_any_sync(LZF_FULL_MASK, h);
@@ -266,8 +292,9 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
                 uint32_t fsum = 0;
                 uint32_t v_c1 = 0, v_c2 = 0, v_c3 = 0, v_cm1 = 0;
                 bool v_hasb = false, v_pre = false;
-                // addressable (:200-201): 1 <= distance <= 0xFFFF (distance 0 only ever means "p == 0", :200)
-                if (!is_end && tdist - 1u < 0xffffu) {
+                // addressable (:200-201): not the first position of the block (cursor != init_cursor), 1 <= distance
+                // <= 0xFFFF, and inside the history that is physically there
+                if (!is_end && p != cursor0 && tdist - 1u < 0xffffu && tdist <= p) {
                     if (consecutive && tcand + 16 <= len) {
                         const bool hasb = tcand >= 4;
                         const uint32_t s0 = hasb ? tcand - 4 : tcand;
@@ -324,6 +351,7 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
                 uint32_t ins = 0;       // lanes whose probe (or cursor-2 insert) has happened, in order
                 uint32_t s = 0;         // first lane of the current run inside this batch
                 bool committed = false;
+                uint32_t late_q2 = 0xffffffffu;   // a cursor-2 insert that falls on a lane without a hash (last 11 bytes)
                 // Batches in which no two lanes share a table slot (the common case) need no per-sequence
                 // candidate resolution at all: who matches is one ballot per batch, and each further sequence
                 // of the batch is found with scalar bit arithmetic.
@@ -342,10 +370,11 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
                         }
                         w = __ffs(trig) - 1;
                         if ((endmask >> w) & 1u) {
-                            // final literal-only sequence  :178-190
+                            // final literal-only sequence  :178-190.  The probes before the end lane did their
+                            // table.replace: a later block of the same chain (dependent blocks) sees them.
                             if (!emit_sequence(out, opos, cap, in, lit_start, len - lit_start, 0, 0, true, false, 0, 0)) status = LZF_WRITER_FULL;
+                            ins |= ((1u << w) - 1u) & ~((1u << s) - 1u);
                             done = true;
-                            committed = true;                                 // the table is never read again
                             break;
                         }
                         ins |= ((2u << w) - 1u) & ~((1u << s) - 1u);         // probes s..w happened
@@ -371,8 +400,8 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
                         w = __ffs(trig) - 1;
                         if ((endmask >> w) & 1u) {
                             if (!emit_sequence(out, opos, cap, in, lit_start, len - lit_start, 0, 0, true, false, 0, 0)) status = LZF_WRITER_FULL;
+                            ins |= ((1u << w) - 1u) & ~((1u << s) - 1u);
                             done = true;
-                            committed = true;
                             break;
                         }
                         ins |= ((2u << w) - 1u) & ~((1u << s) - 1u);
@@ -413,6 +442,7 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
                             j = 0;
                             const uint32_t l2 = cursor - 2 - base;                // table.replace(cursor - 2) :218
                             if (!((endmask >> l2) & 1u)) ins |= 1u << l2;
+                            else late_q2 = cursor - 2;
                             s = cursor - base;
                             continue;
                         }
@@ -498,34 +528,36 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
                     const bool lits_in_regs = consecutive && lit_start >= base;
                     if (!emit_sequence(out, opos, cap, in, lit_start, cur - backtrack - lit_start, cur - cnd, extra, false,
                                        lits_in_regs, v32, lit_start - base)) {
+                        // the writer refused (:150-163 via NoPartialWrites): compress2 returns here, AFTER the
+                        // table.replace(cursor - 2) of this match (:218) — a later block of the chain sees that state
                         status = LZF_WRITER_FULL;
                         done = true;
-                        committed = true;
-                        break;
                     }
                     lit_start = cursor;
                     j = 0;
 
                     // ---- table.replace(input, cursor - 2)  :218, and where the parse resumes
                     const uint32_t q2 = cursor - 2;
-                    if (consecutive && cursor - base < 32) {
+                    if (consecutive && cursor - base < 32 && !done) {
                         const uint32_t l2 = q2 - base;
-                        // a lane past the 12-byte rule has no hash; its insert can never be read again
+                        // a lane past the 12-byte rule has no hash: its insert is applied after the batch's commit
+                        // (only a later block of the same chain can ever read it)
                         if (!((endmask >> l2) & 1u)) ins |= 1u << l2;
+                        else late_q2 = q2;
                         s = cursor - base;
                         continue;                                             // next sequence of the same batch
                     }
                     // the match left the batch: commit, then insert cursor - 2 behind everything committed
                     {
                         const uint32_t later = same & ins & ~lower_mask & ~(1u << lane);
-                        if (((ins >> lane) & 1u) && later == 0) table.put(h, p);
+                        if (((ins >> lane) & 1u) && later == 0) table.put(h, p + ab);
                         __syncwarp();
                         if (lane == 0) {
                             uint32_t h2;
                             if (kHash4) h2 = hash4(ld4(in, q2), hashlog);
                             else if (len - q2 >= 8) h2 = hash5(ld4(in, q2), in[q2 + 4], hashlog);
                             else h2 = 0;                                      // :43 unwrap_or(0) -> hash of 0
-                            table.put(h2, q2);
+                            table.put(h2, q2 + ab);
                         }
                         committed = true;
                     }
@@ -534,7 +566,17 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
                 if (!committed) {
                     // last inserted lane of each slot wins (mem::swap order, :64-71)
                     const uint32_t later = same & ins & ~lower_mask & ~(1u << lane);
-                    if (((ins >> lane) & 1u) && later == 0) table.put(h, p);
+                    if (((ins >> lane) & 1u) && later == 0) table.put(h, p + ab);
+                    if (late_q2 != 0xffffffffu) {
+                        __syncwarp();
+                        if (lane == 0) {
+                            uint32_t h2;
+                            if (kHash4) h2 = hash4(ld4(in, late_q2), hashlog);
+                            else if (len - late_q2 >= 8) h2 = hash5(ld4(in, late_q2), in[late_q2 + 4], hashlog);
+                            else h2 = 0;                                          // :43 unwrap_or(0) -> hash of 0
+                            table.put(h2, late_q2 + ab);
+                        }
+                    }
                 }
                 __syncwarp();
             }
@@ -547,11 +589,12 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
         }
         // XXH32 of the plaintext / of the stored bytes (compressed, or the plaintext when stored raw):
         // queued so that 8 blocks are hashed per warp pass
-        if (a.xxh_plain) hash_queue_push(&hashq, in, len, a.xxh_plain + b);
+        if (a.xxh_plain) hash_queue_push(&hashq, in + cursor0, own_len, a.xxh_plain + b);
         if (a.xxh_stored) {
             if (status == LZF_OK) hash_queue_push(&hashq, out, opos, a.xxh_stored + b);
-            else hash_queue_push(&hashq, in, len, a.xxh_stored + b);
+            else hash_queue_push(&hashq, in + cursor0, own_len, a.xxh_stored + b);
         }
+      }   // blocks of the chain
     }
     hash_queue_finish(&hashq, kEncodeWarpsPerCta);
 }
@@ -576,7 +619,8 @@ static int launch_encode_variant(const EncodeArgs* args, int num_sms, uint32_t n
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     if (!smem_tables && ctas_per_sm > kGlobalTableCtasPerSm) ctas_per_sm = kGlobalTableCtasPerSm;
     unsigned grid = (unsigned)(num_sms * ctas_per_sm);
-    const unsigned need = (args->nblocks + kWarps - 1) / kWarps;
+    const uint32_t nwork = args->chain_first ? args->nchains : args->nblocks;
+    const unsigned need = (nwork + kWarps - 1) / kWarps;
     if (grid > need) grid = need;
     LZF_LAUNCH(kern, grid, kWarps * 32, dyn, stream, *args, nslots, smem_tables ? 1 : 0);
     return (int)cudaGetLastError();
@@ -590,7 +634,8 @@ extern "C" int lzf_launch_encode(const lzf::EncodeArgs* args, int num_sms, cudaS
     const bool hash4 = args->table_kind == LZF_TABLE_U16;
     const uint32_t nslots = hash4 ? (2u << hashlog) : (1u << hashlog);
     // u16 slots are exact whenever every position fits 16 bits; blocks up to 16 MiB use packed 17-bit slots
-    const bool slot16 = hash4 || (args->max_block_len != 0 && args->max_block_len <= 65536u);
+    const uint64_t span = args->max_pos ? args->max_pos : args->max_block_len;
+    const bool slot16 = hash4 || (span != 0 && span <= 65536u);
     const bool packed = !slot16 && args->max_block_len != 0 && args->max_block_len <= kPacked17MaxLen;
     const size_t table_bytes = slot16 ? (size_t)nslots * 2 : packed ? (size_t)nslots * 2 + nslots / 8 : (size_t)nslots * 4;
     // per-warp tables up to 32 KiB live in shared memory; larger ones (hashlog >= 14 extension) in a

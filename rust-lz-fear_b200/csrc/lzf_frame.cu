@@ -31,6 +31,23 @@ __global__ void __launch_bounds__(32) xxh32_stripes_kernel(const uint8_t* data, 
     if (lane < 4) acc[lane] = a;
 }
 
+constexpr uint32_t kSliceBytes = 64 * 1024;
+
+// compress with a dictionary: block k's input becomes dst[dst_off[k]] = dictionary ++ block, so that the
+// history compress2 sees in front of the block (in_buffer = block_initializer ++ block, compress.rs:218,268)
+// is physically contiguous.  grid = (blocks, 64 KiB slices of the block).
+__global__ void __launch_bounds__(256) stage_dict_kernel(StageArgs a) {
+    const uint32_t k = blockIdx.x;
+    uint8_t* dst = a.dst + a.dst_off[k];
+    const unsigned warp = threadIdx.x >> 5;
+    if (blockIdx.y == 0) {
+        for (uint64_t w0 = (uint64_t)warp * 8192; w0 < a.dlen; w0 += 8 * 8192)
+            warp_copy(dst + w0, a.dict + w0, min((uint64_t)8192, (uint64_t)a.dlen - w0));
+    }
+    const uint64_t s0 = (uint64_t)blockIdx.y * kSliceBytes + (uint64_t)warp * 8192;
+    if (s0 < a.len[k]) warp_copy(dst + a.dlen + s0, a.in + a.src_off[k] + s0, min((uint64_t)8192, (uint64_t)a.len[k] - s0));
+}
+
 // ------------------------------------------------------------------------------------------
 // compress: layout.  One warp per frame scans its blocks' stored sizes, decides the position of
 // every block inside the frame, and writes header, EndMark and content checksum.
@@ -94,7 +111,6 @@ __global__ void __launch_bounds__(128) frame_layout_kernel(LayoutArgs a) {
 // compress: assembly.  grid = (blocks, slices); every CTA moves one 64 KiB slice of one block's
 // stored payload into the frame; slice 0 also writes the length word and the block checksum.
 // ------------------------------------------------------------------------------------------
-constexpr uint32_t kSliceBytes = 64 * 1024;
 
 __global__ void __launch_bounds__(256) frame_assemble_kernel(AssembleArgs a) {
     const uint32_t b = blockIdx.x;
@@ -203,6 +219,13 @@ extern "C" int lzf_launch_xxh32_ranges(const uint8_t* data, const uint64_t* off,
 }
 extern "C" int lzf_launch_xxh32_stripes(const uint8_t* data, uint64_t nstripes, uint32_t* acc, cudaStream_t s) {
     LZF_LAUNCH(lzf::xxh32_stripes_kernel, 1, 32, 0, s, data, nstripes, acc);
+    return (int)cudaGetLastError();
+}
+extern "C" int lzf_launch_stage_dict(const lzf::StageArgs* a, cudaStream_t s) {
+    if (!a->n) return 0;
+    uint32_t slices = 64;                      // blocks are at most 4 MiB here (16 MiB for raw callers: loop below covers it)
+    dim3 grid(a->n, slices);
+    LZF_LAUNCH(lzf::stage_dict_kernel, grid, 256, 0, s, *a);
     return (int)cudaGetLastError();
 }
 extern "C" int lzf_launch_layout(const lzf::LayoutArgs* a, cudaStream_t s) {

@@ -11,6 +11,21 @@ struct EncodeArgs {
     uint8_t* out; const uint64_t* out_off; const uint32_t* out_cap;
     uint32_t* out_len; int32_t* status; uint32_t* xxh_plain; uint32_t* xxh_stored;
     uint32_t* work_counter; uint8_t* global_tables; uint32_t max_block_len;
+    // internal (frame layer): dependent blocks and dictionaries (src/framed/compress.rs:202-214,220,271-275).
+    //   prefix_len[b]  bytes of addressable history physically in front of block b (window / dictionary):
+    //                  compress2's `cursor` (window_offset, compress.rs:222,243)
+    //   abs_base[b]    stream position of the first history byte (the table stores stream positions, :65)
+    //   prime_len[b]   dictionary bytes at the start of b's history whose positions 0, 3, 6, ... are
+    //                  inserted before the block is parsed (compress.rs:204-214); first block of a chain only
+    //   chains         consecutive blocks [chain_first[c], + chain_count[c]) share one table and are parsed in
+    //                  order by one warp; null = every block is its own chain with a fresh table
+    const uint32_t* prefix_len; const uint32_t* abs_base; const uint32_t* prime_len;
+    const uint32_t* chain_first; const uint32_t* chain_count; uint32_t nchains;
+    uint64_t max_pos;   // largest stream position + 1 any block reaches (0 = max_block_len): picks the slot width
+};
+struct StageArgs {      // [dictionary | block] staging copies for blocks whose history is the dictionary
+    uint32_t n; const uint8_t* dict; uint32_t dlen;
+    const uint8_t* in; const uint64_t* src_off; const uint32_t* len; uint8_t* dst; const uint64_t* dst_off;
 };
 struct DecodeArgs {
     const uint8_t* in; const uint64_t* in_off; const uint32_t* in_len; uint32_t nblocks;
@@ -69,6 +84,7 @@ int lzf_launch_decode(const lzf::DecodeArgs* args, int num_sms, cudaStream_t str
 int lzf_launch_xxh32_ranges(const uint8_t* data, const uint64_t* off, const uint64_t* len, uint32_t nranges,
                             uint32_t* hash, cudaStream_t s);
 int lzf_launch_xxh32_stripes(const uint8_t* data, uint64_t nstripes, uint32_t* acc, cudaStream_t s);
+int lzf_launch_stage_dict(const lzf::StageArgs* a, cudaStream_t s);
 int lzf_launch_layout(const lzf::LayoutArgs* a, cudaStream_t s);
 int lzf_launch_assemble(const lzf::AssembleArgs* a, uint32_t max_block_len, cudaStream_t s);
 int lzf_launch_walk(const lzf::WalkArgs* a, cudaStream_t s);

@@ -232,3 +232,19 @@ def test_dependent_and_dictionary_frames(gpu, oracle, issue15_input, corpora, li
         assert (st, plain) == (0, data), kw
     rc, fr = oracle.frame_compress(data, independent_blocks=False, block_size=64 << 10)
     assert gpu.ctx.frame_decompress(fr, cap=len(data) + 16)[:3] == (0, 0, data)
+
+
+def test_dependent_and_dictionary_frames_compress(gpu, oracle, issue15_input):
+    """Compress side of SURVEY §8(f) rank 2: one warp carries the table through all blocks of a dependent
+    frame; dictionaries prime the table.  Frames are byte-identical to the oracle's."""
+    import test_simt_kernels as T
+    T.test_dependent_block_frames_compress(gpu, oracle, issue15_input)
+    T.test_dictionary_frames_compress(gpu, oracle)
+    data = W.text(9 << 20, 7).numpy().tobytes() + W.random_bytes(5 << 20, 8).numpy().tobytes() + W.lowent(3 << 20, 9).numpy().tobytes()
+    dic = W.text(100000, 10).numpy().tobytes()
+    for kw in (dict(independent_blocks=False), dict(independent_blocks=False, block_size=1 << 20, block_checksums=True),
+               dict(dictionary=dic, dictionary_id=1), dict(dictionary=dic, independent_blocks=False, block_size=256 << 10)):
+        st, frame = gpu.ctx.frame_compress(data, **kw)
+        assert (st, frame) == oracle.frame_compress(data, **kw), sorted(kw)
+        d = kw.get("dictionary", b"")
+        assert gpu.ctx.frame_decompress(frame, dictionary=d, cap=len(data) + 16)[:3] == (0, 0, data)

@@ -94,8 +94,7 @@ def test_frame_settings_errors(emu, oracle):
     assert emu.ctx.frame_compress(data, block_size=16 << 20)[0] == N.F_PANIC
     st, frame = emu.ctx.frame_compress(data, cap=10)
     assert st == N.F_WRITE_ERROR == oracle.F_WRITE_ERROR
-    with pytest.raises(N.LzfCallError):
-        emu.ctx.frame_compress(data, independent_blocks=False)     # not on the GPU path yet: fails loudly
+    assert emu.ctx.frame_compress(data, independent_blocks=False) == oracle.frame_compress(data, independent_blocks=False)
 
 
 def test_frame_decode_corpus(emu, oracle, corpora):              # fuzz/corpus/decode replay
@@ -270,3 +269,35 @@ def test_dependent_frames_with_short_blocks(emu, oracle):
     dic = b"0123456789" * 10
     far = bytes([0x00, 30, 0, 0x10, 0x21])                           # offset 30 at o=0: into the dictionary
     parity.check_frame_decode_errors(emu, oracle, [hdr + W(far) + W(b) + W(c) + struct.pack("<I", 0)], dictionary=dic)
+
+
+def _dep_inputs():
+    from lz_fear_b200 import workloads as W
+    t = W.text(200000, 41).numpy().tobytes()
+    return [b"", b"abc", t[:70000], t + W.lowent(90000, 42).numpy().tobytes() + t[:50000], bytes(200000),
+            W.random_bytes(150000, 5).numpy().tobytes(), t[:65536], t[:65537], t[:131072]]
+
+
+def test_dependent_block_frames_compress(emu, oracle, issue15_input):   # compress.rs:220,271-275; tests/issue-15.rs
+    for kw in (dict(independent_blocks=False, block_size=64 << 10),
+               dict(independent_blocks=False, block_size=64 << 10, block_checksums=True, content_checksum=False),
+               dict(independent_blocks=False, block_size=256 << 10)):
+        for data in _dep_inputs() + [issue15_input]:
+            st, frame = emu.ctx.frame_compress(data, **kw)
+            orc, oframe = oracle.frame_compress(data, **kw)
+            assert (st, frame) == (orc, oframe), (kw, len(data))
+            assert emu.ctx.frame_decompress(frame, cap=len(data) + 16)[:3] == (0, 0, data)
+
+
+def test_dictionary_frames_compress(emu, oracle):                       # compress.rs:202-214
+    from lz_fear_b200 import workloads as W
+    dic_small = [1, 3, 3, 7]                                             # tests/output_equivalence.rs:44
+    dic = W.text(70000, 43).numpy().tobytes()
+    for d in (bytes(dic_small), dic[:1000], dic[:65536], dic):
+        for kw in (dict(block_size=64 << 10), dict(independent_blocks=False, block_size=64 << 10),
+                   dict(block_size=256 << 10, block_checksums=True)):
+            for data in _dep_inputs()[2:6]:
+                st, frame = emu.ctx.frame_compress(data, dictionary=d, dictionary_id=9, **kw)
+                orc, oframe = oracle.frame_compress(data, dictionary=d, dictionary_id=9, **kw)
+                assert (st, frame) == (orc, oframe), (len(d), kw, len(data))
+                assert emu.ctx.frame_decompress(frame, dictionary=d, cap=len(data) + 16)[:3] == (0, 0, data)
