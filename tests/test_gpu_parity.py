@@ -240,6 +240,9 @@ def test_dependent_and_dictionary_frames_compress(gpu, oracle, issue15_input):
     import test_simt_kernels as T
     T.test_dependent_block_frames_compress(gpu, oracle, issue15_input)
     T.test_dictionary_frames_compress(gpu, oracle)
+    for kw in (dict(independent_blocks=False, block_size=256 << 10), dict(block_size=256 << 10, block_checksums=True, dictionary=bytes(range(200)) * 400)):
+        for d in T._dep_inputs():
+            assert gpu.ctx.frame_compress(d, **kw) == oracle.frame_compress(d, **kw)
     data = W.text(9 << 20, 7).numpy().tobytes() + W.random_bytes(5 << 20, 8).numpy().tobytes() + W.lowent(3 << 20, 9).numpy().tobytes()
     dic = W.text(100000, 10).numpy().tobytes()
     for kw in (dict(independent_blocks=False), dict(independent_blocks=False, block_size=1 << 20, block_checksums=True),
