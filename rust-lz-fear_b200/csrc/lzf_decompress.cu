@@ -40,14 +40,16 @@ struct __align__(16) DecodeWarpSmem {
     uint8_t win[kWin];            // staged compressed bytes
     uint8_t step[kWin + 32];      // step[p] = encoded size of the LSIC-free sequence whose token is win[p]; 0 = not fast
     uint8_t stage[kStage];        // output staging ring
-    uint32_t plist[32];           // token positions of the current step (walk32: shared-memory addresses of step[p])
+    uint32_t plist[32];           // token positions of the current step
     uint64_t mbar;
     uint64_t pad;
 };
 
 // step[] for the freshly staged window: 4 positions per lane and pass, SIMD-in-a-word.
-//   step = 3 + (token >> 4), or 0 when either nibble is 15 (LSIC extension -> slow path) or when
-//   the sequence would end beyond `wend` (window / block end -> refill or slow path).
+//   step = 3 + (token >> 4) for a sequence without length extensions;
+//   step = 1 when either nibble is 15: the walk works the size out itself if it ever lands there
+//          (most such bytes are literals, not tokens, so nothing is spent on them here);
+//   step = 0 when a plain sequence would end beyond `wend` (window / block end -> refill or slow path).
 __device__ __forceinline__ void build_steps(DecodeWarpSmem& sm, uint32_t wlen, uint32_t wend) {
     const unsigned lane = lane_id();
     const uint32_t* w4 = reinterpret_cast<const uint32_t*>(sm.win);
@@ -56,14 +58,37 @@ __device__ __forceinline__ void build_steps(DecodeWarpSmem& sm, uint32_t wlen, u
     for (uint32_t i = lane; i < nwords; i += 32) {
         const uint32_t w = w4[i];
         const uint32_t special = __vcmpeq4(w & 0xf0f0f0f0u, 0xf0f0f0f0u) | __vcmpeq4(w & 0x0f0f0f0fu, 0x0f0f0f0fu);
-        s4[i] = (((w >> 4) & 0x0f0f0f0fu) + 0x03030303u) & ~special;
+        s4[i] = ((((w >> 4) & 0x0f0f0f0fu) + 0x03030303u) & ~special) | (special & 0x01010101u);
     }
     __syncwarp();
     // the last kFastSeqMax positions may describe sequences that cross wend; wend itself terminates a walk
     const uint32_t p = wend - min(wend, kFastSeqMax + 1u) + lane;
-    if (p <= wend && (p == wend || p + sm.step[p] > wend)) sm.step[p] = 0;
+    if (p <= wend && (p == wend || (sm.step[p] != 1 && p + sm.step[p] > wend))) sm.step[p] = 0;
     __syncwarp();
 }
+
+// Encoded size of the sequence whose token sits at win[p] when it carries single-byte length extensions
+// (literal run 15..269, match 19..273); 0 when an extension continues (0xFF), when the sequence does not
+// fit the window, or when it touches the end of the block (all of those: slow path).  Warp-uniform.
+__device__ __forceinline__ uint32_t medium_size(const DecodeWarpSmem& sm, uint32_t p, uint32_t wend) {
+    if (p + 4 > wend) return 0;
+    const uint32_t tok = sm.win[p];
+    uint32_t lit = tok >> 4, q = p + 1;
+    if (lit == 15u) {
+        const uint32_t e = sm.win[q];
+        if (e == 255u) return 0;
+        lit += e; q++;
+    }
+    q += lit + 2;                                   // literals + offset
+    if (q > wend) return 0;
+    if ((tok & 15u) == 15u) {
+        if (q + 1 > wend || sm.win[q] == 255u) return 0;
+        q++;
+    }
+    return q - p;
+}
+constexpr uint32_t kStageBudget = 1400;             // output bytes one step may stage (ring is 2048)
+constexpr uint32_t kLaneCopyMax = 20;               // longer literal runs / matches are copied by the whole warp
 
 // 128-byte register window over the compressed stream (slow path).
 struct Window {
@@ -225,91 +250,6 @@ __device__ __forceinline__ uint32_t rebase_stage(uint8_t* stage, const uint8_t* 
     return nb;
 }
 
-// The serial part of the decoder: follow step[] from `pp` for at most 32 sequences, recording where each
-// token sits.  Five instructions per sequence (load, test, branch, store, add); written in PTX because
-// the compiler's version of this loop carries three redundant induction variables.
-//   pp      in/out: shared-memory address of step[p]
-//   plist   shared-memory address of the position list (u32 x 32)
-// returns the number of sequences walked.
-#if !defined(LZF_SIMT_EMU) && defined(LZF_DEC_PTX_WALK)   // measured slower than the compiler's loop (322 vs 354 GiB/s): kept for reference
-__device__ __noinline__ uint32_t walk32(uint32_t& pp, uint32_t plist) {
-    uint32_t cnt;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred q;\n\t"
-        ".reg .u32 d, pl;\n\t"
-        "mov.u32 %0, 0;\n\t"
-        "mov.u32 pl, %2;\n\t"
-        "WALK_LOOP:\n\t"
-        "ld.shared.u8 d, [%1];\n\t"
-        "setp.eq.u32 q, d, 0;\n\t"
-        "@q bra.uni WALK_DONE_0;\n\t"
-        "st.shared.u32 [pl+0], %1;\n\t"
-        "add.u32 %1, %1, d;\n\t"
-        "ld.shared.u8 d, [%1];\n\t"
-        "setp.eq.u32 q, d, 0;\n\t"
-        "@q bra.uni WALK_DONE_1;\n\t"
-        "st.shared.u32 [pl+4], %1;\n\t"
-        "add.u32 %1, %1, d;\n\t"
-        "ld.shared.u8 d, [%1];\n\t"
-        "setp.eq.u32 q, d, 0;\n\t"
-        "@q bra.uni WALK_DONE_2;\n\t"
-        "st.shared.u32 [pl+8], %1;\n\t"
-        "add.u32 %1, %1, d;\n\t"
-        "ld.shared.u8 d, [%1];\n\t"
-        "setp.eq.u32 q, d, 0;\n\t"
-        "@q bra.uni WALK_DONE_3;\n\t"
-        "st.shared.u32 [pl+12], %1;\n\t"
-        "add.u32 %1, %1, d;\n\t"
-        "ld.shared.u8 d, [%1];\n\t"
-        "setp.eq.u32 q, d, 0;\n\t"
-        "@q bra.uni WALK_DONE_4;\n\t"
-        "st.shared.u32 [pl+16], %1;\n\t"
-        "add.u32 %1, %1, d;\n\t"
-        "ld.shared.u8 d, [%1];\n\t"
-        "setp.eq.u32 q, d, 0;\n\t"
-        "@q bra.uni WALK_DONE_5;\n\t"
-        "st.shared.u32 [pl+20], %1;\n\t"
-        "add.u32 %1, %1, d;\n\t"
-        "ld.shared.u8 d, [%1];\n\t"
-        "setp.eq.u32 q, d, 0;\n\t"
-        "@q bra.uni WALK_DONE_6;\n\t"
-        "st.shared.u32 [pl+24], %1;\n\t"
-        "add.u32 %1, %1, d;\n\t"
-        "ld.shared.u8 d, [%1];\n\t"
-        "setp.eq.u32 q, d, 0;\n\t"
-        "@q bra.uni WALK_DONE_7;\n\t"
-        "st.shared.u32 [pl+28], %1;\n\t"
-        "add.u32 %1, %1, d;\n\t"
-        "add.u32 pl, pl, 32;\n\t"
-        "add.u32 %0, %0, 8;\n\t"
-        "setp.lt.u32 q, %0, 32;\n\t"
-        "@q bra.uni WALK_LOOP;\n\t"
-        "bra.uni WALK_END;\n\t"
-        "WALK_DONE_1: add.u32 %0, %0, 1;\n\t"
-        "bra.uni WALK_END;\n\t"
-        "WALK_DONE_2: add.u32 %0, %0, 2;\n\t"
-        "bra.uni WALK_END;\n\t"
-        "WALK_DONE_3: add.u32 %0, %0, 3;\n\t"
-        "bra.uni WALK_END;\n\t"
-        "WALK_DONE_4: add.u32 %0, %0, 4;\n\t"
-        "bra.uni WALK_END;\n\t"
-        "WALK_DONE_5: add.u32 %0, %0, 5;\n\t"
-        "bra.uni WALK_END;\n\t"
-        "WALK_DONE_6: add.u32 %0, %0, 6;\n\t"
-        "bra.uni WALK_END;\n\t"
-        "WALK_DONE_7: add.u32 %0, %0, 7;\n\t"
-        "bra.uni WALK_END;\n\t"
-        "WALK_DONE_0:\n\t"
-        "WALK_END:\n\t"
-        "}"
-        : "=r"(cnt), "+r"(pp)
-        : "r"(plist)
-        : "memory");
-    return cnt;
-}
-#endif
-
 __global__ void __launch_bounds__(kDecodeWarpsPerCta * 32, LZF_DEC_MINCTAS)
 decode_blocks_kernel(DecodeArgs a) {
     LZF_DYN_SMEM(smem_raw);
@@ -395,25 +335,22 @@ decode_blocks_kernel(DecodeArgs a) {
                 }
                 // window-relative positions from here on
                 uint32_t p = (uint32_t)(q - wq);
+                const uint32_t wend = (uint32_t)(((wq + wlen) < qn ? (wq + wlen) : qn) - wq);
 
-                // ---- walk: up to 32 LSIC-free sequences that lie completely inside the window.  This is
-                // the only serial part of the decoder: one shared-memory byte per sequence.
+                // ---- walk: up to 32 sequences that lie completely inside the window (plain ones, and ones whose
+                // length extensions are single bytes).  This is the only serial part of the decoder: one
+                // shared-memory byte per plain sequence.  (A hand-written PTX version of this loop — 5 instructions
+                // per sequence — measured slower than the compiler's, 322 vs 354 GiB/s, and was dropped.)
                 uint32_t cnt = 0;
-#if !defined(LZF_SIMT_EMU) && defined(LZF_DEC_PTX_WALK)
-                const uint32_t step_sa = smem_addr(sm.step);
-                if (s.olen + 32u * 32u <= bound) {
-                    uint32_t pp = step_sa + p;
-                    cnt = walk32(pp, smem_addr(sm.plist));
-                    p = pp - step_sa;
-                }
-                __syncwarp();
-                const uint32_t my_p = sm.plist[lane] - step_sa;
-#else
-                if (s.olen + 32u * 32u <= bound) {
+                {
 #pragma unroll 8
                     for (int k = 0; k < 32; k++) {
-                        const uint32_t d = sm.step[p];
-                        if (d == 0) break;
+                        uint32_t d = sm.step[p];
+                        if (d < 3) {                                  // 0: stop; 1: a token with length extensions
+                            if (d == 0) break;
+                            d = medium_size(sm, p, wend);
+                            if (d == 0) break;
+                        }
                         sm.plist[k] = p;
                         p += d;
                         cnt = k + 1;
@@ -421,14 +358,18 @@ decode_blocks_kernel(DecodeArgs a) {
                 }
                 __syncwarp();
                 const uint32_t my_p = sm.plist[lane];
-#endif
                 // ---- per-lane decode of the sequence headers, output positions by warp scan
-                uint32_t lit = 0, ml = 0, off = 1, tot = 0;
+                uint32_t lit = 0, ml = 0, off = 1, tot = 0, lit_src = 0;
                 if (lane < cnt) {
                     const uint32_t tok = sm.win[my_p];
                     lit = tok >> 4;
-                    ml = (tok & 15u) + 4u;
-                    off = (uint32_t)sm.win[my_p + 1 + lit] | ((uint32_t)sm.win[my_p + 2 + lit] << 8);
+                    lit_src = my_p + 1;
+                    if (lit == 15u) { lit += sm.win[lit_src]; lit_src++; }
+                    const uint32_t op = lit_src + lit;
+                    off = (uint32_t)sm.win[op] | ((uint32_t)sm.win[op + 1] << 8);
+                    ml = tok & 15u;
+                    if (ml == 15u) ml += sm.win[op + 2];
+                    ml += 4u;
                     tot = lit + ml;
                 }
                 uint32_t inc = tot;
@@ -440,20 +381,18 @@ decode_blocks_kernel(DecodeArgs a) {
                 const uint32_t olen0 = (uint32_t)s.olen;
                 const uint32_t o_k = olen0 + inc - tot;                       // output position of my literals
                 const uint32_t dstp = o_k + lit;                               // ... and of my match
-                // offsets must be non-zero and inside prefix ++ output (decompress.rs:83-89); anything
-                // else is replayed by the slow path, which reports the error exactly like the reference
-                const bool bad = lane < cnt && (off == 0u || (uint64_t)off > (uint64_t)dstp + s.plen);
+                // A step stops before: a sequence whose offset is zero or reaches outside prefix ++ output
+                // (decompress.rs:83-89) or that would pass the output limit / capacity — the slow path replays it
+                // and reports the error exactly like the reference — and before the staging budget runs out.
+                const bool bad = lane < cnt && (off == 0u || (uint64_t)off > (uint64_t)dstp + s.plen ||
+                                                (uint64_t)olen0 + inc > bound || (inc > kStageBudget && lane > 0));
                 const uint32_t fb = __ballot_sync(LZF_FULL_MASK, bad);
                 uint32_t in_end = p;
                 if (fb) {
                     const uint32_t keep = (uint32_t)(__ffs(fb) - 1);
                     if (keep < cnt) {                                           // the next sequence starts where the kept ones end
                         cnt = keep;
-#if !defined(LZF_SIMT_EMU) && defined(LZF_DEC_PTX_WALK)
-                        in_end = sm.plist[keep] - step_sa;
-#else
                         in_end = sm.plist[keep];
-#endif
                     }
                 }
                 if (cnt == 0) {
@@ -468,11 +407,18 @@ decode_blocks_kernel(DecodeArgs a) {
                 const uint32_t out_end = __shfl_sync(LZF_FULL_MASK, o_k + tot, cnt - 1);
 
                 // ---- literals: every lane copies its own run into the staging ring
-                if (act) {
-                    const uint8_t* src = sm.win + my_p + 1;
+                if (act && lit <= kLaneCopyMax) {
+                    const uint8_t* src = sm.win + lit_src;
                     uint8_t* d = sm.stage + (o_k - sbias);
 #pragma unroll
-                    for (uint32_t i = 0; i < 14; i++) if (i < lit) d[i] = src[i];
+                    for (uint32_t i = 0; i < kLaneCopyMax; i++) if (i < lit) d[i] = src[i];
+                }
+                for (uint32_t lm = __ballot_sync(LZF_FULL_MASK, act && lit > kLaneCopyMax); lm; lm &= lm - 1) {
+                    const uint32_t k = __ffs(lm) - 1;                           // a long run: the whole warp copies it
+                    const uint32_t n = __shfl_sync(LZF_FULL_MASK, lit, k);
+                    const uint8_t* src = sm.win + __shfl_sync(LZF_FULL_MASK, lit_src, k);
+                    uint8_t* d = sm.stage + (__shfl_sync(LZF_FULL_MASK, o_k, k) - sbias);
+                    for (uint32_t i = lane; i < n; i += 32) d[i] = src[i];
                 }
                 __syncwarp();
 
@@ -482,7 +428,27 @@ decode_blocks_kernel(DecodeArgs a) {
                 while (pending) {
                     const uint32_t first = __ffs(pending) - 1;
                     const uint32_t dst_first = __shfl_sync(LZF_FULL_MASK, dstp, first);
-                    const bool ready = ((pending >> lane) & 1u) && (lane == first || srcp + (int64_t)ml <= (int64_t)dst_first);
+                    const uint32_t ml_first = __shfl_sync(LZF_FULL_MASK, ml, first);
+                    if (ml_first > kLaneCopyMax) {
+                        // a long match at the head of the queue: the whole warp copies it, 32 bytes per pass when
+                        // the offset allows, as the periodic pattern it is when source and destination overlap closely
+                        const uint32_t off_f = __shfl_sync(LZF_FULL_MASK, off, first);
+                        const int64_t src_f = (int64_t)dst_first - (int64_t)off_f;
+                        uint8_t* d = sm.stage + (dst_first - sbias);
+                        for (uint32_t k0 = 0; k0 < ml_first; k0 += 32) {
+                            const uint32_t k = k0 + lane;
+                            if (k < ml_first) {
+                                const int64_t x = src_f + (off_f >= 32 ? (int64_t)k : (int64_t)(k % off_f));
+                                d[k] = x >= (int64_t)flushed ? sm.stage[(uint32_t)x - sbias] : hist_byte(s.out, s.prefix_end, x);
+                            }
+                            if (off_f >= 32) __syncwarp();
+                        }
+                        __syncwarp();
+                        pending &= ~(1u << first);
+                        continue;
+                    }
+                    const bool ready = ((pending >> lane) & 1u) && ml <= kLaneCopyMax &&
+                                       (lane == first || srcp + (int64_t)ml <= (int64_t)dst_first);
                     if (ready) {
                         uint8_t* d = sm.stage + (dstp - sbias);
                         if (srcp >= (int64_t)flushed) {
@@ -491,7 +457,7 @@ decode_blocks_kernel(DecodeArgs a) {
                         } else if (srcp >= 0 && srcp + (int64_t)ml <= (int64_t)flushed) {
                             const uint8_t* g = s.out + srcp;                      // flushed history -> staged
 #pragma unroll
-                            for (uint32_t i = 0; i < 18; i++) if (i < ml) d[i] = g[i];
+                            for (uint32_t i = 0; i < kLaneCopyMax; i++) if (i < ml) d[i] = g[i];
                         } else {
                             for (uint32_t i = 0; i < ml; i++) {                   // straddles the flush point or the prefix
                                 const int64_t x = srcp + i;
