@@ -26,7 +26,7 @@
 namespace lzf {
 
 #ifndef LZF_DEC_MINCTAS
-#define LZF_DEC_MINCTAS 5                  // resident CTAs per SM the register budget is tuned for (48 regs)
+#define LZF_DEC_MINCTAS 4                  // resident CTAs per SM the register budget is tuned for (64 regs; 5 x 48 spills)
 #endif
 #ifndef LZF_DEC_WIN
 #define LZF_DEC_WIN 1024
