@@ -214,9 +214,8 @@ int compress_blocks_impl(lzf_ctx* c, const uint8_t* d_in, const uint64_t* d_in_o
     a.xxh_plain = d_xxh_plain; a.xxh_stored = d_xxh_stored;
     a.work_counter = cur_slot(c)->d_counter;
     a.max_block_len = max_block_len;
-    const size_t nslots = table_kind == LZF_TABLE_U16 ? ((size_t)2 << hashlog) : ((size_t)1 << hashlog);
-    if (nslots * 2 > 16 * 1024) {      // any layout that may not fit shared memory (lzf_launch_encode decides)
-        const int rc = ensure_dev(c, cur_slot(c)->d_tables, lzf_encode_global_table_warps(c->num_sms) * nslots * 4);
+    if (const size_t scratch = lzf_encode_global_table_bytes(&a, c->num_sms)) {   // tables that do not fit shared memory
+        const int rc = ensure_dev(c, cur_slot(c)->d_tables, scratch);
         if (rc) return rc;
         a.global_tables = (uint8_t*)cur_slot(c)->d_tables.p;
     }

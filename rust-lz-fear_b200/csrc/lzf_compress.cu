@@ -29,6 +29,7 @@
 // when every position fits u16).
 #include "lzf_kernels.cuh"
 
+#include <stdlib.h>
 #include <type_traits>
 
 namespace lzf {
@@ -162,13 +163,22 @@ constexpr uint32_t kPacked17MaxLen = 16u << 20;
 #ifndef LZF_ENC_WARPS
 #define LZF_ENC_WARPS 4
 #endif
+#ifndef LZF_ENC_BIG_WARPS
+#define LZF_ENC_BIG_WARPS 28
+#endif
 constexpr int kEncodeWarpsPerCta = LZF_ENC_WARPS;
-constexpr int kGlobalTableCtasPerSm = 4;   // bounds the global table scratch
+// The parse is one long dependent chain per warp (~8 cycles per instruction, ncu r01_ncu_encode_v5), so
+// throughput is resident warps x chain speed.  Tables of <= 8.5 KiB (u16 / packed 17-bit slots) therefore
+// run ONE CTA of kEncodeBigWarps warps per SM at <= 72 registers; as many tables as fit live in shared
+// memory (26 packed ones in 227 KiB), the remaining warps keep theirs in an L2-resident global scratch.
+constexpr int kEncodeBigWarps = LZF_ENC_BIG_WARPS;
+constexpr int kGlobalTableCtasPerSm = 4;   // bounds the global table scratch (CTAs of kEncodeWarpsPerCta warps)
+constexpr size_t kSmemPerCtaMax = 227 * 1024;   // sm_100a opt-in maximum per CTA
 
 // kTab: 0 = u32 slots, 1 = u16 slots (positions fit 16 bits), 2 = packed 17-bit slots
 template <int kTab, bool kHash4, int kWarps>
 __global__ void __launch_bounds__(kWarps * 32)
-encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
+encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int n_smem_warps) {
     LZF_DYN_SMEM(smem_raw);
     __shared__ HashQueue hashq;
     constexpr bool kPacked = kTab == 2;
@@ -178,10 +188,10 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
     const unsigned warp_in_cta = threadIdx.x >> 5;
     const size_t table_bytes = kPacked ? (size_t)nslots * 2 + nslots / 8 : (size_t)nslots * sizeof(Slot);
     uint8_t* table_mem;
-    if (smem_tables) {
+    if ((int)warp_in_cta < n_smem_warps) {
         table_mem = smem_raw + (size_t)warp_in_cta * table_bytes;
     } else {
-        const size_t gw = (size_t)blockIdx.x * kEncodeWarpsPerCta + warp_in_cta;
+        const size_t gw = (size_t)blockIdx.x * (kEncodeWarpsPerCta - n_smem_warps) + (warp_in_cta - n_smem_warps);
         table_mem = a.global_tables + gw * table_bytes;
     }
     typename std::conditional<kPacked, Packed17Table, PlainTable<Slot>>::type table;
@@ -603,13 +613,59 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int smem_tables) {
 
 // Host-side launcher.  Returns a cudaError_t as int.
 namespace lzf {
+// Which instantiation a batch runs on, and where its tables live.
+struct EncodePlan {
+    int variant;            // 0: u32 slots, 1: u16 slots, 2: packed 17-bit slots, 3: hash4 (U16Table)
+    uint32_t nslots;
+    size_t table_bytes;     // per warp
+    int warps;              // per CTA
+    int n_smem_warps;       // warps of a CTA whose table is in shared memory
+    int global_warps_per_sm;   // upper bound of warps per SM that keep their table in the global scratch
+};
+
+static EncodePlan plan_encode(const EncodeArgs* args) {
+    EncodePlan p;
+    const uint32_t hashlog = args->hashlog;
+    const bool hash4 = args->table_kind == LZF_TABLE_U16;
+    p.nslots = hash4 ? (2u << hashlog) : (1u << hashlog);
+    // u16 slots are exact whenever every position fits 16 bits; blocks up to 16 MiB use packed 17-bit slots
+    const uint64_t span = args->max_pos ? args->max_pos : args->max_block_len;
+    const bool slot16 = hash4 || (span != 0 && span <= 65536u);
+    const bool packed = !slot16 && args->max_block_len != 0 && args->max_block_len <= kPacked17MaxLen;
+    p.table_bytes = slot16 ? (size_t)p.nslots * 2 : packed ? (size_t)p.nslots * 2 + p.nslots / 8 : (size_t)p.nslots * 4;
+    p.variant = hash4 ? 3 : slot16 ? 1 : packed ? 2 : 0;
+    bool big = p.variant == 1 || p.variant == 2;
+    if (p.variant == 2 && getenv("LZF_B200_ENC_U32")) {               // tuning knob: plain u32 slots in the global scratch
+        p.variant = 0;
+        p.table_bytes = (size_t)p.nslots * 4;
+    }
+    const size_t smem_budget = kSmemPerCtaMax - sizeof(HashQueue) - 256;
+    if (big) {
+        // one big CTA per SM; whatever does not fit shared memory goes to the global scratch
+        p.warps = kEncodeBigWarps;
+        int fit = (int)(smem_budget / p.table_bytes);
+        if (const char* e = getenv("LZF_B200_ENC_SMEM_WARPS")) {      // test / tuning knob: fewer shared-memory tables
+            const int v = atoi(e);
+            if (v >= 0 && v < fit) fit = v;
+        }
+        p.n_smem_warps = fit < p.warps ? fit : p.warps;
+        p.global_warps_per_sm = 2 * (p.warps - p.n_smem_warps);       // 2: small tables could make two CTAs resident
+    } else {
+        // 16 KiB and larger tables (u32 slots, U16Table): CTAs of 4 warps, all in shared memory or all in the scratch
+        p.warps = kEncodeWarpsPerCta;
+        const bool smem_tables = p.table_bytes <= 32 * 1024 && p.table_bytes * p.warps <= 200 * 1024;
+        p.n_smem_warps = smem_tables ? p.warps : 0;
+        p.global_warps_per_sm = smem_tables ? 0 : kGlobalTableCtasPerSm * p.warps;
+    }
+    return p;
+}
+
 template <int kTab, bool kHash4, int kWarps>
-static int launch_encode_variant(const EncodeArgs* args, int num_sms, uint32_t nslots, size_t table_bytes, bool smem_tables,
-                                 cudaStream_t stream) {
+static int launch_encode_variant(const EncodeArgs* args, int num_sms, const EncodePlan& p, cudaStream_t stream) {
     auto kern = encode_blocks_kernel<kTab, kHash4, kWarps>;
     cudaError_t e;
     int ctas_per_sm = 1;
-    const size_t dyn = smem_tables ? table_bytes * kWarps : 0;
+    const size_t dyn = p.table_bytes * p.n_smem_warps;
     if (dyn > 48 * 1024) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
         if (e != cudaSuccess) return (int)e;
@@ -617,12 +673,13 @@ static int launch_encode_variant(const EncodeArgs* args, int num_sms, uint32_t n
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kWarps * 32, dyn);
     if (e != cudaSuccess) return (int)e;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
-    if (!smem_tables && ctas_per_sm > kGlobalTableCtasPerSm) ctas_per_sm = kGlobalTableCtasPerSm;
+    const int gw = kWarps - p.n_smem_warps;                           // global-table warps per CTA
+    if (gw > 0 && ctas_per_sm * gw > p.global_warps_per_sm) ctas_per_sm = p.global_warps_per_sm / gw;
     unsigned grid = (unsigned)(num_sms * ctas_per_sm);
     const uint32_t nwork = args->chain_first ? args->nchains : args->nblocks;
     const unsigned need = (nwork + kWarps - 1) / kWarps;
     if (grid > need) grid = need;
-    LZF_LAUNCH(kern, grid, kWarps * 32, dyn, stream, *args, nslots, smem_tables ? 1 : 0);
+    LZF_LAUNCH(kern, grid, kWarps * 32, dyn, stream, *args, p.nslots, p.n_smem_warps);
     return (int)cudaGetLastError();
 }
 }  // namespace lzf
@@ -630,26 +687,20 @@ static int launch_encode_variant(const EncodeArgs* args, int num_sms, uint32_t n
 extern "C" int lzf_launch_encode(const lzf::EncodeArgs* args, int num_sms, cudaStream_t stream) {
     using namespace lzf;
     if (args->nblocks == 0) return 0;
-    const uint32_t hashlog = args->hashlog;
-    const bool hash4 = args->table_kind == LZF_TABLE_U16;
-    const uint32_t nslots = hash4 ? (2u << hashlog) : (1u << hashlog);
-    // u16 slots are exact whenever every position fits 16 bits; blocks up to 16 MiB use packed 17-bit slots
-    const uint64_t span = args->max_pos ? args->max_pos : args->max_block_len;
-    const bool slot16 = hash4 || (span != 0 && span <= 65536u);
-    const bool packed = !slot16 && args->max_block_len != 0 && args->max_block_len <= kPacked17MaxLen;
-    const size_t table_bytes = slot16 ? (size_t)nslots * 2 : packed ? (size_t)nslots * 2 + nslots / 8 : (size_t)nslots * 4;
-    // per-warp tables up to 32 KiB live in shared memory; larger ones (hashlog >= 14 extension) in a
-    // ctx-owned global scratch that stays L2-resident
-    const int warps = (hash4 || (!slot16 && !packed)) ? kEncodeWarpsPerCta : 8;
-    const bool smem_tables = table_bytes <= 32 * 1024 && table_bytes * warps <= 200 * 1024;
-    if (!smem_tables && args->global_tables == nullptr) return (int)cudaErrorInvalidValue;
-    if (hash4) return launch_encode_variant<1, true, kEncodeWarpsPerCta>(args, num_sms, nslots, table_bytes, smem_tables, stream);
-    if (slot16) return launch_encode_variant<1, false, 8>(args, num_sms, nslots, table_bytes, smem_tables, stream);
-    if (packed) return launch_encode_variant<2, false, 8>(args, num_sms, nslots, table_bytes, smem_tables, stream);
-    return launch_encode_variant<0, false, kEncodeWarpsPerCta>(args, num_sms, nslots, table_bytes, smem_tables, stream);
+    const EncodePlan p = plan_encode(args);
+    if (p.global_warps_per_sm > 0 && args->global_tables == nullptr) return (int)cudaErrorInvalidValue;
+    switch (p.variant) {
+        case 3: return launch_encode_variant<1, true, kEncodeWarpsPerCta>(args, num_sms, p, stream);
+        case 1: return launch_encode_variant<1, false, kEncodeBigWarps>(args, num_sms, p, stream);
+        case 2: return launch_encode_variant<2, false, kEncodeBigWarps>(args, num_sms, p, stream);
+        default:
+            if (p.warps == kEncodeBigWarps) return launch_encode_variant<0, false, kEncodeBigWarps>(args, num_sms, p, stream);
+            return launch_encode_variant<0, false, kEncodeWarpsPerCta>(args, num_sms, p, stream);
+    }
 }
 
-// Number of warps a global-table launch may start (sizing of the scratch).
-extern "C" size_t lzf_encode_global_table_warps(int num_sms) {
-    return (size_t)num_sms * lzf::kGlobalTableCtasPerSm * 8;
+// Bytes of global table scratch a launch with these arguments may touch (0: every table is in shared memory).
+extern "C" size_t lzf_encode_global_table_bytes(const lzf::EncodeArgs* args, int num_sms) {
+    const lzf::EncodePlan p = lzf::plan_encode(args);
+    return (size_t)num_sms * p.global_warps_per_sm * p.table_bytes;
 }

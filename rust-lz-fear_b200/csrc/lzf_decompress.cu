@@ -309,6 +309,7 @@ decode_blocks_kernel(DecodeArgs a) {
             // the fast path works in 32-bit output positions and never exceeds this bound
             const uint64_t bound64 = s.cap < s.limit ? s.cap : s.limit;
             const uint32_t bound = bound64 > 0xfffff000ull ? 0xfffff000u : (uint32_t)bound64;
+            bool plain_mode = true;   // the walk flavour follows the stream: plain sequences only / mixed with length extensions
 
             while (s.pos < s.n && s.status == LZF_OK && !s.finished) {
                 const uint64_t q = q0 + s.pos;
@@ -339,22 +340,61 @@ decode_blocks_kernel(DecodeArgs a) {
 
                 // ---- walk: up to 32 sequences that lie completely inside the window (plain ones, and ones whose
                 // length extensions are single bytes).  This is the only serial part of the decoder: one
-                // shared-memory byte per plain sequence.  (A hand-written PTX version of this loop — 5 instructions
-                // per sequence — measured slower than the compiler's, 322 vs 354 GiB/s, and was dropped.)
+                // shared-memory byte per plain sequence.
                 uint32_t cnt = 0;
-                {
-#pragma unroll 8
-                    for (int k = 0; k < 32; k++) {
+                if (plain_mode) {
+                    // plain prefix, branch-free: a position that is not a plain sequence (step < 3) does not advance
+                    // p, so the walk sticks there and every later slot repeats it; four instructions per sequence
+                    // (LDS, STS, ISETP, predicated IADD) and one uniform branch per 8
+                    uint32_t d = 3, nk = 0;
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        if (d >= 3) {
+#pragma unroll
+                            for (int i = 0; i < 8; i++) {
+                                d = sm.step[p];
+                                sm.plist[c * 8 + i] = p;
+                                if (d >= 3) p += d;
+                            }
+                            nk = c * 8 + 8;
+                        }
+                    }
+                    __syncwarp();
+                    const uint32_t dm = lane < nk ? sm.step[sm.plist[lane]] : 0u;
+                    cnt = __popc(__ballot_sync(LZF_FULL_MASK, dm >= 3));        // a prefix of the lanes
+                    // the rest of the step: sequences with single-byte length extensions mixed with plain ones
+                    bool medium = false;
+#pragma unroll 4
+                    for (uint32_t k = cnt; k < 32; k++) {
                         uint32_t d = sm.step[p];
                         if (d < 3) {                                  // 0: stop; 1: a token with length extensions
                             if (d == 0) break;
                             d = medium_size(sm, p, wend);
                             if (d == 0) break;
+                            medium = true;
                         }
                         sm.plist[k] = p;
                         p += d;
                         cnt = k + 1;
                     }
+                    plain_mode = !medium;
+                } else {
+                    // streams that mix in length extensions (text): one loop that takes both kinds
+                    bool medium = false;
+#pragma unroll 8
+                    for (int k = 0; k < 32; k++) {
+                        uint32_t d = sm.step[p];
+                        if (d < 3) {
+                            if (d == 0) break;
+                            d = medium_size(sm, p, wend);
+                            if (d == 0) break;
+                            medium = true;
+                        }
+                        sm.plist[k] = p;
+                        p += d;
+                        cnt = k + 1;
+                    }
+                    plain_mode = !medium;
                 }
                 __syncwarp();
                 const uint32_t my_p = sm.plist[lane];
@@ -407,12 +447,20 @@ decode_blocks_kernel(DecodeArgs a) {
                 const uint32_t out_end = __shfl_sync(LZF_FULL_MASK, o_k + tot, cnt - 1);
 
                 // ---- literals: every lane copies its own run into the staging ring
-                if (act && lit <= kLaneCopyMax) {
+                {
+                    // trip counts follow the longest run / match of the step (warp-uniform), four bytes per check
+                    const uint32_t mylit = (act && lit <= kLaneCopyMax) ? lit : 0u;
+                    const uint32_t maxlit = warp_max_u32(mylit);
                     const uint8_t* src = sm.win + lit_src;
                     uint8_t* d = sm.stage + (o_k - sbias);
 #pragma unroll
-                    for (uint32_t i = 0; i < kLaneCopyMax; i++) if (i < lit) d[i] = src[i];
+                    for (uint32_t c = 0; c < kLaneCopyMax; c += 4) {
+                        if (c >= maxlit) break;
+#pragma unroll
+                        for (uint32_t i = c; i < c + 4; i++) if (i < mylit) d[i] = src[i];
+                    }
                 }
+                const uint32_t maxml = warp_max_u32((act && ml <= kLaneCopyMax) ? ml : 0u);
                 for (uint32_t lm = __ballot_sync(LZF_FULL_MASK, act && lit > kLaneCopyMax); lm; lm &= lm - 1) {
                     const uint32_t k = __ffs(lm) - 1;                           // a long run: the whole warp copies it
                     const uint32_t n = __shfl_sync(LZF_FULL_MASK, lit, k);
@@ -456,8 +504,24 @@ decode_blocks_kernel(DecodeArgs a) {
                             for (uint32_t i = 0; i < ml; i++) d[i] = sp[i];
                         } else if (srcp >= 0 && srcp + (int64_t)ml <= (int64_t)flushed) {
                             const uint8_t* g = s.out + srcp;                      // flushed history -> staged
+                            // loads first, then stores: one round trip for matches up to 12 bytes, two beyond
+                            uint8_t v[12];
 #pragma unroll
-                            for (uint32_t i = 0; i < kLaneCopyMax; i++) if (i < ml) d[i] = g[i];
+                            for (uint32_t c = 0; c < 12; c += 4) {
+                                if (c >= maxml) break;
+#pragma unroll
+                                for (uint32_t i = c; i < c + 4; i++) if (i < ml) v[i] = g[i];
+                            }
+#pragma unroll
+                            for (uint32_t c = 0; c < 12; c += 4) {
+                                if (c >= maxml) break;
+#pragma unroll
+                                for (uint32_t i = c; i < c + 4; i++) if (i < ml) d[i] = v[i];
+                            }
+                            if (maxml > 12) {
+#pragma unroll
+                                for (uint32_t i = 12; i < kLaneCopyMax; i++) if (i < ml) d[i] = g[i];
+                            }
                         } else {
                             for (uint32_t i = 0; i < ml; i++) {                   // straddles the flush point or the prefix
                                 const int64_t x = srcp + i;

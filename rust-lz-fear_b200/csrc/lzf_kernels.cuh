@@ -79,7 +79,7 @@ struct WalkArgs {
 
 extern "C" {
 int lzf_launch_encode(const lzf::EncodeArgs* args, int num_sms, cudaStream_t stream);
-size_t lzf_encode_global_table_warps(int num_sms);
+size_t lzf_encode_global_table_bytes(const lzf::EncodeArgs* args, int num_sms);
 int lzf_launch_decode(const lzf::DecodeArgs* args, int num_sms, cudaStream_t stream);
 int lzf_launch_xxh32_ranges(const uint8_t* data, const uint64_t* off, const uint64_t* len, uint32_t nranges,
                             uint32_t* hash, cudaStream_t s);

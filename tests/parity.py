@@ -61,7 +61,7 @@ def mutate(blob, seed, k=1):
     return bytes(a)
 
 
-def check_batched_blocks(backend, oracle, inputs, use_torch_device=None):
+def check_batched_blocks(backend, oracle, inputs, use_torch_device=None, max_block_len=0):
     """lzf_compress_blocks + lzf_decompress_blocks with (emulated or real) device buffers."""
     import torch
     dev = use_torch_device or "cpu"
@@ -80,7 +80,7 @@ def check_batched_blocks(backend, oracle, inputs, use_torch_device=None):
     d_st = torch.zeros(nb, dtype=torch.int32, device=dev)
     d_xp = torch.zeros(nb, dtype=torch.int32, device=dev)
     d_xs = torch.zeros(nb, dtype=torch.int32, device=dev)
-    backend.ctx.compress_blocks(d_in, d_off, d_len, nb, d_out, d_off, None, d_olen, d_st, d_xp, d_xs)
+    backend.ctx.compress_blocks(d_in, d_off, d_len, nb, d_out, d_off, None, d_olen, d_st, d_xp, d_xs, max_block_len=max_block_len)
     if dev != "cpu":
         torch.cuda.synchronize()
     out = d_out.cpu().numpy(); olen = d_olen.cpu().numpy().view(np.uint32); st = d_st.cpu().numpy()

@@ -22,7 +22,7 @@ int simt_encode_blocks(const uint8_t* in, const uint64_t* in_off, const uint32_t
     uint32_t counter = 0;
     a.work_counter = &counter;
     a.max_block_len = max_block_len;
-    std::vector<uint8_t> gt(lzf_encode_global_table_warps(num_sms) * ((size_t)4 << 17));
+    std::vector<uint8_t> gt(lzf_encode_global_table_bytes(&a, num_sms) + 16);
     a.global_tables = gt.data();
     return lzf_launch_encode(&a, num_sms, nullptr);
 }

@@ -79,6 +79,20 @@ def test_batched_blocks(emu, oracle):
     parity.check_batched_blocks(emu, oracle, inputs)
 
 
+def test_batched_blocks_tables_in_global_scratch(emu, oracle, monkeypatch):
+    """max_block_len promise -> u16 / packed 17-bit slot tables in one big CTA per SM; with fewer shared-memory
+    tables than warps the remaining warps keep theirs in the global scratch (same bytes either way)."""
+    inputs = [b for b in parity.sample_inputs() if len(b) > 0]
+    small = [b for b in inputs if len(b) <= 65536]
+    for smem_warps in ("1", "0", None):
+        if smem_warps is None:
+            monkeypatch.delenv("LZF_B200_ENC_SMEM_WARPS", raising=False)
+        else:
+            monkeypatch.setenv("LZF_B200_ENC_SMEM_WARPS", smem_warps)
+        parity.check_batched_blocks(emu, oracle, inputs, max_block_len=max(len(b) for b in inputs))     # packed slots
+        parity.check_batched_blocks(emu, oracle, small, max_block_len=65536)                            # u16 slots
+
+
 def test_frames_roundtrip_and_bytes(emu, oracle):
     inputs = [b"", b"a", bytes(65536), parity.sample_inputs()[6], parity.sample_inputs()[7][:70001],
               parity.sample_inputs()[5] * 30]
