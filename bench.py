@@ -51,6 +51,9 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-xxh", action="store_true", help="experiment: skip the fused XXH32 epilogue")
     ap.add_argument("--gather", action="store_true", help="N > 1: also time the frame-granular NCCL gather of compressed frames to rank 0")
+    ap.add_argument("--extra", action="store_true", help="also run BASELINE configs 4 (mixed-entropy frames) and 5 (large hash tables)")
+    ap.add_argument("--mixed-gib", type=float, default=8.0, help="config-4 plaintext GiB per GPU (64 GiB over 8 GPUs)")
+    ap.add_argument("--lowent-gib", type=float, default=1.0, help="config-5 plaintext GiB")
     return ap.parse_args()
 
 
@@ -519,6 +522,98 @@ def main():
                                             "sample": "first %d config-3 blocks (%d MiB), best of 2, C port of lz-fear compress2, one block "
                                                       "per task; GPU output byte-identical on this sample" % (ns, ns * BLOCK3 >> 20)}
 
+    # =========================================================================================
+    # config 4 (mixed-entropy frames, this rank's shard) and config 5 (large hash tables) — opt-in
+    # =========================================================================================
+    extra = None
+    if args.extra:
+        extra = {}
+        torch.cuda.empty_cache()
+        # ---- config 4: block b's class = b mod 3 -> random (stored-block fallback) / text / lowent; frames of 16 x 4 MiB
+        nb4 = max(BLOCKS_PER_FRAME3, int(args.mixed_gib * GiB) // BLOCK3 // BLOCKS_PER_FRAME3 * BLOCKS_PER_FRAME3)
+        mixed = W.mixed_blocks(nb4, BLOCK3, seed=0x4C5A0004 + 1000003 * rank, device=dev)
+        nf4 = nb4 // BLOCKS_PER_FRAME3
+        fp4 = BLOCKS_PER_FRAME3 * BLOCK3
+        s4, _k4 = N.make_settings()
+        bound4 = ctx.frame_bound(s4, fp4)
+        fr4 = torch.empty(nf4 * bound4, dtype=torch.uint8, device=dev)
+        fi_off = np.arange(nf4, dtype=np.uint64) * fp4
+        fi_len = np.full(nf4, fp4, np.uint64)
+        fo_off = np.arange(nf4, dtype=np.uint64) * bound4
+        fo_cap = np.full(nf4, bound4, np.uint64)
+        back4 = torch.empty_like(mixed)
+
+        def c4_compress():
+            return ctx.frames_compress_device(mixed, fi_off, fi_len, fr4, fo_off, fo_cap, s4)
+
+        def c4_decompress(fl):
+            return ctx.frames_decompress_device(fr4, fo_off, fl, back4, fi_off, fi_len)
+
+        for _ in range(2):
+            fl4, fs4 = c4_compress()
+            ol4, ds4, _d = c4_decompress(fl4)
+        assert not fs4.any() and not ds4.any() and (ol4 == fp4).all() and torch.equal(back4, mixed), "config 4 round trip failed"
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            c4_compress()                    # synchronous: returns once the frames are assembled
+        torch.cuda.synchronize()
+        tc = time.perf_counter() - t0
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            c4_decompress(fl4)
+        torch.cuda.synchronize()
+        td = time.perf_counter() - t0
+        barrier()
+        tc, td = max_over_ranks(tc), max_over_ranks(td)
+        tot4 = sum_over_ranks(nb4 * BLOCK3)
+        extra["config4"] = {
+            "workload": "mixed-entropy frames (block class = b mod 3: random / text / lowent), %d frames of 16 x 4 MiB per GPU, "
+                        "default CompressionSettings, device-resident, whole frame calls (walk/encode/layout/assemble, content checksums)" % nf4,
+            "compress_GiB_per_s": tot4 * K / GiB / tc, "decompress_GiB_per_s": tot4 * K / GiB / td,
+            "ratio": float(nb4 * BLOCK3) / float(fl4.sum()), "n_gpus": world,
+            "timing": "host clock around K synchronous frame calls, max over ranks", "roundtrip": "bit-exact on the device"}
+        del mixed, fr4, back4
+        torch.cuda.empty_cache()
+        # ---- config 5: low-entropy blocks, HASHLOG 12 (reference) / 14 / 16 (extension): sizes vs the oracle at the same HASHLOG
+        if rank == 0:
+            import oracle
+            nb5 = max(1, int(args.lowent_gib * GiB) // BLOCK3)
+            low = torch.cat([W.lowent(BLOCK3, 0x4C5A0005 + b, device=dev) for b in range(nb5)])
+            off5 = torch.arange(nb5, device=dev, dtype=torch.int64) * BLOCK3
+            len5 = torch.full((nb5,), BLOCK3, dtype=torch.int32, device=dev)
+            c5 = torch.empty(nb5 * BLOCK3, dtype=torch.uint8, device=dev)
+            cl5 = torch.zeros(nb5, dtype=torch.int32, device=dev)
+            cs5 = torch.zeros(nb5, dtype=torch.int32, device=dev)
+            back5 = torch.empty_like(low)
+            res5 = {}
+            sample = low[:2 * BLOCK3].cpu().numpy()
+            for hl in (12, 14, 16):
+                def run5():
+                    ctx.compress_blocks(low, off5, len5, nb5, c5, off5, None, cl5, cs5, None, None, hashlog=hl, stream=stream, max_block_len=BLOCK3)
+                for _ in range(2):
+                    run5()
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(K):
+                    run5()
+                e1.record()
+                torch.cuda.synchronize()
+                assert int(cs5.abs().sum().item()) == 0
+                ctx.decompress_blocks(c5, off5, cl5, nb5, back5, off5, len5, len5, torch.zeros_like(cl5), cs5, None, stream=stream)
+                torch.cuda.synchronize()
+                assert int(cs5.abs().sum().item()) == 0 and torch.equal(back5, low), "config 5 round trip failed"
+                got = cl5[:2].cpu().numpy().view(np.uint32)
+                want = [len(oracle.compress_block(sample[i * BLOCK3:(i + 1) * BLOCK3].tobytes(), hashlog=hl)[1]) for i in range(2)]
+                res5["hashlog%d" % hl] = {"compress_GiB_per_s": nb5 * BLOCK3 * K / GiB / (e0.elapsed_time(e1) / 1e3),
+                                          "ratio": float(nb5 * BLOCK3) / float(cl5.to(torch.int64).sum().item()),
+                                          "size_vs_oracle_same_hashlog": [int(a) - int(b) for a, b in zip(got, want)]}
+            extra["config5"] = {"workload": "%d x 4 MiB low-entropy blocks (4-symbol alphabet, runs U{1..64}); HASHLOG 12 is the reference's table, "
+                                            "14 / 16 are the large-table extension (parity against the oracle run with the same HASHLOG)" % nb5,
+                                "results": res5}
+            del low, c5, back5
+
     if rank == 0:
         line = {
             "metric": "LZ4 block decompress throughput (config 2: 64 KiB independent blocks, seq50)",
@@ -533,6 +628,8 @@ def main():
             "roofline": dec_roof, "cpu_baseline": cpu_dec, "e2e": dec_e2e, "gpu_launches": dec_launches,
             "clocks": clocks, "compress": comp_section,
         }
+        if extra is not None:
+            line["extra_configs"] = extra
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

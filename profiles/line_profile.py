@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def line_table(kernel_substr, cubin_substr):
     tmp = tempfile.mkdtemp()
-    subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "rust-lz-fear_b200", "liblzfear_b200.so")], cwd=tmp, capture_output=True)
+    subprocess.run(["cuobjdump", "-xelf", "all", os.environ.get("LZF_PROFILE_LIB") or os.path.join(ROOT, "rust-lz-fear_b200", "liblzfear_b200.so")], cwd=tmp, capture_output=True)
     cub = [f for f in os.listdir(tmp) if f.startswith(cubin_substr + ".")][0]
     dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout.splitlines()
     out, on, cur = {}, False, ("?", 0)

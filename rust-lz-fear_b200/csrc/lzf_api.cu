@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <functional>
 #include <mutex>
 #include <new>
 #include <string>
@@ -72,7 +73,9 @@ struct lzf_ctx {
     // warp owns one block, so the chunks in flight together must hold enough blocks to fill the GPU
     // (148 SMs x tens of warps): up to kSlots chunks run concurrently, one host thread + stream each.
     uint64_t chunk_bytes = 512ull << 20;            // decompress: compressed + plaintext bytes
-    uint64_t compress_chunk_bytes = 2ull << 30;     // compress: plaintext bytes (4 MiB blocks need many in flight)
+    // compress: plaintext bytes.  0 = one full wave of the block kernel (one warp per block, 28 warps per SM;
+    // the parse is latency-bound, so a chunk with fewer blocks takes just as long), at most 24 GiB
+    uint64_t compress_chunk_bytes = 0;
 };
 
 // slot of the calling thread: worker threads of the host-buffer pipelines bind their own, every other
@@ -694,6 +697,9 @@ int frames_compress_core(lzf_ctx* c, const lzf_settings* s, const uint8_t* d_in,
 struct DecodeOut {          // optional extra per-frame results
     uint64_t* consumed;     // nullable
     int32_t* detail;        // nullable
+    // host-buffer pipeline hook: called once the block kernel is queued on the stream (before the host
+    // waits for its results), so the D2H copy of the plaintext can start while the outcome is resolved
+    std::function<int()> after_decode;
 };
 
 int frames_decompress_core(lzf_ctx* c, const uint8_t* d_in, const uint64_t* in_off, const uint64_t* in_len,
@@ -844,6 +850,7 @@ int frames_decompress_core(lzf_ctx* c, const uint8_t* d_in, const uint64_t* in_o
                                     (const uint32_t*)(d + o_bcap), (const uint32_t*)(d + o_blim), (uint32_t*)(r + r_olen),
                                     (int32_t*)(r + r_bst), nullptr, st, use_hist, d_wait, d_done);
         if (rc) return rc;
+        if (extra.after_decode && (rc = extra.after_decode())) return rc;
         LZF_CU(c, cudaMemcpyAsync(hr + r_olen, r + r_olen, r_bxxh - r_olen, cudaMemcpyDeviceToHost, st));
         if (any_block_checksums) {
             LZF_CU(c, cudaMemcpyAsync(hr + r_bxxh, r + r_bxxh, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, st));
@@ -1146,7 +1153,13 @@ extern "C" int lzf_frames_compress(lzf_ctx* c, const lzf_settings* s, const uint
     if (nframes && (!in_off || !in_len || !out_off || !out_cap || !out_len || !status))
         return fail(c, LZF_ERR_INVALID_ARG, "null pointer");
     LZF_CU(c, cudaSetDevice(c->device));
-    const std::vector<uint32_t> chunks = plan_chunks(in_len, nframes, c->compress_chunk_bytes);
+    uint64_t target = c->compress_chunk_bytes;
+    if (target == 0) {
+        target = (uint64_t)c->num_sms * 28 * (s->block_size ? s->block_size : (4ull << 20));
+        if (target < (256ull << 20)) target = 256ull << 20;
+        if (target > (24ull << 30)) target = 24ull << 30;
+    }
+    const std::vector<uint32_t> chunks = plan_chunks(in_len, nframes, target);
     return run_chunks(c, (uint32_t)chunks.size() - 1, [&](uint32_t i, lzf_slot& sl) {
         return compress_chunk(c, sl, s, chunks[i], chunks[i + 1], in, in_off, in_len, out, out_off, out_cap, out_len, status);
     });
@@ -1167,7 +1180,7 @@ extern "C" int lzf_frames_decompress_device(lzf_ctx* c, const uint8_t* d_in, con
                                             const uint64_t* out_cap, uint64_t* out_len, int32_t* status, int32_t* detail) {
     if (!c) return LZF_ERR_INVALID_ARG;
     LZF_CU(c, cudaSetDevice(c->device));
-    DecodeOut ex{nullptr, detail};
+    DecodeOut ex{nullptr, detail, nullptr};
     return frames_decompress_core(c, d_in, in_off, in_len, nframes, d_out, out_off, out_cap, out_len, status, ex, cur_slot(c)->stream);
 }
 
@@ -1203,14 +1216,29 @@ int decompress_chunk(lzf_ctx* c, lzf_slot& sl, uint32_t f0, uint32_t f1, const u
         if ((rc = ensure_dev(c, sl.d_dict, dlen + 16))) return rc;
         LZF_CU(c, cudaMemcpyAsync(sl.d_dict.p, dict, dlen, cudaMemcpyHostToDevice, sl.stream));
     }
-    DecodeOut ex{consumed ? consumed + f0 : nullptr, detail ? detail + f0 : nullptr};
+    // The plaintext of a dense run of frames travels back as ONE copy that starts as soon as the block kernel
+    // has run, on the slot's side stream, while this thread resolves the per-frame outcome (and the content
+    // checksums run) on the main stream.  Whatever the resolution then finds irregular (short frames, errors,
+    // re-decoded frames) is copied again, frame by frame, after both streams have drained.
+    bool early_copy = false;
+    DecodeOut ex{consumed ? consumed + f0 : nullptr, detail ? detail + f0 : nullptr, nullptr};
+    if (lo.dense && lo.span) {
+        ex.after_decode = [&]() -> int {
+            LZF_CU(c, cudaEventRecord(sl.ev_fork, sl.stream));
+            LZF_CU(c, cudaStreamWaitEvent(sl.side, sl.ev_fork, 0));
+            LZF_CU(c, cudaMemcpyAsync(out + lo.base, dout, lo.span, cudaMemcpyDeviceToHost, sl.side));
+            early_copy = true;
+            return LZF_SUCCESS;
+        };
+    }
     rc = frames_decompress_core(c, din, li.dev_off.data(), in_len + f0, n, (uint8_t*)sl.d_io_out.p, lo.dev_off.data(),
                                 dcap.data(), out_len + f0, status + f0, ex, sl.stream, dlen ? (const uint8_t*)sl.d_dict.p : nullptr, dlen);
+    if (early_copy) LZF_CU(c, cudaStreamSynchronize(sl.side));
     if (rc) return rc;
     bool full = lo.dense;      // every frame filled its capacity exactly: one copy moves the whole run
     for (uint32_t f = f0; f < f1 && full; f++) full = out_len[f] == dcap[f - f0];
     if (full) {
-        if (lo.span) LZF_CU(c, cudaMemcpyAsync(out + lo.base, dout, lo.span, cudaMemcpyDeviceToHost, sl.stream));
+        if (lo.span && !early_copy) LZF_CU(c, cudaMemcpyAsync(out + lo.base, dout, lo.span, cudaMemcpyDeviceToHost, sl.stream));
     } else {
         for (uint32_t f = f0; f < f1; f++)
             if (out_len[f])

@@ -169,9 +169,13 @@ constexpr uint32_t kPacked17MaxLen = 16u << 20;
 constexpr int kEncodeWarpsPerCta = LZF_ENC_WARPS;
 // The parse is one long dependent chain per warp (~8 cycles per instruction, ncu r01_ncu_encode_v5), so
 // throughput is resident warps x chain speed.  Tables of <= 8.5 KiB (u16 / packed 17-bit slots) therefore
-// run ONE CTA of kEncodeBigWarps warps per SM at <= 72 registers; as many tables as fit live in shared
-// memory (26 packed ones in 227 KiB), the remaining warps keep theirs in an L2-resident global scratch.
+// run ONE CTA of kEncodeBigWarps warps per SM at <= 72 registers (4096 blocks of config 3 = one wave on 148
+// SMs).  Half of the warps keep their table in shared memory, the other half in an L2-resident global
+// scratch read through L1: measured on B200 (config 3, GiB/s) 13 shared + 15 global 32.2, all global 31.6,
+// 26 shared + 2 global 29.6 (a 227 KiB carve-out leaves almost no L1 for the input and candidate loads),
+// 32 warps 30.2, 16 warps (two waves) 22.8.
 constexpr int kEncodeBigWarps = LZF_ENC_BIG_WARPS;
+constexpr int kEncodeSmemWarpsMax = kEncodeBigWarps / 2 - 1;
 constexpr int kGlobalTableCtasPerSm = 4;   // bounds the global table scratch (CTAs of kEncodeWarpsPerCta warps)
 constexpr size_t kSmemPerCtaMax = 227 * 1024;   // sm_100a opt-in maximum per CTA
 
@@ -644,6 +648,7 @@ static EncodePlan plan_encode(const EncodeArgs* args) {
         // one big CTA per SM; whatever does not fit shared memory goes to the global scratch
         p.warps = kEncodeBigWarps;
         int fit = (int)(smem_budget / p.table_bytes);
+        if (fit > kEncodeSmemWarpsMax) fit = kEncodeSmemWarpsMax;
         if (const char* e = getenv("LZF_B200_ENC_SMEM_WARPS")) {      // test / tuning knob: fewer shared-memory tables
             const int v = atoi(e);
             if (v >= 0 && v < fit) fit = v;

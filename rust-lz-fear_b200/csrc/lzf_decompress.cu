@@ -309,7 +309,6 @@ decode_blocks_kernel(DecodeArgs a) {
             // the fast path works in 32-bit output positions and never exceeds this bound
             const uint64_t bound64 = s.cap < s.limit ? s.cap : s.limit;
             const uint32_t bound = bound64 > 0xfffff000ull ? 0xfffff000u : (uint32_t)bound64;
-            bool plain_mode = true;   // the walk flavour follows the stream: plain sequences only / mixed with length extensions
 
             while (s.pos < s.n && s.status == LZF_OK && !s.finished) {
                 const uint64_t q = q0 + s.pos;
@@ -342,10 +341,12 @@ decode_blocks_kernel(DecodeArgs a) {
                 // length extensions are single bytes).  This is the only serial part of the decoder: one
                 // shared-memory byte per plain sequence.
                 uint32_t cnt = 0;
-                if (plain_mode) {
+                {
                     // plain prefix, branch-free: a position that is not a plain sequence (step < 3) does not advance
                     // p, so the walk sticks there and every later slot repeats it; four instructions per sequence
-                    // (LDS, STS, ISETP, predicated IADD) and one uniform branch per 8
+                    // (LDS, STS, ISETP, predicated IADD) and one uniform branch per 8.  (Measured on B200: 338 ->
+                    // 371 GiB/s on config 2 against the loop that tests every step; choosing between the two loops
+                    // per step cost more than it gave back on text, 311 / 106 GiB/s.)
                     uint32_t d = 3, nk = 0;
 #pragma unroll
                     for (int c = 0; c < 4; c++) {
@@ -363,38 +364,18 @@ decode_blocks_kernel(DecodeArgs a) {
                     const uint32_t dm = lane < nk ? sm.step[sm.plist[lane]] : 0u;
                     cnt = __popc(__ballot_sync(LZF_FULL_MASK, dm >= 3));        // a prefix of the lanes
                     // the rest of the step: sequences with single-byte length extensions mixed with plain ones
-                    bool medium = false;
-#pragma unroll 4
+#pragma unroll 1
                     for (uint32_t k = cnt; k < 32; k++) {
                         uint32_t d = sm.step[p];
                         if (d < 3) {                                  // 0: stop; 1: a token with length extensions
                             if (d == 0) break;
                             d = medium_size(sm, p, wend);
                             if (d == 0) break;
-                            medium = true;
                         }
                         sm.plist[k] = p;
                         p += d;
                         cnt = k + 1;
                     }
-                    plain_mode = !medium;
-                } else {
-                    // streams that mix in length extensions (text): one loop that takes both kinds
-                    bool medium = false;
-#pragma unroll 8
-                    for (int k = 0; k < 32; k++) {
-                        uint32_t d = sm.step[p];
-                        if (d < 3) {
-                            if (d == 0) break;
-                            d = medium_size(sm, p, wend);
-                            if (d == 0) break;
-                            medium = true;
-                        }
-                        sm.plist[k] = p;
-                        p += d;
-                        cnt = k + 1;
-                    }
-                    plain_mode = !medium;
                 }
                 __syncwarp();
                 const uint32_t my_p = sm.plist[lane];
