@@ -438,7 +438,7 @@ def main():
             import psutil
             avail = psutil.virtual_memory().available
             e2e_blocks = nb3
-            while e2e_blocks > BLOCKS_PER_FRAME3 and e2e_blocks * BLOCK3 * 2.2 > avail * 0.5:
+            while e2e_blocks > BLOCKS_PER_FRAME3 and e2e_blocks * BLOCK3 * 2.2 > avail * 0.5 / world:   # every rank pins its own
                 e2e_blocks //= 2
             e2e_blocks = e2e_blocks // BLOCKS_PER_FRAME3 * BLOCKS_PER_FRAME3
             nf3 = e2e_blocks // BLOCKS_PER_FRAME3

@@ -51,7 +51,9 @@ using lzf::Buf;
 struct lzf_slot {
     cudaStream_t stream = nullptr;      // copies + kernels of this slot
     cudaStream_t side = nullptr;        // content-checksum chain, overlapped with the block kernels
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t copy = nullptr;        // sliced H2D feed of the host-buffer compress pipeline
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_feed0 = nullptr, ev_feed1 = nullptr;
+    uint32_t* h_seq = nullptr;          // pinned 1, 2, 3, ...: sources of the progress-word copies
     uint32_t* d_counter = nullptr;      // dynamic work counters (encode, decode)
     Buf d_tables;                       // per-warp global hash tables (hashlog >= 14)
     Buf d_desc, h_desc;                 // descriptor arenas (device / pinned host)
@@ -61,6 +63,7 @@ struct lzf_slot {
     Buf d_dict, d_aux;                  // dictionary copy / dependent-block descriptors and window scratch
 };
 constexpr int kSlots = 4;
+constexpr uint32_t kMaxSlices = 256;
 
 struct lzf_ctx {
     int device = 0;
@@ -153,8 +156,14 @@ extern "C" int lzf_create(int device, lzf_ctx** out) {
              cudaStreamCreateWithFlags(&sl.side, cudaStreamNonBlocking) == cudaSuccess &&
              cudaEventCreateWithFlags(&sl.ev_fork, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&sl.ev_join, cudaEventDisableTiming) == cudaSuccess &&
+             cudaStreamCreateWithFlags(&sl.copy, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&sl.ev_feed0, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&sl.ev_feed1, cudaEventDisableTiming) == cudaSuccess &&
+             cudaMallocHost((void**)&sl.h_seq, kMaxSlices * sizeof(uint32_t)) == cudaSuccess &&
              cudaMalloc((void**)&sl.d_counter, 256) == cudaSuccess;
     }
+    for (int i = 0; i < kSlots && ok; i++)
+        for (uint32_t k = 0; k < kMaxSlices; k++) c->slots[i].h_seq[k] = k + 1;
     if (const char* e = getenv("LZF_B200_CHUNK_BYTES")) {       // tuning / test knob
         const unsigned long long v = strtoull(e, nullptr, 10);
         if (v) c->chunk_bytes = c->compress_chunk_bytes = v;
@@ -171,6 +180,10 @@ extern "C" void lzf_destroy(lzf_ctx* c) {
         lzf_slot& sl = c->slots[i];
         if (sl.stream) cudaStreamSynchronize(sl.stream);
         if (sl.side) cudaStreamSynchronize(sl.side);
+        if (sl.copy) { cudaStreamSynchronize(sl.copy); cudaStreamDestroy(sl.copy); }
+        if (sl.ev_feed0) cudaEventDestroy(sl.ev_feed0);
+        if (sl.ev_feed1) cudaEventDestroy(sl.ev_feed1);
+        if (sl.h_seq) cudaFreeHost(sl.h_seq);
         Buf* dev[] = {&sl.d_tables, &sl.d_desc, &sl.d_res, &sl.d_comp, &sl.d_io_in, &sl.d_io_out, &sl.d_dict, &sl.d_aux};
         for (Buf* b : dev) if (b->p) cudaFree(b->p);
         Buf* host[] = {&sl.h_desc, &sl.h_res};
@@ -193,11 +206,22 @@ extern "C" size_t lzf_compress_bound(size_t n) { return n + n / 255 + 16; }
 // ------------------------------------------------------------------------------------------------
 namespace {
 
+// Host-buffer pipeline: the plaintext is still being copied in (slice k of every block, then slice k + 1, ...) on
+// another stream while the block kernel runs; see EncodeArgs::progress.
+struct InputFeed {
+    const uint32_t* d_progress; uint32_t slice_bytes;
+    cudaEvent_t ready;      // recorded behind the last slice
+    // queues the slice copies.  Called right before the block kernel is launched, after every other host->device
+    // copy and memset of the call has been queued: the copy engine works first-in first-out across streams, so
+    // anything queued behind 16 GiB of slices would hold the kernel launch back until the feed is over
+    std::function<int()> start;
+};
+
 int compress_blocks_impl(lzf_ctx* c, const uint8_t* d_in, const uint64_t* d_in_off, const uint32_t* d_in_len,
                          uint32_t nblocks, uint32_t hashlog, uint32_t table_kind, uint32_t max_block_len,
                          uint8_t* d_out, const uint64_t* d_out_off, const uint32_t* d_out_cap,
                          uint32_t* d_out_len, int32_t* d_status, uint32_t* d_xxh_plain, uint32_t* d_xxh_stored,
-                         cudaStream_t s, const lzf::EncodeArgs* chains = nullptr) {
+                         cudaStream_t s, const lzf::EncodeArgs* chains = nullptr, const InputFeed* feed = nullptr) {
     if (hashlog == 0) hashlog = 12;
     if (hashlog < 8 || hashlog > 16) return fail(c, LZF_ERR_INVALID_ARG, "hashlog must be 0 or 8..16");
     if (table_kind != LZF_TABLE_U32 && table_kind != LZF_TABLE_U16) return fail(c, LZF_ERR_INVALID_ARG, "table_kind");
@@ -223,6 +247,11 @@ int compress_blocks_impl(lzf_ctx* c, const uint8_t* d_in, const uint64_t* d_in_o
         a.global_tables = (uint8_t*)cur_slot(c)->d_tables.p;
     }
     LZF_CU(c, cudaMemsetAsync(cur_slot(c)->d_counter, 0, 4, s));
+    if (feed) {
+        const int rc = feed->start();
+        if (rc) return rc;
+        a.progress = feed->d_progress; a.slice_bytes = feed->slice_bytes;
+    }
     LZF_LAUNCHED(c, lzf_launch_encode(&a, c->num_sms, s), 1);
     return LZF_SUCCESS;
 }
@@ -498,7 +527,8 @@ int build_header(const lzf_settings* s, uint64_t content_size, uint8_t* hdr, uin
 // ------------------------------------------------------------------------------------------------
 int frames_compress_core(lzf_ctx* c, const lzf_settings* s, const uint8_t* d_in, const uint64_t* in_off,
                          const uint64_t* in_len, uint32_t nframes, uint8_t* d_out, const uint64_t* out_off,
-                         const uint64_t* out_cap, uint64_t* out_len, int32_t* status, cudaStream_t st) {
+                         const uint64_t* out_cap, uint64_t* out_len, int32_t* status, cudaStream_t st,
+                         const InputFeed* feed = nullptr) {
     if (!s || (nframes && (!in_off || !in_len || !out_off || !out_cap || !out_len || !status)))
         return fail(c, LZF_ERR_INVALID_ARG, "null pointer");
     for (uint32_t f = 0; f < nframes; f++) { out_len[f] = 0; status[f] = LZF_F_OK; }
@@ -627,14 +657,9 @@ int frames_compress_core(lzf_ctx* c, const lzf_settings* s, const uint8_t* d_in,
     }
 
     LZF_CU(c, cudaMemcpyAsync(d, h, da.used, cudaMemcpyHostToDevice, st));
-    // content checksum of each frame's plaintext (compress.rs:172,233-235,279-281) on the side stream
-    if (s->content_checksum) {
-        LZF_CU(c, cudaEventRecord(cur_slot(c)->ev_fork, st));
-        LZF_CU(c, cudaStreamWaitEvent(cur_slot(c)->side, cur_slot(c)->ev_fork, 0));
-        LZF_LAUNCHED(c, lzf_launch_xxh32_ranges(d_in, (const uint64_t*)(d + o_hoff), (const uint64_t*)(d + o_hlen), nframes,
-                                               (uint32_t*)(r + r_chash), cur_slot(c)->side), 1);
-        LZF_CU(c, cudaEventRecord(cur_slot(c)->ev_join, cur_slot(c)->side));
-    }
+    if (s->content_checksum) LZF_CU(c, cudaEventRecord(cur_slot(c)->ev_fork, st));
+    const bool fed = feed && !chained && nblocks;       // the slice feed only serves independent blocks without history
+    if (feed && !fed) { if ((rc = feed->start())) return rc; LZF_CU(c, cudaStreamWaitEvent(st, feed->ready, 0)); }
     if (nblocks) {
         lzf::EncodeArgs ch;
         memset(&ch, 0, sizeof(ch));
@@ -654,8 +679,18 @@ int frames_compress_core(lzf_ctx* c, const lzf_settings* s, const uint8_t* d_in,
         rc = compress_blocks_impl(c, enc_base, (const uint64_t*)(d + o_bin_off), (const uint32_t*)(d + o_bin_len), nblocks,
                                   hashlog, LZF_TABLE_U32, max_block_len, (uint8_t*)cur_slot(c)->d_comp.p,
                                   (const uint64_t*)(d + o_bc_off), nullptr, (uint32_t*)(r + r_clen), (int32_t*)(r + r_bst),
-                                  nullptr, s->block_checksums ? (uint32_t*)(r + r_xs) : nullptr, st, chained ? &ch : nullptr);
+                                  nullptr, s->block_checksums ? (uint32_t*)(r + r_xs) : nullptr, st,
+                                  chained ? &ch : nullptr, fed ? feed : nullptr);
         if (rc) return rc;
+        if (fed) LZF_CU(c, cudaStreamWaitEvent(st, feed->ready, 0));      // stored blocks are copied from the plaintext
+    }
+    // content checksum of each frame's plaintext (compress.rs:172,233-235,279-281) on the side stream
+    if (s->content_checksum) {
+        LZF_CU(c, cudaStreamWaitEvent(cur_slot(c)->side, cur_slot(c)->ev_fork, 0));
+        if (fed) LZF_CU(c, cudaStreamWaitEvent(cur_slot(c)->side, feed->ready, 0));       // the whole plaintext
+        LZF_LAUNCHED(c, lzf_launch_xxh32_ranges(d_in, (const uint64_t*)(d + o_hoff), (const uint64_t*)(d + o_hlen), nframes,
+                                               (uint32_t*)(r + r_chash), cur_slot(c)->side), 1);
+        LZF_CU(c, cudaEventRecord(cur_slot(c)->ev_join, cur_slot(c)->side));
     }
     if (s->content_checksum) LZF_CU(c, cudaStreamWaitEvent(st, cur_slot(c)->ev_join, 0));
     lzf::LayoutArgs la;
@@ -1126,7 +1161,33 @@ int compress_chunk(lzf_ctx* c, lzf_slot& sl, const lzf_settings* s, uint32_t f0,
     if ((rc = ensure_dev(c, sl.d_io_out, lo.span + 256))) return rc;
     uint8_t* din = (uint8_t*)sl.d_io_in.p;
     const uint8_t* dout = (const uint8_t*)sl.d_io_out.p;
-    if (li.dense) {
+    // One warp parses one block at its own (latency-bound) pace, far below PCIe speed, so a chunk of large
+    // independent blocks is fed while the kernel already runs: slice k of EVERY block travels before slice k + 1
+    // of any (one strided copy per slice), followed by a 4-byte copy that bumps the progress word the warps poll.
+    const uint64_t bs = s->block_size;
+    uint64_t slice = 256 << 10, min_blocks = 64;
+    if (const char* e = getenv("LZF_B200_FEED_SLICE")) slice = strtoull(e, nullptr, 10);       // tuning / test knobs; 0 = off
+    if (const char* e = getenv("LZF_B200_FEED_MIN_BLOCKS")) min_blocks = strtoull(e, nullptr, 10);
+    bool sliced = li.dense && s->independent_blocks && !(s->dictionary && s->dictionary_len) && slice >= 4096 &&
+                  bs >= 4 * slice && bs % slice == 0 && bs / slice <= kMaxSlices && li.span >= min_blocks * bs;
+    for (uint32_t f = 0; f < n && sliced; f++) sliced = in_len[f0 + f] % bs == 0;
+    InputFeed feed{nullptr, 0, nullptr, nullptr};
+    if (sliced) {
+        uint32_t* d_progress = sl.d_counter + 32;
+        feed.d_progress = d_progress; feed.slice_bytes = (uint32_t)slice; feed.ready = sl.ev_feed1;
+        feed.start = [&, d_progress]() -> int {
+            const uint64_t rows = li.span / bs;
+            LZF_CU(c, cudaMemsetAsync(d_progress, 0, 4, sl.stream));
+            LZF_CU(c, cudaEventRecord(sl.ev_feed0, sl.stream));
+            LZF_CU(c, cudaStreamWaitEvent(sl.copy, sl.ev_feed0, 0));
+            for (uint64_t k = 0; k < bs / slice; k++) {
+                LZF_CU(c, cudaMemcpy2DAsync(din + k * slice, bs, in + li.base + k * slice, bs, slice, rows, cudaMemcpyHostToDevice, sl.copy));
+                LZF_CU(c, cudaMemcpyAsync(d_progress, sl.h_seq + k, 4, cudaMemcpyHostToDevice, sl.copy));
+            }
+            LZF_CU(c, cudaEventRecord(sl.ev_feed1, sl.copy));
+            return LZF_SUCCESS;
+        };
+    } else if (li.dense) {
         if (li.span) LZF_CU(c, cudaMemcpyAsync(din, in + li.base, li.span, cudaMemcpyHostToDevice, sl.stream));
     } else {
         for (uint32_t f = 0; f < n; f++)
@@ -1134,7 +1195,8 @@ int compress_chunk(lzf_ctx* c, lzf_slot& sl, const lzf_settings* s, uint32_t f0,
                 LZF_CU(c, cudaMemcpyAsync(din + li.dev_off[f], in + in_off[f0 + f], in_len[f0 + f], cudaMemcpyHostToDevice, sl.stream));
     }
     rc = frames_compress_core(c, s, din, li.dev_off.data(), in_len + f0, n, (uint8_t*)sl.d_io_out.p, lo.dev_off.data(),
-                              dcap.data(), out_len + f0, status + f0, sl.stream);
+                              dcap.data(), out_len + f0, status + f0, sl.stream, sliced ? &feed : nullptr);
+    if (sliced) cudaStreamSynchronize(sl.copy);
     if (rc) return rc;
     // compressed frames are much shorter than their capacity: copy each frame's bytes
     for (uint32_t f = f0; f < f1; f++)

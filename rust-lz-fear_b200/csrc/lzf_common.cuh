@@ -127,28 +127,11 @@ __device__ __forceinline__ uint32_t warp_xxh32(const uint8_t* p, size_t n) {
 // accumulator chains of one range are inherently serial, so a single range can only ever keep
 // 4 lanes busy; packing 8 independent ranges (blocks / frames) into one warp fills all 32.
 // Returns the hash of range j in all four lanes of group j.
-__device__ __forceinline__ uint32_t warp_xxh32_x8(const uint8_t* p, uint64_t n) {
+// Tail and avalanche of warp_xxh32_x8: `acc` = accumulator a of range j after all 16-byte stripes.
+__device__ __forceinline__ uint32_t warp_xxh32_x8_finish(uint32_t acc, const uint8_t* p, uint64_t n) {
     const unsigned lane = lane_id();
     const unsigned a = lane & 3u;
     const uint64_t nstripes = n >> 4;
-    uint32_t acc = xxh32_seed_acc(a);
-    {
-        const uint8_t* q = p + 4 * a;
-        uint64_t s = 0;
-        if ((reinterpret_cast<uintptr_t>(p) & 3u) == 0) {
-            const uint32_t* qw = reinterpret_cast<const uint32_t*>(q);
-            for (; s + 8 <= nstripes; s += 8) {
-                uint32_t x[8];
-#pragma unroll
-                for (int i = 0; i < 8; i++) x[i] = qw[(s + i) * 4];
-#pragma unroll
-                for (int i = 0; i < 8; i++) acc = xxh_round(acc, x[i]);
-            }
-            for (; s < nstripes; s++) acc = xxh_round(acc, qw[s * 4]);
-        } else {
-            for (; s < nstripes; s++) acc = xxh_round(acc, ld_u32_unaligned(q + s * 16));
-        }
-    }
     const unsigned g = lane & ~3u;
     const uint32_t a0 = __shfl_sync(LZF_FULL_MASK, acc, g);
     const uint32_t a1 = __shfl_sync(LZF_FULL_MASK, acc, g + 1);
@@ -174,6 +157,31 @@ __device__ __forceinline__ uint32_t warp_xxh32_x8(const uint8_t* p, uint64_t n) 
     return __shfl_sync(LZF_FULL_MASK, h, g);
 }
 
+__device__ __forceinline__ uint32_t warp_xxh32_x8(const uint8_t* p, uint64_t n) {
+    const unsigned lane = lane_id();
+    const unsigned a = lane & 3u;
+    const uint64_t nstripes = n >> 4;
+    uint32_t acc = xxh32_seed_acc(a);
+    {
+        const uint8_t* q = p + 4 * a;
+        uint64_t s = 0;
+        if ((reinterpret_cast<uintptr_t>(p) & 3u) == 0) {
+            const uint32_t* qw = reinterpret_cast<const uint32_t*>(q);
+            for (; s + 8 <= nstripes; s += 8) {
+                uint32_t x[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) x[i] = qw[(s + i) * 4];
+#pragma unroll
+                for (int i = 0; i < 8; i++) acc = xxh_round(acc, x[i]);
+            }
+            for (; s < nstripes; s++) acc = xxh_round(acc, qw[s * 4]);
+        } else {
+            for (; s < nstripes; s++) acc = xxh_round(acc, ld_u32_unaligned(q + s * 16));
+        }
+    }
+    return warp_xxh32_x8_finish(acc, p, n);
+}
+
 // ---- per-CTA queue of finished blocks whose XXH32 is still owed -------------------------------
 // A warp that finishes a block pushes (pointer, length, destination slot); the warp that pushes
 // the 8th entry of a group hashes the whole group with warp_xxh32_x8; the last warp to leave the
@@ -181,6 +189,7 @@ __device__ __forceinline__ uint32_t warp_xxh32_x8(const uint8_t* p, uint64_t n) 
 #ifdef LZF_SIMT_EMU
 __device__ __forceinline__ void spin_pause() { simt::yield(); }
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) { return *(const volatile uint32_t*)p; }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) { return *(const volatile uint32_t*)p; }
 __device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) { *(volatile uint32_t*)p = v; }
 #else
 __device__ __forceinline__ void spin_pause() { __nanosleep(32); }
@@ -192,6 +201,12 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
 }
 __device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// system-scope acquire: the writer is the copy engine (a host-issued cudaMemcpyAsync on another stream)
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 #endif
 
@@ -298,6 +313,24 @@ __device__ __forceinline__ void warp_copy(uint8_t* __restrict__ dst, const uint8
     const unsigned tail = (unsigned)(n - done);
     if (lane < tail) dst[done + lane] = src[done + lane];
 }
+
+// ---- shared memory addressed by its 32-bit offset ---------------------------------------------
+// A chain of dependent shared-memory loads (the decoder's token walk) wants ONE register that is both the loop
+// variable and the load address.  `base` = the CTA's dynamic shared memory; offsets are relative to it in the
+// CPU test harness and are shared-window addresses on the device.
+#ifndef LZF_SIMT_EMU
+__device__ __forceinline__ uint32_t smem_off(const uint8_t*, const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int kImm>
+__device__ __forceinline__ uint32_t lds_u8(const uint8_t*, uint32_t off) {      // byte at off + kImm
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(off), "n"(kImm) : "memory");
+    return v;
+}
+#else
+__device__ __forceinline__ uint32_t smem_off(const uint8_t* base, const void* p) { return (uint32_t)((const uint8_t*)p - base); }
+template <int kImm>
+__device__ __forceinline__ uint32_t lds_u8(const uint8_t* base, uint32_t off) { return base[off + kImm]; }
+#endif
 
 // ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers ------------------------------
 // One elected lane arms the barrier with the byte count and issues the copy; every lane of the

@@ -82,6 +82,16 @@ __device__ __forceinline__ uint32_t ld4(const uint8_t* in, uint32_t pos) {
     return __funnelshift_r(lo, __ldg(w + 1), sh);
 }
 
+// Host-buffer pipeline: blocks until bytes [0, need) of the block have arrived (EncodeArgs::progress); returns
+// the arrived byte count (saturated).  Warp-uniform.
+__device__ __forceinline__ uint32_t wait_arrival(const uint32_t* progress, uint32_t slice_bytes, uint32_t need) {
+    for (;;) {
+        const uint64_t bytes = (uint64_t)ld_acquire_sys(progress) * slice_bytes;
+        if (bytes >= need) return bytes > 0xffffffffull ? 0xffffffffu : (uint32_t)bytes;
+        spin_pause();
+    }
+}
+
 // One LZ4 sequence (write_group :150-163, or the literal-only tail :182-189 when `final`).
 // Returns false when the bounded writer would refuse it (NoPartialWrites, compress.rs:298-301).
 __device__ __forceinline__ bool emit_sequence(uint8_t* out, uint32_t& opos, uint32_t cap, const uint8_t* in,
@@ -232,6 +242,9 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int n_smem_warps) {
 
         int status = LZF_OK;
         uint32_t opos = 0;
+        // plaintext still in flight over PCIe (independent blocks without history only): bytes below `arrived` are there
+        const bool gated = a.progress != nullptr && cursor0 == 0;
+        uint32_t arrived = gated ? 0u : 0xffffffffu;
 
         // assert!(input.len() <= T::payload_size_limit())  :167 / "EncoderTable contract violated" :67,92;
         // the slot width must hold every stream position
@@ -274,6 +287,12 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int n_smem_warps) {
                 const bool is_end = p64 >= len || len - (uint32_t)p64 < 12;    // :178
                 const uint32_t p = (uint32_t)p64;
                 const uint32_t endmask = __ballot_sync(LZF_FULL_MASK, is_end);
+                if (gated) {
+                    // the batch reads at most 16 bytes past its last probe position
+                    const uint32_t p_top = __shfl_sync(LZF_FULL_MASK, p64 < len ? (uint32_t)p64 : len, 31);
+                    const uint32_t need = len - p_top < 64 ? len : p_top + 64;
+                    if (need > arrived) arrived = wait_arrival(a.progress, a.slice_bytes, need);
+                }
                 if constexpr (kPacked) {
                     const uint32_t p_hi = __shfl_sync(LZF_FULL_MASK, p64 < len ? (uint32_t)p64 : len, 31);
                     if (p_hi + ab - last_sweep >= 65536u) {
@@ -464,6 +483,10 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int n_smem_warps) {
                     if (!fast) {
                     // ---- general extension: lanes 0..23 look 96 bytes ahead (count_matching_bytes :117-145 over
                     // input[cur..len-5]), lanes 24..31 look 32 bytes behind (backtrack :211-214)
+                    if (gated) {
+                        const uint32_t need = len - cur < 128 ? len : cur + 128;
+                        if (need > arrived) arrived = wait_arrival(a.progress, a.slice_bytes, need);
+                    }
                     uint32_t cnt = 4;                                         // bytes this lane's word contributes
                     if (lane < 24) {
                         const uint32_t f = 4 + 4 * lane;
@@ -496,6 +519,11 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int n_smem_warps) {
                             // long match: stream on, 8 bytes per lane and step
                             matching = 100;
                             for (;;) {
+                                if (gated) {
+                                    const uint32_t top = cur + matching;          // this pass reads [top, top + 264)
+                                    const uint32_t need = len - top < 264 ? len : top + 264;
+                                    if (need > arrived) arrived = wait_arrival(a.progress, a.slice_bytes, need);
+                                }
                                 const uint32_t idx = matching + lane * 8;
                                 uint32_t c = 0;
                                 if (idx < limit) {
@@ -601,6 +629,7 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int n_smem_warps) {
             a.out_len[b] = (status == LZF_OK) ? opos : 0u;
             a.status[b] = status;
         }
+        if (gated && len > arrived) arrived = wait_arrival(a.progress, a.slice_bytes, len);   // a refused block stops early
         // XXH32 of the plaintext / of the stored bytes (compressed, or the plaintext when stored raw):
         // queued so that 8 blocks are hashed per warp pass
         if (a.xxh_plain) hash_queue_push(&hashq, in + cursor0, own_len, a.xxh_plain + b);

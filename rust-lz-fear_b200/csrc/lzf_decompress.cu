@@ -21,6 +21,7 @@
 //     touch the end of the block, every error and the out-of-capacity "dry" mode.
 #include "lzf_kernels.cuh"
 
+#include <stddef.h>
 #include <stdlib.h>
 
 namespace lzf {
@@ -40,16 +41,19 @@ struct __align__(16) DecodeWarpSmem {
     uint8_t win[kWin];            // staged compressed bytes
     uint8_t step[kWin + 32];      // step[p] = encoded size of the LSIC-free sequence whose token is win[p]; 0 = not fast
     uint8_t stage[kStage];        // output staging ring
-    uint32_t plist[32];           // token positions of the current step
+    uint32_t plist[40];           // token positions of the current step (a group of 8 may overshoot the 32 kept)
     uint64_t mbar;
     uint64_t pad;
 };
 
+constexpr int kStepOff = (int)kWin;          // offsetof(DecodeWarpSmem, step)
+static_assert(offsetof(DecodeWarpSmem, step) == kStepOff, "step[] follows win[]");
+
 // step[] for the freshly staged window: 4 positions per lane and pass, SIMD-in-a-word.
-//   step = 3 + (token >> 4) for a sequence without length extensions;
-//   step = 1 when either nibble is 15: the walk works the size out itself if it ever lands there
-//          (most such bytes are literals, not tokens, so nothing is spent on them here);
-//   step = 0 when a plain sequence would end beyond `wend` (window / block end -> refill or slow path).
+//   step = 3 + (token >> 4) for a sequence without length extensions that ends inside the window;
+//   step = 0 otherwise: either nibble is 15 (the walk works the size out itself if it ever lands there — most
+//          such bytes are literals, not tokens, so nothing is spent on them here), or the sequence would end
+//          beyond `wend` (window / block end -> refill or slow path).  Adding a 0 step leaves the walk in place.
 __device__ __forceinline__ void build_steps(DecodeWarpSmem& sm, uint32_t wlen, uint32_t wend) {
     const unsigned lane = lane_id();
     const uint32_t* w4 = reinterpret_cast<const uint32_t*>(sm.win);
@@ -58,12 +62,12 @@ __device__ __forceinline__ void build_steps(DecodeWarpSmem& sm, uint32_t wlen, u
     for (uint32_t i = lane; i < nwords; i += 32) {
         const uint32_t w = w4[i];
         const uint32_t special = __vcmpeq4(w & 0xf0f0f0f0u, 0xf0f0f0f0u) | __vcmpeq4(w & 0x0f0f0f0fu, 0x0f0f0f0fu);
-        s4[i] = ((((w >> 4) & 0x0f0f0f0fu) + 0x03030303u) & ~special) | (special & 0x01010101u);
+        s4[i] = (((w >> 4) & 0x0f0f0f0fu) + 0x03030303u) & ~special;
     }
     __syncwarp();
     // the last kFastSeqMax positions may describe sequences that cross wend; wend itself terminates a walk
     const uint32_t p = wend - min(wend, kFastSeqMax + 1u) + lane;
-    if (p <= wend && (p == wend || (sm.step[p] != 1 && p + sm.step[p] > wend))) sm.step[p] = 0;
+    if (p <= wend && (p == wend || p + sm.step[p] > wend)) sm.step[p] = 0;
     __syncwarp();
 }
 
@@ -342,40 +346,56 @@ decode_blocks_kernel(DecodeArgs a) {
                 // shared-memory byte per plain sequence.
                 uint32_t cnt = 0;
                 {
-                    // plain prefix, branch-free: a position that is not a plain sequence (step < 3) does not advance
-                    // p, so the walk sticks there and every later slot repeats it; four instructions per sequence
-                    // (LDS, STS, ISETP, predicated IADD) and one uniform branch per 8.  (Measured on B200: 338 ->
-                    // 371 GiB/s on config 2 against the loop that tests every step; choosing between the two loops
-                    // per step cost more than it gave back on text, 311 / 106 GiB/s.)
-                    uint32_t d = 3, nk = 0;
+                    // Three instructions per plain sequence (LDS step, STS slot, IADD): positions are kept as offsets
+                    // into the CTA's shared memory so that one register addresses the step byte, and a 0 step (not a
+                    // plain sequence) simply leaves the walk where it is — no test inside a group of 8.
+                    const uint32_t qbase = smem_off(smem_raw, &sm);             // slot value = qbase + window position
+                    uint32_t q = qbase + p, d = 1, nk = 0;
 #pragma unroll
                     for (int c = 0; c < 4; c++) {
-                        if (d >= 3) {
+                        if (d != 0) {
 #pragma unroll
                             for (int i = 0; i < 8; i++) {
-                                d = sm.step[p];
-                                sm.plist[c * 8 + i] = p;
-                                if (d >= 3) p += d;
+                                d = lds_u8<kStepOff>(smem_raw, q);
+                                sm.plist[c * 8 + i] = q;
+                                q += d;
                             }
                             nk = c * 8 + 8;
                         }
                     }
                     __syncwarp();
-                    const uint32_t dm = lane < nk ? sm.step[sm.plist[lane]] : 0u;
-                    cnt = __popc(__ballot_sync(LZF_FULL_MASK, dm >= 3));        // a prefix of the lanes
-                    // the rest of the step: sequences with single-byte length extensions mixed with plain ones
-#pragma unroll 1
-                    for (uint32_t k = cnt; k < 32; k++) {
-                        uint32_t d = sm.step[p];
-                        if (d < 3) {                                  // 0: stop; 1: a token with length extensions
-                            if (d == 0) break;
-                            d = medium_size(sm, p, wend);
-                            if (d == 0) break;
+                    const uint32_t dm = lane < nk ? lds_u8<kStepOff>(smem_raw, sm.plist[lane]) : 0u;
+                    cnt = __popc(__ballot_sync(LZF_FULL_MASK, dm != 0));        // a prefix of the lanes
+                    p = q - qbase;
+                    if (cnt < 32) {
+                        // stuck: a sequence with single-byte length extensions is sized by medium_size and the walk
+                        // goes on behind it with counted slots (text: ~6 % of the sequences); anything else ends the step
+                        uint32_t* kp = sm.plist + cnt;
+                        for (;;) {
+                            const uint32_t m = medium_size(sm, p, wend);
+                            if (m == 0) break;
+                            *kp++ = qbase + p;
+                            p += m;
+                            if (kp >= sm.plist + 32) break;
+                            q = qbase + p;
+                            for (;;) {
+#pragma unroll
+                                for (int i = 0; i < 8; i++) {
+                                    d = lds_u8<kStepOff>(smem_raw, q);
+                                    *kp = q;
+                                    q += d;
+                                    kp += d != 0;
+                                }
+                                if (d == 0 || kp >= sm.plist + 32) break;
+                            }
+                            p = q - qbase;
+                            if (kp >= sm.plist + 32) break;
                         }
-                        sm.plist[k] = p;
-                        p += d;
-                        cnt = k + 1;
+                        cnt = (uint32_t)(kp - sm.plist);
+                        if (cnt > 32) { cnt = 32; p = sm.plist[32] - qbase; }     // a group overshot: sequence 32 starts the next step
                     }
+                    __syncwarp();
+                    if (lane < cnt) sm.plist[lane] -= qbase;                      // back to window positions
                 }
                 __syncwarp();
                 const uint32_t my_p = sm.plist[lane];

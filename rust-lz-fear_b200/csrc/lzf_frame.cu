@@ -12,14 +12,81 @@ namespace lzf {
 // ------------------------------------------------------------------------------------------
 // XXH32 of ranges: 8 ranges per warp (4 lanes = the 4 accumulator chains of one range)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+// One warp per CTA at 32 registers: such a CTA still fits on an SM whose register file is otherwise taken by the
+// 28-warp block-encode CTA (28 x 32 x 72 of 65 536 registers), so frame content checksums overlap the encode kernel.
+//
+// The four accumulator chains of one range are serial (~13 cycles per 16-byte stripe), so the only way to hash a
+// long range fast is to keep its bytes from ever being waited for: each range streams through a double-buffered
+// 2 KiB shared-memory window filled by TMA bulk copies (cp.async.bulk + mbarrier) while the previous window is
+// being hashed.  Loading straight from global memory instead (8 stripes in flight per lane) measured 5.2 ms per
+// MiB on B200 — every group of 8 stripes paid a full memory round trip.
+constexpr uint32_t kHashWin = 2048;
+struct __align__(16) RangeHashSmem {
+    uint8_t buf[8][2][kHashWin];
+    uint64_t bar[8][2];
+};
+
+#ifdef LZF_SIMT_EMU
+__global__ void
+#else
+__global__ void __maxnreg__(32)
+#endif
 xxh32_ranges_kernel(const uint8_t* data, const uint64_t* off, const uint64_t* len, uint32_t nranges, uint32_t* hash) {
-    const uint32_t warp = blockIdx.x * 4 + (threadIdx.x >> 5);
+    __shared__ RangeHashSmem sm;
+    const uint32_t warp = blockIdx.x;
     const unsigned lane = lane_id();
-    const uint32_t r = warp * 8 + (lane >> 2);
+    const unsigned j = lane >> 2, a = lane & 3u;
+    const uint32_t r = warp * 8 + j;
     const bool valid = r < nranges;
-    const uint32_t h = warp_xxh32_x8(valid ? data + off[r] : nullptr, valid ? len[r] : 0);
-    if (valid && (lane & 3u) == 0) hash[r] = h;
+    const uint8_t* p = valid ? data + off[r] : nullptr;
+    const uint64_t n = valid ? len[r] : 0;
+    // TMA wants 16-byte aligned sources; anything else (and short ranges) takes the plain path
+    const bool streamable = (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
+    if (__ballot_sync(LZF_FULL_MASK, !streamable) != 0 || warp_max_u32((uint32_t)(n > 0xffffffffull ? 0xffffffffu : n)) < 4 * kHashWin) {
+        const uint32_t h = warp_xxh32_x8(p, n);
+        if (valid && a == 0) hash[r] = h;
+        return;
+    }
+    const uint64_t nstripes = n >> 4;
+    const uint64_t nwin = (nstripes * 16 + kHashWin - 1) / kHashWin;              // windows of this range
+    uint64_t nwin_max = nwin;
+    for (int sft = 16; sft; sft >>= 1) {                                          // 64-bit max over the warp
+        const uint64_t o = __shfl_xor_sync(LZF_FULL_MASK, nwin_max, sft);
+        nwin_max = o > nwin_max ? o : nwin_max;
+    }
+    if (a == 0) { mbar_init(&sm.bar[j][0], 1); mbar_init(&sm.bar[j][1], 1); }
+    __syncwarp();
+    auto issue = [&](uint64_t w) {                                                // leader lane of the range
+        const uint64_t o = w * kHashWin;
+        const uint64_t left = nstripes * 16 - o;
+        bulk_load(sm.buf[j][w & 1], p + o, (uint32_t)(left < kHashWin ? left : kHashWin), &sm.bar[j][w & 1]);
+    };
+    if (a == 0) { if (nwin > 0) issue(0); if (nwin > 1) issue(1); }
+    __syncwarp();
+    uint32_t acc = xxh32_seed_acc(a);
+    for (uint64_t w = 0; w < nwin_max; w++) {
+        if (w < nwin) {
+#ifndef LZF_SIMT_EMU   // (the CPU test harness copies synchronously, and its wait is a warp collective)
+            mbar_wait(&sm.bar[j][w & 1], (uint32_t)((w >> 1) & 1));
+#endif
+            const uint64_t left = nstripes - w * (kHashWin / 16);
+            const uint32_t ns = (uint32_t)(left < kHashWin / 16 ? left : kHashWin / 16);
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(sm.buf[j][w & 1]) + a;
+            uint32_t s = 0;
+            for (; s + 8 <= ns; s += 8) {
+                uint32_t x[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) x[i] = q[(s + i) * 4];
+#pragma unroll
+                for (int i = 0; i < 8; i++) acc = xxh_round(acc, x[i]);
+            }
+            for (; s < ns; s++) acc = xxh_round(acc, q[s * 4]);
+        }
+        __syncwarp();                                                             // the window is free again
+        if (a == 0 && w + 2 < nwin) issue(w + 2);
+    }
+    const uint32_t h = warp_xxh32_x8_finish(acc, p, n);
+    if (valid && a == 0) hash[r] = h;
 }
 
 // Stripe phase only, one warp, carrying a running state: acc[0..4) in/out (streaming content
@@ -214,7 +281,7 @@ __global__ void __launch_bounds__(64) frame_walk_kernel(WalkArgs a) {
 extern "C" int lzf_launch_xxh32_ranges(const uint8_t* data, const uint64_t* off, const uint64_t* len,
                                        uint32_t nranges, uint32_t* hash, cudaStream_t s) {
     if (!nranges) return 0;
-    LZF_LAUNCH(lzf::xxh32_ranges_kernel, (nranges + 31) / 32, 128, 0, s, data, off, len, nranges, hash);
+    LZF_LAUNCH(lzf::xxh32_ranges_kernel, (nranges + 7) / 8, 32, 0, s, data, off, len, nranges, hash);
     return (int)cudaGetLastError();
 }
 extern "C" int lzf_launch_xxh32_stripes(const uint8_t* data, uint64_t nstripes, uint32_t* acc, cudaStream_t s) {

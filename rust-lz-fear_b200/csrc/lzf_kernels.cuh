@@ -22,6 +22,10 @@ struct EncodeArgs {
     const uint32_t* prefix_len; const uint32_t* abs_base; const uint32_t* prime_len;
     const uint32_t* chain_first; const uint32_t* chain_count; uint32_t nchains;
     uint64_t max_pos;   // largest stream position + 1 any block reaches (0 = max_block_len): picks the slot width
+    // internal (host-buffer pipeline): the plaintext is still arriving over PCIe while the kernel runs.  Bytes
+    // [0, *progress * slice_bytes) of EVERY block are in place (the host copies one slice of all blocks after the
+    // other and bumps *progress after each); a warp waits before it reads past that.  null = everything is there.
+    const uint32_t* progress; uint32_t slice_bytes;
 };
 struct StageArgs {      // [dictionary | block] staging copies for blocks whose history is the dictionary
     uint32_t n; const uint8_t* dict; uint32_t dlen;

@@ -234,6 +234,26 @@ def test_dependent_and_dictionary_frames(gpu, oracle, issue15_input, corpora, li
     assert gpu.ctx.frame_decompress(fr, cap=len(data) + 16)[:3] == (0, 0, data)
 
 
+def test_sliced_input_feed(gpu, oracle, monkeypatch):
+    """lzf_frames_compress over host buffers: the plaintext arrives slice by slice while the block kernel runs."""
+    import test_simt_kernels as T
+    T.test_frame_compress_with_sliced_input_feed(gpu, oracle, monkeypatch, scale=8)
+    # many frames in one call, default slice size, 1 MiB blocks
+    monkeypatch.setenv("LZF_B200_FEED_MIN_BLOCKS", "2")
+    monkeypatch.delenv("LZF_B200_FEED_SLICE")
+    nf, fp = 6, 8 << 20
+    src = np.concatenate([W.mixed_blocks(8, 1 << 20, seed=77 + f).numpy() for f in range(nf)])
+    s, keep = N.make_settings(block_size=1 << 20, block_checksums=True)
+    bound = gpu.ctx.frame_bound(s, fp)
+    out = np.zeros(nf * bound, dtype=np.uint8)
+    fl, fs = gpu.ctx.frames_compress(src, np.arange(nf, dtype=np.uint64) * fp, np.full(nf, fp, np.uint64), out,
+                                     np.arange(nf, dtype=np.uint64) * bound, np.full(nf, bound, np.uint64), s)
+    assert not fs.any()
+    for f in range(nf):
+        want = oracle.frame_compress(src[f * fp:(f + 1) * fp].tobytes(), block_size=1 << 20, block_checksums=True)
+        assert (0, out[f * bound:f * bound + int(fl[f])].tobytes()) == want, f
+
+
 def test_dependent_and_dictionary_frames_compress(gpu, oracle, issue15_input):
     """Compress side of SURVEY §8(f) rank 2: one warp carries the table through all blocks of a dependent
     frame; dictionaries prime the table.  Frames are byte-identical to the oracle's."""

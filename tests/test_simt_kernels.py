@@ -93,6 +93,22 @@ def test_batched_blocks_tables_in_global_scratch(emu, oracle, monkeypatch):
         parity.check_batched_blocks(emu, oracle, small, max_block_len=65536)                            # u16 slots
 
 
+def test_frame_compress_with_sliced_input_feed(emu, oracle, monkeypatch, scale=1):
+    """Host-buffer compress feeds large independent blocks slice by slice while the kernel runs (the warps poll a
+    progress word); same frames as the oracle, stored (incompressible) blocks included."""
+    from lz_fear_b200 import workloads as W
+    monkeypatch.setenv("LZF_B200_FEED_MIN_BLOCKS", "2")
+    monkeypatch.setenv("LZF_B200_FEED_SLICE", "65536")
+    bs = 256 << 10
+    data = (W.text(bs + bs // 2, 21).numpy().tobytes() + W.random_bytes(bs, 22).numpy().tobytes() +
+            W.lowent(bs // 2, 23).numpy().tobytes() + bytes(bs)) * scale
+    assert len(data) % bs == 0
+    for kw in (dict(block_size=bs), dict(block_size=bs, block_checksums=True, content_checksum=False)):
+        st, frame = emu.ctx.frame_compress(data, **kw)
+        assert (st, frame) == oracle.frame_compress(data, **kw)
+    assert emu.ctx.frame_decompress(frame, cap=len(data) + 16)[:3] == (0, 0, data)
+
+
 def test_frames_roundtrip_and_bytes(emu, oracle):
     inputs = [b"", b"a", bytes(65536), parity.sample_inputs()[6], parity.sample_inputs()[7][:70001],
               parity.sample_inputs()[5] * 30]
