@@ -143,17 +143,25 @@ def test_config2_seq50_decompress_vs_oracle(gpu, oracle):
         assert xs[b] == oracle.xxh32(ref[b * 65536:(b + 1) * 65536])
 
 
-def test_config3_text_compress_vs_oracle(gpu, oracle):
-    """64 of the config-3 blocks (4 MiB text) byte-identical to the oracle, then decoded back."""
+@pytest.mark.parametrize("variant", ["u32-small-ctas", "packed-28-warps", "packed-all-global", "u32-all-global"])
+def test_config3_text_compress_vs_oracle(gpu, oracle, monkeypatch, variant):
+    """64 of the config-3 blocks (4 MiB text) byte-identical to the oracle, then decoded back — on every table
+    layout of the encode kernel: u32 slots in 4-warp CTAs (no max_block_len promise), packed 17-bit slots in the
+    28-warp CTA (13 tables in shared memory, the rest in the L2 scratch), all tables in the scratch, plain u32 there."""
     import torch
     nb, B = 64, 4 << 20
+    mbl = 0 if variant == "u32-small-ctas" else B
+    if variant in ("packed-all-global", "u32-all-global"):
+        monkeypatch.setenv("LZF_B200_ENC_SMEM_WARPS", "0")
+    if variant == "u32-all-global":
+        monkeypatch.setenv("LZF_B200_ENC_U32", "1")
     data = W.TextSource(device="cuda").make(nb * B)
     off = torch.arange(nb, device="cuda", dtype=torch.int64) * B
     ln = torch.full((nb,), B, dtype=torch.int32, device="cuda")
     comp = torch.empty(nb * B, dtype=torch.uint8, device="cuda")
     olen = torch.zeros(nb, dtype=torch.int32, device="cuda")
     st = torch.zeros(nb, dtype=torch.int32, device="cuda")
-    gpu.ctx.compress_blocks(data, off, ln, nb, comp, off, None, olen, st)
+    gpu.ctx.compress_blocks(data, off, ln, nb, comp, off, None, olen, st, max_block_len=mbl)
     torch.cuda.synchronize()
     assert int(st.abs().sum()) == 0
     h = data.cpu().numpy()
