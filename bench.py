@@ -50,7 +50,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-xxh", action="store_true", help="experiment: skip the fused XXH32 epilogue")
-    ap.add_argument("--gather", action="store_true", help="N > 1: also time the frame-granular NCCL gather of compressed frames to rank 0")
+    ap.add_argument("--gather", action="store_true", help="(default when N > 1) also time the frame-granular NCCL gather of compressed frames to rank 0")
+    ap.add_argument("--no-gather", action="store_true", help="N > 1: skip the NCCL gather section")
     ap.add_argument("--extra", action="store_true", help="also run BASELINE configs 4 (mixed-entropy frames) and 5 (large hash tables)")
     ap.add_argument("--mixed-gib", type=float, default=8.0, help="config-4 plaintext GiB per GPU (64 GiB over 8 GPUs)")
     ap.add_argument("--lowent-gib", type=float, default=1.0, help="config-5 plaintext GiB")
@@ -477,41 +478,44 @@ def main():
             st_, det_, pl_, _c = ctx.frame_decompress(out_h[: int(fl[0])], cap=fp + 16)
             assert st_ == 0 and np.array_equal(np.frombuffer(pl_, dtype=np.uint8), in_h[:fp])
             del in_t, out_t
-        if args.gather and world > 1:
-            # config-4 flavour: the one real exchange step — compressed frames of every rank travel to rank 0 over
-            # NCCL (all-gather of per-frame sizes, then grouped send/recv of the variable-length payloads)
-            from lz_fear_b200 import sharding
-            gb = min(nb3, 1024)                                     # up to 4 GiB of plaintext per rank
-            nf = gb // BLOCKS_PER_FRAME3
-            fp = BLOCKS_PER_FRAME3 * BLOCK3
-            sset, _k2 = N.make_settings()
-            bound = ctx.frame_bound(sset, fp)
-            fr = torch.empty(nf * bound, dtype=torch.uint8, device=dev)
-            g_off = np.arange(nf, dtype=np.uint64) * bound
-            fl, fs = ctx.frames_compress_device(data, np.arange(nf, dtype=np.uint64) * fp, np.full(nf, fp, np.uint64), fr, g_off,
-                                                np.full(nf, bound, np.uint64), sset)
-            assert not fs.any()
-            packed = torch.cat([fr[int(o):int(o) + int(l)] for o, l in zip(g_off, fl)])
-            sizes = torch.from_numpy(fl.astype(np.int64)).to(dev)
-            for _ in range(2):                                       # NCCL sets its point-to-point channels up on first use
-                per_rank = sharding.all_gather_sizes(sizes)
-                got = sharding.gather_bytes(packed, per_rank, dst=0)
-            barrier()
-            e0.record()
-            for _ in range(K):
-                per_rank = sharding.all_gather_sizes(sizes)
-                got = sharding.gather_bytes(packed, per_rank, dst=0)
-            e1.record()
-            barrier()
-            g_ms = max_over_ranks(e0.elapsed_time(e1)) / K
-            total_bytes = sum(int(x.sum().item()) for x in per_rank)
-            if rank == 0:
-                assert got.numel() == total_bytes and torch.equal(got[: packed.numel()], packed)
-            comp_section["gather"] = {"ms": g_ms, "compressed_bytes_all_ranks": total_bytes,
-                                      "GiB_per_s_into_rank0": (total_bytes - int(packed.numel())) / GiB / (g_ms / 1e3),
-                                      "plaintext_GiB_per_rank": nf * fp / GiB,
-                                      "note": "NCCL all_gather(sizes) + send/recv of whole frames to rank 0; not part of `value`"}
-            del fr, packed, got
+        if world > 1 and not args.no_gather:
+            try:
+                # config-4 flavour: the one real exchange step — compressed frames of every rank travel to rank 0 over
+                # NCCL (all-gather of per-frame sizes, then grouped send/recv of the variable-length payloads)
+                from lz_fear_b200 import sharding
+                gb = min(nb3, 1024)                                     # up to 4 GiB of plaintext per rank
+                nf = gb // BLOCKS_PER_FRAME3
+                fp = BLOCKS_PER_FRAME3 * BLOCK3
+                sset, _k2 = N.make_settings()
+                bound = ctx.frame_bound(sset, fp)
+                fr = torch.empty(nf * bound, dtype=torch.uint8, device=dev)
+                g_off = np.arange(nf, dtype=np.uint64) * bound
+                fl, fs = ctx.frames_compress_device(data, np.arange(nf, dtype=np.uint64) * fp, np.full(nf, fp, np.uint64), fr, g_off,
+                                                    np.full(nf, bound, np.uint64), sset)
+                assert not fs.any()
+                packed = torch.cat([fr[int(o):int(o) + int(l)] for o, l in zip(g_off, fl)])
+                sizes = torch.from_numpy(fl.astype(np.int64)).to(dev)
+                for _ in range(2):                                       # NCCL sets its point-to-point channels up on first use
+                    per_rank = sharding.all_gather_sizes(sizes)
+                    got = sharding.gather_bytes(packed, per_rank, dst=0)
+                barrier()
+                e0.record()
+                for _ in range(K):
+                    per_rank = sharding.all_gather_sizes(sizes)
+                    got = sharding.gather_bytes(packed, per_rank, dst=0)
+                e1.record()
+                barrier()
+                g_ms = max_over_ranks(e0.elapsed_time(e1)) / K
+                total_bytes = sum(int(x.sum().item()) for x in per_rank)
+                if rank == 0:
+                    assert got.numel() == total_bytes and torch.equal(got[: packed.numel()], packed)
+                comp_section["gather"] = {"ms": g_ms, "compressed_bytes_all_ranks": total_bytes,
+                                          "GiB_per_s_into_rank0": (total_bytes - int(packed.numel())) / GiB / (g_ms / 1e3),
+                                          "plaintext_GiB_per_rank": nf * fp / GiB,
+                                          "note": "NCCL all_gather(sizes) + send/recv of whole frames to rank 0; not part of `value`"}
+                del fr, packed, got
+            except Exception as e:                                   # the exchange step is reported beside the value, never instead of it
+                comp_section["gather"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
         if rank == 0 and not args.no_cpu:
             cores = os.cpu_count() or 1
             ns = min(nb3, max(cores, 32))

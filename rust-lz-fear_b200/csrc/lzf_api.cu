@@ -734,7 +734,8 @@ struct DecodeOut {          // optional extra per-frame results
     int32_t* detail;        // nullable
     // host-buffer pipeline hook: called once the block kernel is queued on the stream (before the host
     // waits for its results), so the D2H copy of the plaintext can start while the outcome is resolved
-    std::function<int()> after_decode;
+    // (argument: upper bound of the plaintext bytes the frames can decode to, from their block counts)
+    std::function<int(uint64_t)> after_decode;
 };
 
 int frames_decompress_core(lzf_ctx* c, const uint8_t* d_in, const uint64_t* in_off, const uint64_t* in_len,
@@ -885,7 +886,14 @@ int frames_decompress_core(lzf_ctx* c, const uint8_t* d_in, const uint64_t* in_o
                                     (const uint32_t*)(d + o_bcap), (const uint32_t*)(d + o_blim), (uint32_t*)(r + r_olen),
                                     (int32_t*)(r + r_bst), nullptr, st, use_hist, d_wait, d_done);
         if (rc) return rc;
-        if (extra.after_decode && (rc = extra.after_decode())) return rc;
+        if (extra.after_decode) {
+            uint64_t expect = 0;
+            for (uint32_t f = 0; f < nframes; f++) {
+                const uint64_t e = (uint64_t)wf[f].nblocks * wf[f].block_maxsize;
+                expect += e < out_cap[f] ? e : out_cap[f];
+            }
+            if ((rc = extra.after_decode(expect))) return rc;
+        }
         LZF_CU(c, cudaMemcpyAsync(hr + r_olen, r + r_olen, r_bxxh - r_olen, cudaMemcpyDeviceToHost, st));
         if (any_block_checksums) {
             LZF_CU(c, cudaMemcpyAsync(hr + r_bxxh, r + r_bxxh, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, st));
@@ -1117,7 +1125,7 @@ std::vector<uint32_t> plan_chunks(const uint64_t* len, uint32_t n, uint64_t targ
 // one chunk with the kernels of another and the D2H copy of a third comes from the streams running
 // side by side, and kernels of different chunks share the SMs.
 template <typename F>
-int run_chunks(lzf_ctx* c, uint32_t nchunks, F work) {
+int run_chunks(lzf_ctx* c, uint32_t nchunks, F work, uint32_t max_workers = kSlots) {
     if (nchunks == 0) return LZF_SUCCESS;
     std::atomic<uint32_t> next{0};
     std::atomic<int> rc_all{LZF_SUCCESS};
@@ -1136,7 +1144,7 @@ int run_chunks(lzf_ctx* c, uint32_t nchunks, F work) {
 #ifdef LZF_SIMT_EMU
     const uint32_t nworkers = 1;                 // the CPU SIMT test harness is single-threaded
 #else
-    const uint32_t nworkers = nchunks < (uint32_t)kSlots ? nchunks : (uint32_t)kSlots;
+    const uint32_t nworkers = nchunks < max_workers ? nchunks : max_workers;
 #endif
     std::vector<std::thread> threads;
     for (uint32_t k = 1; k < nworkers; k++) threads.emplace_back(worker, (int)k);
@@ -1222,9 +1230,11 @@ extern "C" int lzf_frames_compress(lzf_ctx* c, const lzf_settings* s, const uint
         if (target > (24ull << 30)) target = 24ull << 30;
     }
     const std::vector<uint32_t> chunks = plan_chunks(in_len, nframes, target);
+    // wave-sized chunks hold three buffers of their own size each, and two block kernels never share an SM: two
+    // slots are enough to overlap the copies of one chunk with the kernel of the next
     return run_chunks(c, (uint32_t)chunks.size() - 1, [&](uint32_t i, lzf_slot& sl) {
         return compress_chunk(c, sl, s, chunks[i], chunks[i + 1], in, in_off, in_len, out, out_off, out_cap, out_len, status);
-    });
+    }, target >= (2ull << 30) ? 2u : (uint32_t)kSlots);
 }
 
 extern "C" int lzf_frame_compress(lzf_ctx* c, const lzf_settings* s, const uint8_t* in, size_t n,
@@ -1285,7 +1295,8 @@ int decompress_chunk(lzf_ctx* c, lzf_slot& sl, uint32_t f0, uint32_t f1, const u
     bool early_copy = false;
     DecodeOut ex{consumed ? consumed + f0 : nullptr, detail ? detail + f0 : nullptr, nullptr};
     if (lo.dense && lo.span) {
-        ex.after_decode = [&]() -> int {
+        ex.after_decode = [&](uint64_t expect) -> int {
+            if (lo.span > expect + expect / 4) return LZF_SUCCESS;       // generous capacities: copy what was decoded, later
             LZF_CU(c, cudaEventRecord(sl.ev_fork, sl.stream));
             LZF_CU(c, cudaStreamWaitEvent(sl.side, sl.ev_fork, 0));
             LZF_CU(c, cudaMemcpyAsync(out + lo.base, dout, lo.span, cudaMemcpyDeviceToHost, sl.side));
