@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <chrono>
 #include <functional>
 #include <mutex>
 #include <new>
@@ -528,7 +529,11 @@ int build_header(const lzf_settings* s, uint64_t content_size, uint8_t* hdr, uin
 int frames_compress_core(lzf_ctx* c, const lzf_settings* s, const uint8_t* d_in, const uint64_t* in_off,
                          const uint64_t* in_len, uint32_t nframes, uint8_t* d_out, const uint64_t* out_off,
                          const uint64_t* out_cap, uint64_t* out_len, int32_t* status, cudaStream_t st,
-                         const InputFeed* feed = nullptr) {
+                         const InputFeed* feed = nullptr, const uint32_t** deferred_hash = nullptr) {
+    // deferred_hash (host-buffer pipeline): the frames are laid out and assembled without waiting for the content
+    // checksums — only the last 4 bytes of a frame depend on them — and the caller patches those from
+    // *deferred_hash (device, one u32 per frame, complete once the slot's side stream has drained)
+    if (deferred_hash) *deferred_hash = nullptr;
     if (!s || (nframes && (!in_off || !in_len || !out_off || !out_cap || !out_len || !status)))
         return fail(c, LZF_ERR_INVALID_ARG, "null pointer");
     for (uint32_t f = 0; f < nframes; f++) { out_len[f] = 0; status[f] = LZF_F_OK; }
@@ -692,7 +697,10 @@ int frames_compress_core(lzf_ctx* c, const lzf_settings* s, const uint8_t* d_in,
                                                (uint32_t*)(r + r_chash), cur_slot(c)->side), 1);
         LZF_CU(c, cudaEventRecord(cur_slot(c)->ev_join, cur_slot(c)->side));
     }
-    if (s->content_checksum) LZF_CU(c, cudaStreamWaitEvent(st, cur_slot(c)->ev_join, 0));
+    if (s->content_checksum) {
+        if (deferred_hash) *deferred_hash = (const uint32_t*)(r + r_chash);
+        else LZF_CU(c, cudaStreamWaitEvent(st, cur_slot(c)->ev_join, 0));
+    }
     lzf::LayoutArgs la;
     memset(&la, 0, sizeof(la));
     la.nframes = nframes;
@@ -1165,6 +1173,9 @@ int compress_chunk(lzf_ctx* c, lzf_slot& sl, const lzf_settings* s, uint32_t f0,
     const HostLayout li = plan_layout(in_off + f0, in_len + f0, n);
     const HostLayout lo = plan_layout(out_off + f0, dcap.data(), n);
     int rc;
+    const bool trace = getenv("LZF_B200_TRACE") != nullptr;           // phase times of the chunk on stderr
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
     if ((rc = ensure_dev(c, sl.d_io_in, li.span + 256))) return rc;
     if ((rc = ensure_dev(c, sl.d_io_out, lo.span + 256))) return rc;
     uint8_t* din = (uint8_t*)sl.d_io_in.p;
@@ -1173,7 +1184,7 @@ int compress_chunk(lzf_ctx* c, lzf_slot& sl, const lzf_settings* s, uint32_t f0,
     // independent blocks is fed while the kernel already runs: slice k of EVERY block travels before slice k + 1
     // of any (one strided copy per slice), followed by a 4-byte copy that bumps the progress word the warps poll.
     const uint64_t bs = s->block_size;
-    uint64_t slice = 256 << 10, min_blocks = 64;
+    uint64_t slice = 64 << 10, min_blocks = 64;     // 64 KiB: the first slice of 4096 blocks is there after 5 ms
     if (const char* e = getenv("LZF_B200_FEED_SLICE")) slice = strtoull(e, nullptr, 10);       // tuning / test knobs; 0 = off
     if (const char* e = getenv("LZF_B200_FEED_MIN_BLOCKS")) min_blocks = strtoull(e, nullptr, 10);
     bool sliced = li.dense && s->independent_blocks && !(s->dictionary && s->dictionary_len) && slice >= 4096 &&
@@ -1202,15 +1213,32 @@ int compress_chunk(lzf_ctx* c, lzf_slot& sl, const lzf_settings* s, uint32_t f0,
             if (in_len[f0 + f])
                 LZF_CU(c, cudaMemcpyAsync(din + li.dev_off[f], in + in_off[f0 + f], in_len[f0 + f], cudaMemcpyHostToDevice, sl.stream));
     }
+    const uint32_t* d_hash = nullptr;      // content checksums still being computed on the side stream
     rc = frames_compress_core(c, s, din, li.dev_off.data(), in_len + f0, n, (uint8_t*)sl.d_io_out.p, lo.dev_off.data(),
-                              dcap.data(), out_len + f0, status + f0, sl.stream, sliced ? &feed : nullptr);
+                              dcap.data(), out_len + f0, status + f0, sl.stream, sliced ? &feed : nullptr, &d_hash);
     if (sliced) cudaStreamSynchronize(sl.copy);
     if (rc) return rc;
+    const double t_core = since();
     // compressed frames are much shorter than their capacity: copy each frame's bytes
     for (uint32_t f = f0; f < f1; f++)
         if (status[f] == LZF_F_OK && out_len[f])
             LZF_CU(c, cudaMemcpyAsync(out + out_off[f], dout + lo.dev_off[f - f0], out_len[f], cudaMemcpyDeviceToHost, sl.stream));
+    const double t_issued = since();
+    std::vector<uint32_t> hashes;
+    if (d_hash) {
+        // the checksums ran beside the assembly and the D2H copies; they are the last 4 bytes of each frame
+        // (src/framed/compress.rs:279-281)
+        hashes.resize(n);
+        LZF_CU(c, cudaStreamSynchronize(sl.side));
+        LZF_CU(c, cudaMemcpyAsync(hashes.data(), d_hash, (size_t)n * 4, cudaMemcpyDeviceToHost, sl.stream));
+    }
     LZF_CU(c, cudaStreamSynchronize(sl.stream));
+    if (d_hash)
+        for (uint32_t f = f0; f < f1; f++)
+            if (status[f] == LZF_F_OK && out_len[f] >= 4) wr32(out + out_off[f] + out_len[f] - 4, hashes[f - f0]);
+    if (trace)
+        fprintf(stderr, "lzf trace: compress chunk of %u frames (%s feed): kernels + results %.1f ms, D2H issued %.1f ms, done %.1f ms\n",
+                n, sliced ? "sliced" : "plain", t_core, t_issued, since());
     return LZF_SUCCESS;
 }
 
