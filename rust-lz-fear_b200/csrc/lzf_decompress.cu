@@ -32,7 +32,10 @@ namespace lzf {
 #ifndef LZF_DEC_WIN
 #define LZF_DEC_WIN 1024
 #endif
-constexpr int kDecodeWarpsPerCta = 8;
+#ifndef LZF_DEC_WARPS
+#define LZF_DEC_WARPS 8
+#endif
+constexpr int kDecodeWarpsPerCta = LZF_DEC_WARPS;
 constexpr uint32_t kWin = LZF_DEC_WIN;     // staged bytes of compressed stream per refill
 constexpr uint32_t kStage = 2048;          // output staging ring (power of two, > 32 * 32 + 16)
 constexpr uint32_t kFastSeqMax = 3 + 14;   // token + 14 literals + offset: no LSIC byte anywhere

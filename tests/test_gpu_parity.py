@@ -260,6 +260,14 @@ def test_sliced_input_feed(gpu, oracle, monkeypatch):
     for f in range(nf):
         want = oracle.frame_compress(src[f * fp:(f + 1) * fp].tobytes(), block_size=1 << 20, block_checksums=True)
         assert (0, out[f * bound:f * bound + int(fl[f])].tobytes()) == want, f
+    # 4 KiB slices (256 per block): the warps outrun the feed all the time and wait on the progress word
+    monkeypatch.setenv("LZF_B200_FEED_SLICE", "4096")
+    out2 = np.zeros_like(out)
+    fl2, fs2 = gpu.ctx.frames_compress(src, np.arange(nf, dtype=np.uint64) * fp, np.full(nf, fp, np.uint64), out2,
+                                       np.arange(nf, dtype=np.uint64) * bound, np.full(nf, bound, np.uint64), s)
+    assert not fs2.any() and np.array_equal(fl2, fl)
+    for f in range(nf):
+        assert np.array_equal(out2[f * bound:f * bound + int(fl[f])], out[f * bound:f * bound + int(fl[f])]), f
 
 
 def test_dependent_and_dictionary_frames_compress(gpu, oracle, issue15_input):
