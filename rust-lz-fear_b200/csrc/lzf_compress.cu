@@ -302,12 +302,26 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int n_smem_warps) {
                 }
                 uint32_t v32 = 0, h = 0xffff0000u | lane;                     // unique key for idle lanes
                 uint32_t tcand = 0, tdist = 0;
+                uint32_t n_a1 = 0, n_a2 = 0, n_a3 = 0, n_am1 = 0;             // this lane's bytes p+4.., p+8.., p+12.., p-4..
                 if (!is_end) {
                     const uintptr_t ad = reinterpret_cast<uintptr_t>(in + p);
                     const uint32_t* w = reinterpret_cast<const uint32_t*>(ad & ~uintptr_t(3));
                     const unsigned sh = (unsigned)(ad & 3u) * 8u;
                     const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1);          // 12 bytes remain: both words are inside the block
                     v32 = __funnelshift_r(w0, w1, sh);
+                    if (consecutive) {
+                        // bytes p+4.., p+8.., p+12.. and p-4.. for the extension summary below: same cache lines as
+                        // w0 / w1, fetched in the same round trip
+                        const uint32_t w2 = __ldg(w + 2);                     // bytes .. p+11
+                        n_a1 = __funnelshift_r(w1, w2, sh);
+                        if (p + 16 <= len) {
+                            const uint32_t w3 = __ldg(w + 3);
+                            const uint32_t w4 = sh ? __ldg(w + 4) : 0u;       // holds byte p+15 when p is unaligned
+                            n_a2 = __funnelshift_r(w2, w3, sh);
+                            n_a3 = __funnelshift_r(w3, w4, sh);
+                        }
+                        if (p >= 4) n_am1 = __funnelshift_r(__ldg(w - 1), w0, sh);
+                    }
                     h = kHash4 ? hash4(v32, hashlog) : hash5(v32, (w1 >> sh) & 0xffu, hashlog);
                     tdist = table.dist(h, p + ab);                            // table.replace :196 (read half)
                     tcand = p - tdist;
@@ -351,33 +365,20 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int n_smem_warps) {
                     }
                 }
                 const uint32_t base = __shfl_sync(LZF_FULL_MASK, p, 0);
-                if (consecutive) {
-                    // bytes p+4.., p+8.., p+12.. and p-4..: the neighbours' registers where a neighbour exists and
-                    // holds data, a (cache-resident) load otherwise
-                    uint32_t a1 = __shfl_down_sync(LZF_FULL_MASK, v32, 4);
-                    uint32_t a2 = __shfl_down_sync(LZF_FULL_MASK, v32, 8);
-                    uint32_t a3 = __shfl_down_sync(LZF_FULL_MASK, v32, 12);
-                    uint32_t am1 = __shfl_up_sync(LZF_FULL_MASK, v32, 4);
-                    if (v_pre && t_ok) {
-                        const uint32_t live = ~endmask;                          // lanes that loaded their v32
-                        if (p + 16 <= len) {                                     // bytes p .. p+15 are inside the block
-                            if (lane + 4 >= 32 || !((live >> (lane + 4)) & 1u)) a1 = ld4(in, p + 4);
-                            if (lane + 8 >= 32 || !((live >> (lane + 8)) & 1u)) a2 = ld4(in, p + 8);
-                            if (lane + 12 >= 32 || !((live >> (lane + 12)) & 1u)) a3 = ld4(in, p + 12);
-                            const uint32_t x1 = a1 ^ v_c1, x2 = a2 ^ v_c2, x3 = a3 ^ v_c3;
-                            uint32_t fm;
-                            if (x1) fm = 4 + ((uint32_t)(__ffs((int)x1) - 1) >> 3);
-                            else if (x2) fm = 8 + ((uint32_t)(__ffs((int)x2) - 1) >> 3);
-                            else if (x3) fm = 12 + ((uint32_t)(__ffs((int)x3) - 1) >> 3);
-                            else fm = 16;
-                            fsum |= fm | 0x100u;
-                        }
-                        if (v_hasb && p >= 4) {
-                            if (lane < 4) am1 = ld4(in, p - 4);
-                            const uint32_t xb = am1 ^ v_cm1;
-                            const uint32_t nb = xb ? (uint32_t)__clz((int)xb) >> 3 : 4u;
-                            fsum |= (nb << 5) | 0x200u;
-                        }
+                if (consecutive && v_pre && t_ok) {
+                    if (p + 16 <= len) {                                         // bytes p .. p+15 are inside the block
+                        const uint32_t x1 = n_a1 ^ v_c1, x2 = n_a2 ^ v_c2, x3 = n_a3 ^ v_c3;
+                        uint32_t fm;
+                        if (x1) fm = 4 + ((uint32_t)(__ffs((int)x1) - 1) >> 3);
+                        else if (x2) fm = 8 + ((uint32_t)(__ffs((int)x2) - 1) >> 3);
+                        else if (x3) fm = 12 + ((uint32_t)(__ffs((int)x3) - 1) >> 3);
+                        else fm = 16;
+                        fsum |= fm | 0x100u;
+                    }
+                    if (v_hasb && p >= 4) {
+                        const uint32_t xb = n_am1 ^ v_cm1;
+                        const uint32_t nb = xb ? (uint32_t)__clz((int)xb) >> 3 : 4u;
+                        fsum |= (nb << 5) | 0x200u;
                     }
                 }
 
