@@ -287,16 +287,19 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int n_smem_warps) {
                 const bool is_end = p64 >= len || len - (uint32_t)p64 < 12;    // :178
                 const uint32_t p = (uint32_t)p64;
                 const uint32_t endmask = __ballot_sync(LZF_FULL_MASK, is_end);
+                // first and last probe position of the batch (the last one clipped to the block): warp-uniform arithmetic
+                const uint64_t first64 = (uint64_t)lit_start + (consecutive ? (uint64_t)j : probe_offset(j));
+                const uint64_t last64 = (uint64_t)lit_start + (consecutive ? (uint64_t)(j + 31) : probe_offset(j + 31));
+                const uint32_t base = (uint32_t)first64;
+                const uint32_t p_top = last64 < len ? (uint32_t)last64 : len;
                 if (gated) {
                     // the batch reads at most 16 bytes past its last probe position
-                    const uint32_t p_top = __shfl_sync(LZF_FULL_MASK, p64 < len ? (uint32_t)p64 : len, 31);
                     const uint32_t need = len - p_top < 64 ? len : p_top + 64;
                     if (need > arrived) arrived = wait_arrival(a.progress, a.slice_bytes, need);
                 }
                 if constexpr (kPacked) {
-                    const uint32_t p_hi = __shfl_sync(LZF_FULL_MASK, p64 < len ? (uint32_t)p64 : len, 31);
-                    if (p_hi + ab - last_sweep >= 65536u) {
-                        last_sweep = __shfl_sync(LZF_FULL_MASK, (uint32_t)p64, 0) + ab;
+                    if (p_top + ab - last_sweep >= 65536u) {
+                        last_sweep = base + ab;
                         table.sweep(nslots, last_sweep);
                     }
                 }
@@ -330,58 +333,49 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int n_smem_warps) {
                 // table candidate: addressable (:200-201) and >= MINMATCH equal bytes (:206)
                 bool t_ok = false;
                 // FAST-PATH SUMMARY (consecutive batches): each lane also fetches 16 bytes after and 4 bytes
-                // before its table candidate in the same round trip, and compares them with the bytes of its
-                // own position, which sit in the v32 registers of lanes +4, +8, +12 and -4.  If the lane later
+                // before its table candidate in the same round trip, and compares them with the bytes around its
+                // own position (n_a1 .. n_am1, loaded with the probe bytes above).  If the lane later
                 // wins, its forward match length (up to 16) and backtrack (up to 4) are already known and the
                 // whole sequence is resolved with shuffles only — no further memory round trip.
                 //   fsum: bits 0..4 forward match length 4..16, bits 5..7 backtrack 0..4,
                 //         bit 8 forward summary valid, bit 9 backward summary valid
                 uint32_t fsum = 0;
-                uint32_t v_c1 = 0, v_c2 = 0, v_c3 = 0, v_cm1 = 0;
-                bool v_hasb = false, v_pre = false;
                 // addressable (:200-201): not the first position of the block (cursor != init_cursor), 1 <= distance
                 // <= 0xFFFF, and inside the history that is physically there
                 if (!is_end && p != cursor0 && tdist - 1u < 0xffffu && tdist <= p) {
-                    if (consecutive && tcand + 16 <= len) {
-                        const bool hasb = tcand >= 4;
-                        const uint32_t s0 = hasb ? tcand - 4 : tcand;
-                        const uintptr_t ad = reinterpret_cast<uintptr_t>(in + s0);
+                    if (consecutive && tcand >= 4 && tcand + 16 <= len) {
+                        // 4 bytes before and 16 bytes after the candidate, one round trip
+                        const uintptr_t ad = reinterpret_cast<uintptr_t>(in + tcand - 4);
                         const uint32_t* w = reinterpret_cast<const uint32_t*>(ad & ~uintptr_t(3));
                         const unsigned sh = (unsigned)(ad & 3u) * 8u;
-                        const uint32_t nw = hasb ? 5u : 4u;                       // unaligned words wanted from s0
                         uint32_t W[6];
 #pragma unroll
-                        for (int i = 0; i < 6; i++) W[i] = ((uint32_t)i < nw || ((uint32_t)i == nw && sh != 0)) ? __ldg(w + i) : 0u;
+                        for (int i = 0; i < 5; i++) W[i] = __ldg(w + i);
+                        W[5] = sh ? __ldg(w + 5) : 0u;
                         uint32_t U[5];
 #pragma unroll
                         for (int i = 0; i < 5; i++) U[i] = __funnelshift_r(W[i], W[i + 1], sh);
-                        const uint32_t cm1 = U[0];
-                        const uint32_t c0 = hasb ? U[1] : U[0], c1 = hasb ? U[2] : U[1], c2 = hasb ? U[3] : U[2], c3 = hasb ? U[4] : U[3];
-                        t_ok = c0 == v32;
-                        // park the candidate words for the comparison after the shuffles
-                        v_c1 = c1; v_c2 = c2; v_c3 = c3; v_cm1 = cm1; v_hasb = hasb; v_pre = true;
+                        t_ok = U[1] == v32;
+                        if (t_ok) {
+                            if (p + 16 <= len) {                                 // bytes p .. p+15 are inside the block
+                                const uint32_t x1 = n_a1 ^ U[2], x2 = n_a2 ^ U[3], x3 = n_a3 ^ U[4];
+                                uint32_t fm;
+                                if (x1) fm = 4 + ((uint32_t)(__ffs((int)x1) - 1) >> 3);
+                                else if (x2) fm = 8 + ((uint32_t)(__ffs((int)x2) - 1) >> 3);
+                                else if (x3) fm = 12 + ((uint32_t)(__ffs((int)x3) - 1) >> 3);
+                                else fm = 16;
+                                fsum |= fm | 0x100u;
+                            }
+                            if (p >= 4) {
+                                const uint32_t xb = n_am1 ^ U[0];
+                                const uint32_t nb = xb ? (uint32_t)__clz((int)xb) >> 3 : 4u;
+                                fsum |= (nb << 5) | 0x200u;
+                            }
+                        }
                     } else {
                         t_ok = ld4(in, tcand) == v32;
                     }
                 }
-                const uint32_t base = __shfl_sync(LZF_FULL_MASK, p, 0);
-                if (consecutive && v_pre && t_ok) {
-                    if (p + 16 <= len) {                                         // bytes p .. p+15 are inside the block
-                        const uint32_t x1 = n_a1 ^ v_c1, x2 = n_a2 ^ v_c2, x3 = n_a3 ^ v_c3;
-                        uint32_t fm;
-                        if (x1) fm = 4 + ((uint32_t)(__ffs((int)x1) - 1) >> 3);
-                        else if (x2) fm = 8 + ((uint32_t)(__ffs((int)x2) - 1) >> 3);
-                        else if (x3) fm = 12 + ((uint32_t)(__ffs((int)x3) - 1) >> 3);
-                        else fm = 16;
-                        fsum |= fm | 0x100u;
-                    }
-                    if (v_hasb && p >= 4) {
-                        const uint32_t xb = n_am1 ^ v_cm1;
-                        const uint32_t nb = xb ? (uint32_t)__clz((int)xb) >> 3 : 4u;
-                        fsum |= (nb << 5) | 0x200u;
-                    }
-                }
-
                 uint32_t ins = 0;       // lanes whose probe (or cursor-2 insert) has happened, in order
                 uint32_t s = 0;         // first lane of the current run inside this batch
                 bool committed = false;
