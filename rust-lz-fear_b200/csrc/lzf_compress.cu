@@ -454,25 +454,30 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int n_smem_warps) {
                             backtrack = min(nb, max_back);
                         }
                     }
+                    bool emitted = false;
                     if (fast) {
-                        // ---- HOT PATH: a short sequence that starts and ends inside this batch — token, <= 14
+                        // ---- HOT PATH: a short sequence whose literals start inside this batch — token, <= 14
                         // literals (from registers) and the offset are written with one byte per lane
                         const uint32_t L = cur - backtrack - lit_start;
                         const uint32_t extra = matching - 4 + backtrack;
                         const uint32_t cursor = cur + matching;
-                        if (L < 15 && extra < 15 && lit_start >= base && cursor - base < 32 && cap - opos >= 17 && cap >= opos) {
+                        if (L < 15 && extra < 15 && lit_start >= base && cap - opos >= 17 && cap >= opos) {
                             const uint32_t litb = __shfl_sync(LZF_FULL_MASK, v32, lit_start - base + lane - 1) & 0xffu;
                             const uint32_t offset = cur - cnd;
                             const uint32_t v = lane == 0 ? ((L << 4) | extra) : (lane <= L ? litb : (offset >> (8 * (lane - 1 - L))));
                             if (lane < L + 3) out[opos + lane] = (uint8_t)v;
                             opos += L + 3;
-                            lit_start = cursor;
-                            j = 0;
-                            const uint32_t l2 = cursor - 2 - base;                // table.replace(cursor - 2) :218
-                            if (!((endmask >> l2) & 1u)) ins |= 1u << l2;
-                            else late_q2 = cursor - 2;
-                            s = cursor - base;
-                            continue;
+                            if (cursor - base < 32) {
+                                // ... and the match ends inside the batch too: the parse goes on with its later lanes
+                                lit_start = cursor;
+                                j = 0;
+                                const uint32_t l2 = cursor - 2 - base;            // table.replace(cursor - 2) :218
+                                if (!((endmask >> l2) & 1u)) ins |= 1u << l2;
+                                else late_q2 = cursor - 2;
+                                s = cursor - base;
+                                continue;
+                            }
+                            emitted = true;                                       // the match leaves the batch: commit below
                         }
                     }
                     if (!fast) {
@@ -563,8 +568,8 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int n_smem_warps) {
                     // ---- write_group  :150-163,235-236
                     // literal bytes of a run that started inside this batch are the low bytes of the lanes' v32
                     const bool lits_in_regs = consecutive && lit_start >= base;
-                    if (!emit_sequence(out, opos, cap, in, lit_start, cur - backtrack - lit_start, cur - cnd, extra, false,
-                                       lits_in_regs, v32, lit_start - base)) {
+                    if (!emitted && !emit_sequence(out, opos, cap, in, lit_start, cur - backtrack - lit_start, cur - cnd, extra, false,
+                                                   lits_in_regs, v32, lit_start - base)) {
                         // the writer refused (:150-163 via NoPartialWrites): compress2 returns here, AFTER the
                         // table.replace(cursor - 2) of this match (:218) — a later block of the chain sees that state
                         status = LZF_WRITER_FULL;
