@@ -270,6 +270,11 @@ def test_sliced_input_feed(gpu, oracle, monkeypatch):
         assert np.array_equal(out2[f * bound:f * bound + int(fl[f])], out[f * bound:f * bound + int(fl[f])]), f
 
 
+def test_batched_host_frames_with_a_refused_frame(gpu, oracle):
+    import test_simt_kernels as T
+    T.test_batched_host_frames_with_a_refused_frame(gpu, oracle)
+
+
 def test_dependent_and_dictionary_frames_compress(gpu, oracle, issue15_input):
     """Compress side of SURVEY §8(f) rank 2: one warp carries the table through all blocks of a dependent
     frame; dictionaries prime the table.  Frames are byte-identical to the oracle's."""

@@ -109,6 +109,27 @@ def test_frame_compress_with_sliced_input_feed(emu, oracle, monkeypatch, scale=1
     assert emu.ctx.frame_decompress(frame, cap=len(data) + 16)[:3] == (0, 0, data)
 
 
+def test_batched_host_frames_with_a_refused_frame(emu, oracle):
+    """lzf_frames_compress assembles the frames before their content checksums are known and patches the 4-byte
+    trailers afterwards: a frame whose capacity is too small must stay a WriteError and must not be touched."""
+    from lz_fear_b200 import workloads as W
+    nf, fp = 4, 96 << 10
+    src = np.concatenate([W.text(fp, 31 + f).numpy() for f in range(nf)])
+    s, keep = N.make_settings(block_size=64 << 10)
+    bound = emu.ctx.frame_bound(s, fp)
+    out = np.full(nf * bound, 0xEE, dtype=np.uint8)
+    caps = np.full(nf, bound, np.uint64)
+    caps[2] = 100                                                   # far too small for frame 2
+    fl, fs = emu.ctx.frames_compress(src, np.arange(nf, dtype=np.uint64) * fp, np.full(nf, fp, np.uint64), out,
+                                     np.arange(nf, dtype=np.uint64) * bound, caps, s)
+    for f in range(nf):
+        if f == 2:
+            assert fs[f] == N.F_WRITE_ERROR == oracle.F_WRITE_ERROR and (out[f * bound + 100:(f + 1) * bound] == 0xEE).all()
+        else:
+            want = oracle.frame_compress(src[f * fp:(f + 1) * fp].tobytes(), block_size=64 << 10)
+            assert (int(fs[f]), out[f * bound:f * bound + int(fl[f])].tobytes()) == want, f
+
+
 def test_frames_roundtrip_and_bytes(emu, oracle):
     inputs = [b"", b"a", bytes(65536), parity.sample_inputs()[6], parity.sample_inputs()[7][:70001],
               parity.sample_inputs()[5] * 30]
