@@ -65,6 +65,12 @@ def lib():
         L.lzfo_compress_bound.argtypes = [C.c_size_t]
         L.lzfo_compress_block.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_uint, C.c_void_p, C.c_size_t,
                                           C.POINTER(C.c_size_t)]
+        L.lzfo_table_new.restype = C.c_void_p
+        L.lzfo_table_new.argtypes = [C.c_int, C.c_uint]
+        L.lzfo_table_free.argtypes = [C.c_void_p]
+        L.lzfo_table_offset.argtypes = [C.c_void_p, C.c_size_t]
+        L.lzfo_compress2.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t,
+                                     C.POINTER(C.c_size_t)]
         L.lzfo_decompress_raw.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                           C.c_size_t, C.POINTER(C.c_size_t)]
         L.lzfo_settings_default.argtypes = [C.POINTER(Settings)]
@@ -102,6 +108,32 @@ def compress_block(data, table=TABLE_U32, hashlog=12, cap=None):
     out = np.empty(max(cap, 1), dtype=np.uint8)
     w = C.c_size_t(0)
     st = lib().lzfo_compress_block(p, n, table, hashlog, out.ctypes.data, cap, C.byref(w))
+    return st, out[: w.value].tobytes()
+
+
+class Table:
+    """An EncoderTable that lives across compress2 calls (src/raw/compress/mod.rs:19-101)."""
+
+    def __init__(self, kind=TABLE_U32, hashlog=12):
+        self.h = lib().lzfo_table_new(kind, hashlog)
+
+    def offset(self, by):                      # EncoderTable::offset  :72-74
+        lib().lzfo_table_offset(self.h, by)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().lzfo_table_free(self.h)
+            self.h = None
+
+
+def compress2(data, cursor, table, cap=None):
+    """raw::compress2(input, cursor, &mut table, writer): input[..cursor] is match-only history."""
+    p, n, _k = _buf(data)
+    if cap is None:
+        cap = lib().lzfo_compress_bound(n)
+    out = np.empty(max(cap, 1), dtype=np.uint8)
+    w = C.c_size_t(0)
+    st = lib().lzfo_compress2(p, n, cursor, table.h, out.ctypes.data, cap, C.byref(w))
     return st, out[: w.value].tobytes()
 
 

@@ -56,6 +56,12 @@ struct lzf_slot {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_feed0 = nullptr, ev_feed1 = nullptr;
     uint32_t* h_seq = nullptr;          // pinned 1, 2, 3, ...: sources of the progress-word copies
     uint32_t* d_counter = nullptr;      // dynamic work counters (encode, decode)
+    // The block kernels of a slot share its work counters and table scratch, so two batched calls of one slot
+    // never run side by side: a launch on another stream than the previous one first waits for it (ev_last).
+    std::mutex launch_mu;
+    cudaEvent_t ev_last = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool has_last = false;
     Buf d_tables;                       // per-warp global hash tables (hashlog >= 14)
     Buf d_desc, h_desc;                 // descriptor arenas (device / pinned host)
     Buf d_res, h_res;                   // result arenas (device / pinned host)
@@ -157,6 +163,7 @@ extern "C" int lzf_create(int device, lzf_ctx** out) {
              cudaStreamCreateWithFlags(&sl.side, cudaStreamNonBlocking) == cudaSuccess &&
              cudaEventCreateWithFlags(&sl.ev_fork, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&sl.ev_join, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&sl.ev_last, cudaEventDisableTiming) == cudaSuccess &&
              cudaStreamCreateWithFlags(&sl.copy, cudaStreamNonBlocking) == cudaSuccess &&
              cudaEventCreateWithFlags(&sl.ev_feed0, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&sl.ev_feed1, cudaEventDisableTiming) == cudaSuccess &&
@@ -192,6 +199,7 @@ extern "C" void lzf_destroy(lzf_ctx* c) {
         if (sl.d_counter) cudaFree(sl.d_counter);
         if (sl.ev_fork) cudaEventDestroy(sl.ev_fork);
         if (sl.ev_join) cudaEventDestroy(sl.ev_join);
+        if (sl.ev_last) cudaEventDestroy(sl.ev_last);
         if (sl.stream) cudaStreamDestroy(sl.stream);
         if (sl.side) cudaStreamDestroy(sl.side);
     }
@@ -206,6 +214,21 @@ extern "C" size_t lzf_compress_bound(size_t n) { return n + n / 255 + 16; }
 // batched block calls (device pointers, asynchronous on `stream`)
 // ------------------------------------------------------------------------------------------------
 namespace {
+
+// Orders a block-kernel launch on stream `s` behind the previous one of the same slot (see lzf_slot::ev_last).
+// Held for the whole memset + launch + record sequence: host threads sharing a ctx serialise here.
+struct LaunchOrder {
+    lzf_slot* sl; cudaStream_t s; std::unique_lock<std::mutex> lock;
+    LaunchOrder(lzf_slot* slot, cudaStream_t stream) : sl(slot), s(stream), lock(slot->launch_mu) {}
+    cudaError_t begin() {
+        if (sl->has_last && sl->last_stream != s) return cudaStreamWaitEvent(s, sl->ev_last, 0);
+        return cudaSuccess;
+    }
+    cudaError_t end() {
+        sl->has_last = true; sl->last_stream = s;
+        return cudaEventRecord(sl->ev_last, s);
+    }
+};
 
 // Host-buffer pipeline: the plaintext is still being copied in (slice k of every block, then slice k + 1, ...) on
 // another stream while the block kernel runs; see EncodeArgs::progress.
@@ -247,6 +270,8 @@ int compress_blocks_impl(lzf_ctx* c, const uint8_t* d_in, const uint64_t* d_in_o
         if (rc) return rc;
         a.global_tables = (uint8_t*)cur_slot(c)->d_tables.p;
     }
+    LaunchOrder order(cur_slot(c), s);
+    LZF_CU(c, order.begin());
     LZF_CU(c, cudaMemsetAsync(cur_slot(c)->d_counter, 0, 4, s));
     if (feed) {
         const int rc = feed->start();
@@ -254,6 +279,7 @@ int compress_blocks_impl(lzf_ctx* c, const uint8_t* d_in, const uint64_t* d_in_o
         a.progress = feed->d_progress; a.slice_bytes = feed->slice_bytes;
     }
     LZF_LAUNCHED(c, lzf_launch_encode(&a, c->num_sms, s), 1);
+    LZF_CU(c, order.end());
     return LZF_SUCCESS;
 }
 
@@ -275,8 +301,11 @@ int decompress_blocks_impl(lzf_ctx* c, const uint8_t* d_in, const uint64_t* d_in
     a.out_len = d_out_len; a.status = d_status; a.xxh_plain = d_xxh_plain;
     a.prefix_abs = prefix_abs ? 1 : 0; a.wait_for = d_wait_for; a.done = d_done;
     a.work_counter = cur_slot(c)->d_counter + 16;
+    LaunchOrder order(cur_slot(c), s);
+    LZF_CU(c, order.begin());
     LZF_CU(c, cudaMemsetAsync(cur_slot(c)->d_counter + 16, 0, 4, s));
     LZF_LAUNCHED(c, lzf_launch_decode(&a, c->num_sms, s), 1);
+    LZF_CU(c, order.end());
     return LZF_SUCCESS;
 }
 
@@ -674,7 +703,7 @@ int frames_compress_core(lzf_ctx* c, const lzf_settings* s, const uint8_t* d_in,
                 sa.n = nstaged; sa.dict = (const uint8_t*)cur_slot(c)->d_dict.p; sa.dlen = (uint32_t)dlen;
                 sa.in = d_in; sa.src_off = (const uint64_t*)(d + o_ssrc); sa.len = (const uint32_t*)(d + o_slen);
                 sa.dst = (uint8_t*)cur_slot(c)->d_aux.p; sa.dst_off = (const uint64_t*)(d + o_sdst);
-                LZF_LAUNCHED(c, lzf_launch_stage_dict(&sa, st), 1);
+                LZF_LAUNCHED(c, lzf_launch_stage_dict(&sa, max_block_len, st), 1);
             }
             ch.prefix_len = (const uint32_t*)(d + o_pfx); ch.abs_base = (const uint32_t*)(d + o_abs);
             ch.prime_len = (const uint32_t*)(d + o_prime);
@@ -744,6 +773,10 @@ struct DecodeOut {          // optional extra per-frame results
     // waits for its results), so the D2H copy of the plaintext can start while the outcome is resolved
     // (argument: upper bound of the plaintext bytes the frames can decode to, from their block counts)
     std::function<int(uint64_t)> after_decode;
+    // nullable, one flag per frame: set when the frame's plaintext was (re)written AFTER after_decode ran — frames with
+    // short non-final blocks are decoded again at their exact positions — so a copy started by the hook holds the
+    // pass-1 placement of that frame and must be repeated
+    uint8_t* moved = nullptr;
 };
 
 int frames_decompress_core(lzf_ctx* c, const uint8_t* d_in, const uint64_t* in_off, const uint64_t* in_len,
@@ -1023,6 +1056,7 @@ int frames_decompress_core(lzf_ctx* c, const uint8_t* d_in, const uint64_t* in_o
         out_len[f] = o;
         hlen[f] = o;
         if (irregular && !dep) redo_frames.push_back(f);
+        if (extra.moved) extra.moved[f] = (irregular || exact) ? 1 : 0;
         if (extra.detail) extra.detail[f] = det;
         if (extra.consumed) extra.consumed[f] = consumed;
     }
@@ -1280,7 +1314,7 @@ extern "C" int lzf_frames_decompress_device(lzf_ctx* c, const uint8_t* d_in, con
                                             const uint64_t* out_cap, uint64_t* out_len, int32_t* status, int32_t* detail) {
     if (!c) return LZF_ERR_INVALID_ARG;
     LZF_CU(c, cudaSetDevice(c->device));
-    DecodeOut ex{nullptr, detail, nullptr};
+    DecodeOut ex{nullptr, detail, nullptr, nullptr};
     return frames_decompress_core(c, d_in, in_off, in_len, nframes, d_out, out_off, out_cap, out_len, status, ex, cur_slot(c)->stream);
 }
 
@@ -1321,7 +1355,8 @@ int decompress_chunk(lzf_ctx* c, lzf_slot& sl, uint32_t f0, uint32_t f1, const u
     // checksums run) on the main stream.  Whatever the resolution then finds irregular (short frames, errors,
     // re-decoded frames) is copied again, frame by frame, after both streams have drained.
     bool early_copy = false;
-    DecodeOut ex{consumed ? consumed + f0 : nullptr, detail ? detail + f0 : nullptr, nullptr};
+    std::vector<uint8_t> moved(n, 0);
+    DecodeOut ex{consumed ? consumed + f0 : nullptr, detail ? detail + f0 : nullptr, nullptr, moved.data()};
     if (lo.dense && lo.span) {
         ex.after_decode = [&](uint64_t expect) -> int {
             if (lo.span > expect + expect / 4) return LZF_SUCCESS;       // generous capacities: copy what was decoded, later
@@ -1340,6 +1375,11 @@ int decompress_chunk(lzf_ctx* c, lzf_slot& sl, uint32_t f0, uint32_t f1, const u
     for (uint32_t f = f0; f < f1 && full; f++) full = out_len[f] == dcap[f - f0];
     if (full) {
         if (lo.span && !early_copy) LZF_CU(c, cudaMemcpyAsync(out + lo.base, dout, lo.span, cudaMemcpyDeviceToHost, sl.stream));
+        // the early copy left while frames with short non-final blocks still sat at their pass-1 positions: those
+        // frames travel again, now that the side stream has drained and the exact re-decode is queued on the main one
+        for (uint32_t f = f0; f < f1 && early_copy; f++)
+            if (moved[f - f0] && out_len[f])
+                LZF_CU(c, cudaMemcpyAsync(out + out_off[f], dout + lo.dev_off[f - f0], out_len[f], cudaMemcpyDeviceToHost, sl.stream));
     } else {
         for (uint32_t f = f0; f < f1; f++)
             if (out_len[f])

@@ -298,9 +298,16 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int n_smem_warps) {
                     if (need > arrived) arrived = wait_arrival(a.progress, a.slice_bytes, need);
                 }
                 if constexpr (kPacked) {
-                    if (p_top + ab - last_sweep >= 65536u) {
-                        last_sweep = base + ab;
+                    // Every read of this batch must lie below last_sweep + 65536.  A sweep at `at` is exact only while
+                    // at <= last_sweep + 65536 (older slots would alias modulo 2^17) and no inserted position lies at or
+                    // beyond it — every insert so far is below last_sweep + 65536 (see the catch-up before the cursor - 2
+                    // insert) — and it must not lie beyond the next read, so a jump of the parse (the skip step, a refused
+                    // block in front of this one in a chain) is walked in steps of 65536.
+                    while (p_top + ab - last_sweep >= 65536u) {
+                        const bool reach = base + ab - last_sweep <= 65536u;
+                        last_sweep = reach ? base + ab : last_sweep + 65536u;
                         table.sweep(nslots, last_sweep);
+                        if (reach) break;
                     }
                 }
                 uint32_t v32 = 0, h = 0xffff0000u | lane;                     // unique key for idle lanes
@@ -594,6 +601,15 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int n_smem_warps) {
                         const uint32_t later = same & ins & ~lower_mask & ~(1u << lane);
                         if (((ins >> lane) & 1u) && later == 0) table.put(h, p + ab);
                         __syncwarp();
+                        if constexpr (kPacked) {
+                            // a long match: never let more than 65536 positions pass between sweeps (the table does
+                            // not change during a match, so the intermediate sweeps are exact), and keep the insert
+                            // below last_sweep + 65536
+                            while (q2 + ab - last_sweep >= 65536u) {
+                                last_sweep += 65536u;
+                                table.sweep(nslots, last_sweep);
+                            }
+                        }
                         if (lane == 0) {
                             uint32_t h2;
                             if (kHash4) h2 = hash4(ld4(in, q2), hashlog);

@@ -429,7 +429,7 @@ decode_blocks_kernel(DecodeArgs a) {
                 // (decompress.rs:83-89) or that would pass the output limit / capacity — the slow path replays it
                 // and reports the error exactly like the reference — and before the staging budget runs out.
                 const bool bad = lane < cnt && (off == 0u || (uint64_t)off > (uint64_t)dstp + s.plen ||
-                                                (uint64_t)olen0 + inc > bound || (inc > kStageBudget && lane > 0));
+                                                s.olen + inc > bound || (inc > kStageBudget && lane > 0));
                 const uint32_t fb = __ballot_sync(LZF_FULL_MASK, bad);
                 uint32_t in_end = p;
                 if (fb) {

@@ -288,9 +288,10 @@ extern "C" int lzf_launch_xxh32_stripes(const uint8_t* data, uint64_t nstripes, 
     LZF_LAUNCH(lzf::xxh32_stripes_kernel, 1, 32, 0, s, data, nstripes, acc);
     return (int)cudaGetLastError();
 }
-extern "C" int lzf_launch_stage_dict(const lzf::StageArgs* a, cudaStream_t s) {
+extern "C" int lzf_launch_stage_dict(const lzf::StageArgs* a, uint32_t max_block_len, cudaStream_t s) {
     if (!a->n) return 0;
-    uint32_t slices = 64;                      // blocks are at most 4 MiB here (16 MiB for raw callers: loop below covers it)
+    uint32_t slices = (max_block_len + lzf::kSliceBytes - 1) / lzf::kSliceBytes;   // one CTA per 64 KiB of the longest block
+    if (slices == 0) slices = 1;
     dim3 grid(a->n, slices);
     LZF_LAUNCH(lzf::stage_dict_kernel, grid, 256, 0, s, *a);
     return (int)cudaGetLastError();

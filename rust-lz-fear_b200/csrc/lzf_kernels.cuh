@@ -88,7 +88,7 @@ int lzf_launch_decode(const lzf::DecodeArgs* args, int num_sms, cudaStream_t str
 int lzf_launch_xxh32_ranges(const uint8_t* data, const uint64_t* off, const uint64_t* len, uint32_t nranges,
                             uint32_t* hash, cudaStream_t s);
 int lzf_launch_xxh32_stripes(const uint8_t* data, uint64_t nstripes, uint32_t* acc, cudaStream_t s);
-int lzf_launch_stage_dict(const lzf::StageArgs* a, cudaStream_t s);
+int lzf_launch_stage_dict(const lzf::StageArgs* a, uint32_t max_block_len, cudaStream_t s);
 int lzf_launch_layout(const lzf::LayoutArgs* a, cudaStream_t s);
 int lzf_launch_assemble(const lzf::AssembleArgs* a, uint32_t max_block_len, cudaStream_t s);
 int lzf_launch_walk(const lzf::WalkArgs* a, cudaStream_t s);

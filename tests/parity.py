@@ -165,3 +165,63 @@ def check_frame_decode_errors(backend, oracle, frames, dependent_ok=True, dictio
             assert cons == ocons
             n_ok += 1
     return n_ok
+
+
+def long_match_inputs():
+    """a match longer than 64 KiB moves the cursor more than 65 536 positions between two sweeps of the
+    packed 17-bit table; slots 128 KiB back must not come back to life (periodic data would match there)."""
+    rng = np.random.default_rng(32768)
+    x = rng.integers(0, 256, 32768, dtype=np.uint8).tobytes()
+    y = rng.integers(0, 256, 50000, dtype=np.uint8).tobytes()
+    return [x * 5 + b"abc" + x, x * 3 + b"abc" + x, x * 9 + b"q" + x * 2, y * 4 + b"zz" + y + b"\0" * 140000 + y,
+            b"\0" * 200000 + x + b"\0" * 70000 + x, (x[:1000] * 70) + x[:40000] + b"#" + (x[:1000] * 200)]
+
+
+def short_block_frames(oracle, dependent, content_checksum, sizes=(1000, 2000, 500)):
+    """A frame whose NON-FINAL blocks are short (what LZ4F_flush / autoFlush writers produce) -> (frame, plaintext)."""
+    import struct
+    flg = 0x40 | (0 if dependent else 0x20) | (0x04 if content_checksum else 0)
+    hdr = bytes([0x04, 0x22, 0x4D, 0x18, flg, 0x40])
+    hdr += bytes([(oracle.xxh32(hdr[4:]) >> 8) & 0xFF])
+    plain = b"".join(W.text(n, seed=700 + i).numpy().tobytes() for i, n in enumerate(sizes))
+    body, pos = b"", 0
+    table = oracle.Table()
+    for n in sizes:
+        if dependent:       # one table over the whole (short) stream: blocks reach back into the earlier ones
+            st, comp = oracle.compress2(plain[:pos + n], pos, table)
+        else:
+            st, comp = oracle.compress_block(plain[pos:pos + n])
+        assert st == 0
+        body += struct.pack("<I", len(comp)) + comp
+        pos += n
+    frame = hdr + body + struct.pack("<I", 0)
+    if content_checksum:
+        frame += struct.pack("<I", oracle.xxh32(plain))
+    return frame, plain
+
+
+def check_short_block_frames(backend, oracle):
+    """host-buffer decompress with cap == the true decoded size must deliver the exact placement,
+    through the single-frame and the batched entry point."""
+    frames, plains = [], []
+    for dep in (False, True):
+        for cc in (False, True):
+            fr, pl = short_block_frames(oracle, dep, cc)
+            orc, odet, oplain, ocons = oracle.frame_decompress(fr, cap=len(pl))
+            assert (orc, oplain) == (0, pl)
+            st, det, plain, cons = backend.ctx.frame_decompress(fr, cap=len(pl))
+            assert (st, det, plain, cons) == (0, 0, pl, len(fr)), (dep, cc)
+            frames.append(fr); plains.append(pl)
+    # regular frames around them, all in one batched call with a dense output layout and exact capacities
+    reg = W.text(70000, seed=5).numpy().tobytes()
+    frames.insert(1, oracle.frame_compress(reg, block_size=64 << 10)[1]); plains.insert(1, reg)
+    frames.append(oracle.frame_compress(reg[:3000], block_size=64 << 10)[1]); plains.append(reg[:3000])
+    fl = np.array([len(f) for f in frames], dtype=np.uint64)
+    fo = np.zeros(len(frames), dtype=np.uint64); fo[1:] = np.cumsum(fl)[:-1]
+    pl_len = np.array([len(p) for p in plains], dtype=np.uint64)
+    po = np.zeros(len(frames), dtype=np.uint64); po[1:] = np.cumsum(pl_len)[:-1]
+    for _ in range(2):          # the second call sees the first call's bytes as stale device scratch
+        back = np.full(int(pl_len.sum()), 0xEE, dtype=np.uint8)
+        olen, st, det = backend.ctx.frames_decompress(np.frombuffer(b"".join(frames), dtype=np.uint8), fo, fl, back, po, pl_len)
+        assert not st.any() and (olen == pl_len).all()
+        assert back.tobytes() == b"".join(plains)

@@ -292,3 +292,16 @@ def test_dependent_and_dictionary_frames_compress(gpu, oracle, issue15_input):
         assert (st, frame) == oracle.frame_compress(data, **kw), sorted(kw)
         d = kw.get("dictionary", b"")
         assert gpu.ctx.frame_decompress(frame, dictionary=d, cap=len(data) + 16)[:3] == (0, 0, data)
+
+
+def test_packed17_long_matches_never_alias(gpu, oracle):
+    inputs = parity.long_match_inputs()
+    rng = np.random.default_rng(4)
+    x = rng.integers(0, 256, 100000, dtype=np.uint8).tobytes()
+    inputs += [x * 30 + b"!" + x * 11, bytes(3 << 20) + x + bytes(1 << 20) + x]      # 4 MiB-class blocks
+    parity.check_raw_compress(gpu, oracle, inputs, caps=False)
+    parity.check_batched_blocks(gpu, oracle, inputs, use_torch_device="cuda", max_block_len=max(len(b) for b in inputs))
+
+
+def test_short_nonfinal_blocks_with_exact_capacity(gpu, oracle):
+    parity.check_short_block_frames(gpu, oracle)

@@ -350,3 +350,14 @@ def test_dictionary_frames_compress(emu, oracle):                       # compre
                 orc, oframe = oracle.frame_compress(data, dictionary=d, dictionary_id=9, **kw)
                 assert (st, frame) == (orc, oframe), (len(d), kw, len(data))
                 assert emu.ctx.frame_decompress(frame, dictionary=d, cap=len(data) + 16)[:3] == (0, 0, data)
+
+
+def test_packed17_long_matches_never_alias(emu, oracle):
+    parity.check_raw_compress(emu, oracle, parity.long_match_inputs(), caps=False)
+    # the same through the batched call with the max_block_len promise (packed 17-bit slots in the big CTA)
+    inputs = parity.long_match_inputs()
+    parity.check_batched_blocks(emu, oracle, inputs, max_block_len=max(len(b) for b in inputs))
+
+
+def test_short_nonfinal_blocks_with_exact_capacity(emu, oracle):
+    parity.check_short_block_frames(emu, oracle)
