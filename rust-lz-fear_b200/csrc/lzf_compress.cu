@@ -32,6 +32,20 @@
 #include <stdlib.h>
 #include <type_traits>
 
+// encoder path counters of the CPU test harness (tests/simt): which way the batches and sequences went
+#if defined(LZF_SIMT_EMU) && defined(LZF_ENC_STATS)
+extern "C" { uint64_t lzf_enc_stats[32]; }
+#define LZF_STAT(i) do { if (lane_id() == 0) lzf_enc_stats[i]++; } while (0)
+#else
+#define LZF_STAT(i) do { } while (0)
+#endif
+#ifndef LZF_ENC_LOOKAHEAD
+#define LZF_ENC_LOOKAHEAD 1
+#endif
+#ifndef LZF_ENC_PARALLEL
+#define LZF_ENC_PARALLEL 1
+#endif
+
 namespace lzf {
 
 // offset of the j-th probe of a literal run from the run start: the closed form of
@@ -335,6 +349,18 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int n_smem_warps) {
                     h = kHash4 ? hash4(v32, hashlog) : hash5(v32, (w1 >> sh) & 0xffu, hashlog);
                     tdist = table.dist(h, p + ab);                            // table.replace :196 (read half)
                     tcand = p - tdist;
+#if LZF_ENC_LOOKAHEAD
+                    // LOOK-AHEAD: the next batch starts a few dozen bytes further on and will fetch the candidates of
+                    // ITS positions from wherever they are — for windows that do not fit L2 that is a DRAM round trip
+                    // on the warp's critical path.  Each lane therefore also hashes the position 32 further on (its
+                    // bytes and its table slot arrive in the same round trips as this batch's) and asks L2 for that
+                    // candidate's line now.  Purely a hint: the slot may still change, nothing waits for it.
+                    if (!kHash4 && consecutive && len - p >= 32 + 12) {
+                        const uint32_t w8 = __ldg(w + 8), w9 = __ldg(w + 9);
+                        const uint32_t d2 = table.dist(hash5(__funnelshift_r(w8, w9, sh), (w9 >> sh) & 0xffu, hashlog), p + 32 + ab);
+                        if (d2 - 1u < 0xffffu && d2 <= p + 32) prefetch_l2(in + (p + 32 - d2));
+                    }
+#endif
                 }
                 const uint32_t same = __match_any_sync(LZF_FULL_MASK, h);
                 // table candidate: addressable (:200-201) and >= MINMATCH equal bytes (:206)
@@ -385,7 +411,7 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int n_smem_warps) {
                 }
                 uint32_t ins = 0;       // lanes whose probe (or cursor-2 insert) has happened, in order
                 uint32_t s = 0;         // first lane of the current run inside this batch
-                bool committed = false;
+                uint32_t left_q2 = 0xffffffffu;   // the match left the batch: its cursor-2 insert, applied behind the batch's own
                 uint32_t late_q2 = 0xffffffffu;   // a cursor-2 insert that falls on a lane without a hash (last 11 bytes)
                 // Batches in which no two lanes share a table slot (the common case) need no per-sequence
                 // candidate resolution at all: who matches is one ballot per batch, and each further sequence
@@ -394,7 +420,94 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int n_smem_warps) {
                 const uint32_t okmask = __ballot_sync(LZF_FULL_MASK, t_ok);
                 // winner's candidate distance and extension summary travel in one word
                 const uint32_t packed_w = tdist | (fsum << 16);
+#if LZF_ENC_PARALLEL
+                // PARALLEL RESOLVE (consecutive batches).  A lane is GOOD when its table candidate matches, no earlier
+                // lane of the batch shares its table slot (so the candidate cannot change with the parse) and its
+                // extension summary is complete; everything such a lane would emit is then known from its own
+                // registers.  The parse walks from run start to winner to match end with one shuffle per sequence and
+                // only scalar arithmetic; the sequences found are written afterwards, all at once: every literal lane
+                // stores its own byte, every winner its token and offset.  The walk stops in front of anything else
+                // (an end-of-block lane, a lane whose slot an earlier lane shares, a long match or literal run): the
+                // serial step below resolves that one sequence and the walk resumes behind it.
+                //   pinfo: bits 0..5 lane where the match ends (<= 47), 6..8 backtrack summary, 16..31 candidate distance
+                uint32_t pinfo = 0;
+                {
+                    const bool clean = (same & lower_mask) == 0;
+                    if (consecutive && t_ok && clean && (fsum & 0x300u) == 0x300u) {
+                        const uint32_t fm = fsum & 31u, limit = len - 5 - p;
+                        if (fm < 16 || limit <= 16) pinfo = (lane + min(fm, limit)) | (((fsum >> 5) & 7u) << 6) | (tdist << 16);
+                    }
+                }
+                const uint32_t goodmask = __ballot_sync(LZF_FULL_MASK, pinfo != 0);
+                // lanes the walk cannot pass without looking: matches, the end of the block, shared slots
+                const uint32_t trigmask = okmask | endmask | (no_dups ? 0u : __ballot_sync(LZF_FULL_MASK, (same & lower_mask) != 0));
+#endif
                 for (;;) {
+#if LZF_ENC_PARALLEL
+                    if (consecutive && s < 32 && cap >= opos && cap - opos >= 128) {
+                        uint32_t W = 0, orel = 0, mine = 0, e = 0, l_first = 0;
+                        uint32_t pre = base + s - lit_start;          // literals of the current run in front of lane s
+                        const uint32_t pre0 = pre, lit0 = lit_start;
+                        int end = 0;                                  // 0: stopped in front of lane w, 1: no trigger left, 2: match left the batch
+                        for (;;) {
+                            const uint32_t t = trigmask & ~((1u << s) - 1u);
+                            if (t == 0) { end = 1; break; }
+                            const uint32_t w = __ffs(t) - 1;
+                            if (!((goodmask >> w) & 1u)) break;
+                            const uint32_t info = __shfl_sync(LZF_FULL_MASK, pinfo, w);
+                            const uint32_t nb = (info >> 6) & 7u;
+                            const uint32_t lraw = w - s + pre;
+                            const uint32_t max_back = min(lraw, base + w - (info >> 16));       // :211-214
+                            if (nb == 4 && max_back > 4) break;                                   // backtrack beyond the summary
+                            const uint32_t bt = min(nb, max_back);
+                            const uint32_t L = lraw - bt, extra = (info & 63u) - w - 4 + bt;
+                            if (L >= 15 || extra >= 15) break;                                    // length extensions: serial step
+                            e = info & 63u;
+                            if (lane == w) mine = orel | (s << 8) | (pre << 13) | (L << 18) | (extra << 22);   // pre <= 18 here
+                            if (W == 0) l_first = L;
+                            W |= 1u << w;
+                            orel += L + 3;
+                            ins |= ((2u << w) - 1u) & ~((1u << s) - 1u);                         // probes s..w happened
+                            pre = 0;
+                            LZF_STAT(4);
+                            if (e >= 32) { end = 2; break; }
+                            const uint32_t l2 = e - 2;                                            // table.replace(cursor - 2) :218
+                            if (!((endmask >> l2) & 1u)) ins |= 1u << l2;
+                            else late_q2 = base + l2;
+                            s = e;
+                        }
+                        if (W) {
+                            // write_group :150-163 of every sequence found, one byte per lane and role
+                            uint8_t* o = out + opos;
+                            const uint32_t wm = W & ~lower_mask;                                  // winners at or above this lane
+                            const uint32_t m = __shfl_sync(LZF_FULL_MASK, mine, wm ? __ffs(wm) - 1 : 0);
+                            if (wm) {
+                                const uint32_t sw = (m >> 8) & 31u, idx = lane - sw + ((m >> 13) & 31u);
+                                if (lane >= sw && idx < ((m >> 18) & 15u)) o[(m & 0xffu) + 1 + idx] = (uint8_t)v32;
+                            }
+                            if ((W >> lane) & 1u) {
+                                const uint32_t L = (mine >> 18) & 15u, tok = mine & 0xffu;
+                                o[tok] = (uint8_t)((L << 4) | ((mine >> 22) & 15u));
+                                o[tok + 1 + L] = (uint8_t)tdist;
+                                o[tok + 2 + L] = (uint8_t)(tdist >> 8);
+                            }
+                            // literals of the first run that lie in front of the batch
+                            if (lane < min(pre0, l_first)) o[1 + lane] = __ldg(in + lit0 + lane);
+                            opos += orel;
+                            lit_start = base + (end == 2 ? e : s);
+                            j = 0;
+                        }
+                        if (end == 1) {
+                            ins |= ~((1u << s) - 1u);                         // every lane from s on probed and missed
+                            j += 32 - s;
+                            LZF_STAT(5);
+                            break;
+                        }
+                        if (end == 2) { left_q2 = base + e - 2; LZF_STAT(6); break; }
+                        LZF_STAT(7);
+                    }
+#endif
+                    LZF_STAT(8);
                     uint32_t trig, w, cur, cnd, wsum;
                     if (no_dups) {
                         trig = (okmask | endmask) & ~((1u << s) - 1u);
@@ -596,10 +709,18 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int n_smem_warps) {
                         s = cursor - base;
                         continue;                                             // next sequence of the same batch
                     }
-                    // the match left the batch: commit, then insert cursor - 2 behind everything committed
-                    {
-                        const uint32_t later = same & ins & ~lower_mask & ~(1u << lane);
-                        if (((ins >> lane) & 1u) && later == 0) table.put(h, p + ab);
+                    // the match left the batch: its cursor - 2 insert goes behind everything the batch commits
+                    left_q2 = q2;
+                    break;
+                }
+                {
+                    // commit: last inserted lane of each slot wins (mem::swap order, :64-71)
+                    const uint32_t later = same & ins & ~lower_mask & ~(1u << lane);
+                    if (((ins >> lane) & 1u) && later == 0) table.put(h, p + ab);
+                    // ... then the cursor - 2 insert of a match that left the batch, or of one that ended on a lane past
+                    // the 12-byte rule (such a lane has no hash; the two never happen in the same batch)
+                    const uint32_t q2 = left_q2 != 0xffffffffu ? left_q2 : late_q2;
+                    if (q2 != 0xffffffffu) {
                         __syncwarp();
                         if constexpr (kPacked) {
                             // a long match: never let more than 65536 positions pass between sweeps (the table does
@@ -616,23 +737,6 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int n_smem_warps) {
                             else if (len - q2 >= 8) h2 = hash5(ld4(in, q2), in[q2 + 4], hashlog);
                             else h2 = 0;                                      // :43 unwrap_or(0) -> hash of 0
                             table.put(h2, q2 + ab);
-                        }
-                        committed = true;
-                    }
-                    break;
-                }
-                if (!committed) {
-                    // last inserted lane of each slot wins (mem::swap order, :64-71)
-                    const uint32_t later = same & ins & ~lower_mask & ~(1u << lane);
-                    if (((ins >> lane) & 1u) && later == 0) table.put(h, p + ab);
-                    if (late_q2 != 0xffffffffu) {
-                        __syncwarp();
-                        if (lane == 0) {
-                            uint32_t h2;
-                            if (kHash4) h2 = hash4(ld4(in, late_q2), hashlog);
-                            else if (len - late_q2 >= 8) h2 = hash5(ld4(in, late_q2), in[late_q2 + 4], hashlog);
-                            else h2 = 0;                                          // :43 unwrap_or(0) -> hash of 0
-                            table.put(h2, late_q2 + ab);
                         }
                     }
                 }
