@@ -20,6 +20,32 @@ F_INVALID_BLOCK_SIZE, F_WRITE_ERROR, F_PANIC = 20, 21, 22
 TABLE_U32, TABLE_U16 = 0, 1
 
 
+_NATIVE_SO = os.path.join(_DIR, "_native", "liblzf_oracle_native.so")
+_native = None
+
+
+def native_lib():
+    """The same sources built with -march=native ON THIS MACHINE (bench.py's CPU-baseline legs): oracle/_native is
+    never shipped between machines (.gpurunignore), so the first call on a box compiles it there."""
+    global _native
+    if _native is None:
+        src = [os.path.join(_DIR, f) for f in ("lzf_oracle.c", "lzf_oracle.h")]
+        if not (os.path.exists(_NATIVE_SO) and all(os.path.getmtime(_NATIVE_SO) >= os.path.getmtime(x) for x in src)):
+            subprocess.check_call(["make", "-C", _DIR, "-s", "-B", "_native/liblzf_oracle_native.so"])
+        _native = C.CDLL(_NATIVE_SO)
+        _declare_mt(_native)
+    return _native
+
+
+def _declare_mt(L):
+    L.lzfo_compress_blocks_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.lzfo_decompress_blocks_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.lzfo_liblz4_blocks_mt.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+
+
 def build(force=False):
     src = [os.path.join(_DIR, f) for f in ("lzf_oracle.c", "lzf_oracle.h")]
     if (not force and os.path.exists(_SO)
@@ -81,10 +107,7 @@ def lib():
         L.lzfo_frame_parse_header.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(FrameInfo), C.POINTER(C.c_int)]
         L.lzfo_frame_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                             C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
-        L.lzfo_compress_blocks_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint, C.c_void_p,
-                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
-        L.lzfo_decompress_blocks_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
-                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        _declare_mt(L)
     return _lib
 
 
@@ -208,21 +231,33 @@ def parse_header(data):
     return rc, d.value, info
 
 
-def compress_blocks_mt(inp, in_off, in_len, out, out_off, hashlog=12, nthreads=1):
+def compress_blocks_mt(inp, in_off, in_len, out, out_off, hashlog=12, nthreads=1, native=False):
     nb = len(in_len)
     out_len = np.zeros(nb, dtype=np.uint32)
     status = np.zeros(nb, dtype=np.int32)
-    lib().lzfo_compress_blocks_mt(inp.ctypes.data, in_off.ctypes.data, in_len.ctypes.data, nb, hashlog,
+    (native_lib() if native else lib()).lzfo_compress_blocks_mt(inp.ctypes.data, in_off.ctypes.data, in_len.ctypes.data, nb, hashlog,
                                   out.ctypes.data, out_off.ctypes.data, out_len.ctypes.data, status.ctypes.data,
                                   nthreads)
     return out_len, status
 
 
-def decompress_blocks_mt(inp, in_off, in_len, out, out_off, out_cap, out_limit, nthreads=1):
+def decompress_blocks_mt(inp, in_off, in_len, out, out_off, out_cap, out_limit, nthreads=1, native=False):
     nb = len(in_len)
     out_len = np.zeros(nb, dtype=np.uint32)
     status = np.zeros(nb, dtype=np.int32)
-    lib().lzfo_decompress_blocks_mt(inp.ctypes.data, in_off.ctypes.data, in_len.ctypes.data, nb, out.ctypes.data,
+    (native_lib() if native else lib()).lzfo_decompress_blocks_mt(inp.ctypes.data, in_off.ctypes.data, in_len.ctypes.data, nb, out.ctypes.data,
                                     out_off.ctypes.data, out_cap.ctypes.data, out_limit.ctypes.data,
                                     out_len.ctypes.data, status.ctypes.data, nthreads)
     return out_len, status
+
+
+def liblz4_blocks_mt(compress, inp, in_off, in_len, out, out_off, out_cap, nthreads=1, native=True):
+    """C lz4 (liblz4.so.1) over the same blocks on the same thread pool -> (out_len, status), or None when the
+    library is not installed."""
+    nb = len(in_len)
+    out_len = np.zeros(nb, dtype=np.uint32)
+    status = np.zeros(nb, dtype=np.int32)
+    rc = (native_lib() if native else lib()).lzfo_liblz4_blocks_mt(
+        1 if compress else 0, inp.ctypes.data, in_off.ctypes.data, in_len.ctypes.data, nb, out.ctypes.data,
+        out_off.ctypes.data, out_cap.ctypes.data, out_len.ctypes.data, status.ctypes.data, nthreads)
+    return None if rc != 0 else (out_len, status)

@@ -381,7 +381,25 @@ int lzfo_decompress_raw(const uint8_t* in, size_t n, const uint8_t* prefix, size
                 memcpy(out + olen, prefix + plen - need, take);
                 k = take;
             }
-            for (; k < mlen; k++) out[olen + k] = out[olen + k - offset];
+            /* the reference's own fast paths (:100-136), so that the CPU baseline is not slower than the crate:
+             * memset for offset 1, memcpy when the ranges do not overlap, a 16-byte pattern buffer for offsets
+             * 2 / 4 / 8, single bytes otherwise.  Every arm writes the bytes of the sequential loop. */
+            uint8_t* dst = out + olen + k;
+            const size_t rest = mlen - k;
+            if (rest == 0) {
+            } else if (offset == 1) {                          /* :102 */
+                memset(dst, dst[-1], rest);
+            } else if (rest <= offset) {                       /* :104-111 */
+                memcpy(dst, dst - offset, rest);
+            } else if (offset == 2 || offset == 4 || offset == 8) {   /* :112-127 */
+                uint8_t buf[16];
+                for (size_t i = 0; i < 16; i += offset) memcpy(buf + i, dst - offset, offset);
+                size_t i = 0;
+                for (; i + 16 <= rest; i += 16) memcpy(dst + i, buf, 16);
+                if (i < rest) memcpy(dst + i, buf, rest - i);
+            } else {                                           /* :128-135 */
+                for (size_t i = 0; i < rest; i++) dst[i] = dst[(ptrdiff_t)i - (ptrdiff_t)offset];
+            }
         }
         olen += mlen;
     }
@@ -745,4 +763,58 @@ int lzfo_decompress_blocks_mt(const uint8_t* in, const uint64_t* in_off, const u
     j.out = out; j.out_off = out_off; j.out_cap = out_cap; j.out_limit = out_limit;
     j.out_len = out_len; j.status = status;
     return mt_run(&j, nthreads);
+}
+
+/* ------------------------------------------------------------------------ */
+/* second CPU bar: C lz4 (liblz4.so.1, dlopen'ed — the image ships no header) */
+/* README.md:11,18 places lz-fear at ~1x C for decode and 2-3x slower for     */
+/* encode, so this is the stricter bar.  Same thread pool, one block per task */
+/* ------------------------------------------------------------------------ */
+#include <dlfcn.h>
+typedef int (*lz4_compress_fn)(const char*, char*, int, int);
+typedef int (*lz4_decompress_fn)(const char*, char*, int, int);
+typedef struct {
+    lz4_compress_fn comp; lz4_decompress_fn decomp;
+    const uint8_t* in; const uint64_t* in_off; const uint32_t* in_len; uint32_t nblocks;
+    uint8_t* out; const uint64_t* out_off; const uint32_t* out_cap; uint32_t* out_len; int32_t* status;
+    volatile uint32_t next;
+} lz4_job;
+
+static void* lz4_worker(void* arg) {
+    lz4_job* j = (lz4_job*)arg;
+    for (;;) {
+        uint32_t b = __atomic_fetch_add(&j->next, 1, __ATOMIC_RELAXED);
+        if (b >= j->nblocks) break;
+        int r;
+        if (j->comp) r = j->comp((const char*)j->in + j->in_off[b], (char*)j->out + j->out_off[b], (int)j->in_len[b], (int)j->out_cap[b]);
+        else r = j->decomp((const char*)j->in + j->in_off[b], (char*)j->out + j->out_off[b], (int)j->in_len[b], (int)j->out_cap[b]);
+        j->out_len[b] = r > 0 ? (uint32_t)r : 0;
+        j->status[b] = r > 0 ? 0 : 1;       /* compress: 0 = does not fit (stored block); decompress: < 0 = malformed */
+    }
+    return NULL;
+}
+
+/* returns 0, or -1 when liblz4.so.1 is not installed */
+int lzfo_liblz4_blocks_mt(int compress, const uint8_t* in, const uint64_t* in_off, const uint32_t* in_len, uint32_t nblocks,
+                          uint8_t* out, const uint64_t* out_off, const uint32_t* out_cap, uint32_t* out_len,
+                          int32_t* status, int nthreads) {
+    static void* h = NULL;
+    if (!h) h = dlopen("liblz4.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return -1;
+    lz4_job j;
+    memset(&j, 0, sizeof(j));
+    if (compress) j.comp = (lz4_compress_fn)dlsym(h, "LZ4_compress_default");
+    else j.decomp = (lz4_decompress_fn)dlsym(h, "LZ4_decompress_safe");
+    if (!j.comp && !j.decomp) return -1;
+    j.in = in; j.in_off = in_off; j.in_len = in_len; j.nblocks = nblocks;
+    j.out = out; j.out_off = out_off; j.out_cap = out_cap; j.out_len = out_len; j.status = status;
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 512) nthreads = 512;
+    pthread_t th[512];
+    int started = 0;
+    for (int i = 1; i < nthreads; i++)
+        if (pthread_create(&th[started], NULL, lz4_worker, &j) == 0) started++;
+    lz4_worker(&j);
+    for (int i = 0; i < started; i++) pthread_join(th[i], NULL);
+    return 0;
 }

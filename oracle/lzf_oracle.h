@@ -158,6 +158,13 @@ int lzfo_decompress_blocks_mt(const uint8_t* in, const uint64_t* in_off, const u
                               const uint32_t* out_cap, const uint32_t* out_limit, uint32_t* out_len,
                               int32_t* status, int nthreads);
 
+/* second CPU bar: C lz4 1.9.x (liblz4.so.1 via dlopen) on the same thread pool.  compress != 0:
+ * LZ4_compress_default into out_cap[b] bytes (status 1 = does not fit); else LZ4_decompress_safe.
+ * Returns -1 when the library is not installed. */
+int lzfo_liblz4_blocks_mt(int compress, const uint8_t* in, const uint64_t* in_off, const uint32_t* in_len, uint32_t nblocks,
+                          uint8_t* out, const uint64_t* out_off, const uint32_t* out_cap, uint32_t* out_len,
+                          int32_t* status, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -364,9 +364,6 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, 
 __device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void prefetch_l2(const void* gmem_src) {     // one line towards L2, no register, no wait
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(gmem_src) : "memory");
-}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done;
     do {
@@ -380,7 +377,6 @@ __device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) { return __reduce_m
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t) { *bar = 0; }
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t*) { memcpy(smem_dst, gmem_src, bytes); }
 __device__ __forceinline__ void bulk_prefetch_l2(const void*, uint32_t) {}
-__device__ __forceinline__ void prefetch_l2(const void*) {}
 __device__ __forceinline__ void mbar_wait(uint64_t*, uint32_t) { __syncwarp(); }   // the issuing lane has copied by then
 __device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) {
     for (int s = 16; s; s >>= 1) { const uint32_t o = __shfl_xor_sync(LZF_FULL_MASK, v, s); v = o > v ? o : v; }

@@ -39,12 +39,10 @@ extern "C" { uint64_t lzf_enc_stats[32]; }
 #else
 #define LZF_STAT(i) do { } while (0)
 #endif
-#ifndef LZF_ENC_LOOKAHEAD
-#define LZF_ENC_LOOKAHEAD 1
+#ifndef LZF_ENC_WALK
+#define LZF_ENC_WALK 1          // 0: the round-1 resolve loop only (A/B builds)
 #endif
-#ifndef LZF_ENC_PARALLEL
-#define LZF_ENC_PARALLEL 1
-#endif
+
 
 namespace lzf {
 
@@ -349,18 +347,6 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int n_smem_warps) {
                     h = kHash4 ? hash4(v32, hashlog) : hash5(v32, (w1 >> sh) & 0xffu, hashlog);
                     tdist = table.dist(h, p + ab);                            // table.replace :196 (read half)
                     tcand = p - tdist;
-#if LZF_ENC_LOOKAHEAD
-                    // LOOK-AHEAD: the next batch starts a few dozen bytes further on and will fetch the candidates of
-                    // ITS positions from wherever they are — for windows that do not fit L2 that is a DRAM round trip
-                    // on the warp's critical path.  Each lane therefore also hashes the position 32 further on (its
-                    // bytes and its table slot arrive in the same round trips as this batch's) and asks L2 for that
-                    // candidate's line now.  Purely a hint: the slot may still change, nothing waits for it.
-                    if (!kHash4 && consecutive && len - p >= 32 + 12) {
-                        const uint32_t w8 = __ldg(w + 8), w9 = __ldg(w + 9);
-                        const uint32_t d2 = table.dist(hash5(__funnelshift_r(w8, w9, sh), (w9 >> sh) & 0xffu, hashlog), p + 32 + ab);
-                        if (d2 - 1u < 0xffffu && d2 <= p + 32) prefetch_l2(in + (p + 32 - d2));
-                    }
-#endif
                 }
                 const uint32_t same = __match_any_sync(LZF_FULL_MASK, h);
                 // table candidate: addressable (:200-201) and >= MINMATCH equal bytes (:206)
@@ -420,22 +406,23 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int n_smem_warps) {
                 const uint32_t okmask = __ballot_sync(LZF_FULL_MASK, t_ok);
                 // winner's candidate distance and extension summary travel in one word
                 const uint32_t packed_w = tdist | (fsum << 16);
-#if LZF_ENC_PARALLEL
-                // PARALLEL RESOLVE (consecutive batches).  A lane is GOOD when its table candidate matches, no earlier
-                // lane of the batch shares its table slot (so the candidate cannot change with the parse) and its
-                // extension summary is complete; everything such a lane would emit is then known from its own
-                // registers.  The parse walks from run start to winner to match end with one shuffle per sequence and
-                // only scalar arithmetic; the sequences found are written afterwards, all at once: every literal lane
-                // stores its own byte, every winner its token and offset.  The walk stops in front of anything else
-                // (an end-of-block lane, a lane whose slot an earlier lane shares, a long match or literal run): the
-                // serial step below resolves that one sequence and the walk resumes behind it.
-                //   pinfo: bits 0..5 lane where the match ends (<= 47), 6..8 backtrack summary, 16..31 candidate distance
+#if LZF_ENC_WALK
+                // TIGHT WALK (consecutive batches).  A lane is GOOD when its table candidate matches, no earlier lane of
+                // the batch shares its table slot (so the candidate cannot change with the parse) and its extension
+                // summary is complete and short: everything such a lane would emit is then known from its own
+                // registers.  The walk goes from run start to winner to match end with scalar (warp-uniform)
+                // arithmetic, one shuffle to fetch the winner's summary, one to gather the literal bytes and one
+                // store per sequence.  It stops in front of anything else (an end-of-block lane, a lane whose slot
+                // an earlier lane shares, length extensions, literals carried in from earlier batches): the serial
+                // step below resolves that one sequence and the walk resumes behind it.
+                //   pinfo: bits 0..5 lane where the match ends (4..47), 6..7 backtrack summary (0..3), 16..31 candidate distance
                 uint32_t pinfo = 0;
                 {
                     const bool clean = (same & lower_mask) == 0;
                     if (consecutive && t_ok && clean && (fsum & 0x300u) == 0x300u) {
-                        const uint32_t fm = fsum & 31u, limit = len - 5 - p;
-                        if (fm < 16 || limit <= 16) pinfo = (lane + min(fm, limit)) | (((fsum >> 5) & 7u) << 6) | (tdist << 16);
+                        const uint32_t fm = fsum & 31u, limit = len - 5 - p, nb = (fsum >> 5) & 7u;
+                        // length extensions (token nibble 15) and backtracks beyond the summary take the serial step
+                        if ((fm < 16 || limit <= 16) && nb < 4 && min(fm, limit) + nb < 19) pinfo = (lane + min(fm, limit)) | (nb << 6) | (tdist << 16);
                     }
                 }
                 const uint32_t goodmask = __ballot_sync(LZF_FULL_MASK, pinfo != 0);
@@ -443,60 +430,36 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int n_smem_warps) {
                 const uint32_t trigmask = okmask | endmask | (no_dups ? 0u : __ballot_sync(LZF_FULL_MASK, (same & lower_mask) != 0));
 #endif
                 for (;;) {
-#if LZF_ENC_PARALLEL
-                    if (consecutive && s < 32 && cap >= opos && cap - opos >= 128) {
-                        uint32_t W = 0, orel = 0, mine = 0, e = 0, l_first = 0;
-                        uint32_t pre = base + s - lit_start;          // literals of the current run in front of lane s
-                        const uint32_t pre0 = pre, lit0 = lit_start;
-                        int end = 0;                                  // 0: stopped in front of lane w, 1: no trigger left, 2: match left the batch
+#if LZF_ENC_WALK
+                    if (consecutive && lit_start == base + s && s < 32 && cap >= opos && cap - opos >= 128) {
+                        int end = 0;                                          // 0: stopped in front of a lane, 1: no trigger left, 2: match left the batch
+                        uint32_t e = s;
                         for (;;) {
                             const uint32_t t = trigmask & ~((1u << s) - 1u);
                             if (t == 0) { end = 1; break; }
-                            const uint32_t w = __ffs(t) - 1;
+                            const uint32_t w = (uint32_t)__ffs((int)t) - 1u;
                             if (!((goodmask >> w) & 1u)) break;
                             const uint32_t info = __shfl_sync(LZF_FULL_MASK, pinfo, w);
-                            const uint32_t nb = (info >> 6) & 7u;
-                            const uint32_t lraw = w - s + pre;
-                            const uint32_t max_back = min(lraw, base + w - (info >> 16));       // :211-214
-                            if (nb == 4 && max_back > 4) break;                                   // backtrack beyond the summary
-                            const uint32_t bt = min(nb, max_back);
-                            const uint32_t L = lraw - bt, extra = (info & 63u) - w - 4 + bt;
-                            if (L >= 15 || extra >= 15) break;                                    // length extensions: serial step
+                            const uint32_t lraw = w - s;
+                            const uint32_t bt = min((info >> 6) & 3u, lraw);     // :211-214 (the candidate has >= 4 bytes in front of it)
+                            const uint32_t L = lraw - bt;
+                            if (L >= 15) break;                                   // length bytes: serial step
                             e = info & 63u;
-                            if (lane == w) mine = orel | (s << 8) | (pre << 13) | (L << 18) | (extra << 22);   // pre <= 18 here
-                            if (W == 0) l_first = L;
-                            W |= 1u << w;
-                            orel += L + 3;
-                            ins |= ((2u << w) - 1u) & ~((1u << s) - 1u);                         // probes s..w happened
-                            pre = 0;
+                            // write_group :150-163, one byte per lane: token | literals | offset
+                            const uint32_t tl = lane - 1u;
+                            const uint32_t litb = __shfl_sync(LZF_FULL_MASK, v32, s + tl);
+                            const uint32_t v = lane == 0 ? ((L << 4) | (e - w - 4u + bt)) : (tl < L ? litb : (info >> 16) >> (8u * (tl - L)));
+                            if (lane < L + 3u) out[opos + lane] = (uint8_t)v;
+                            opos += L + 3u;
+                            ins |= ((2u << w) - 1u) & ~((1u << s) - 1u);         // probes s..w happened
                             LZF_STAT(4);
                             if (e >= 32) { end = 2; break; }
-                            const uint32_t l2 = e - 2;                                            // table.replace(cursor - 2) :218
+                            const uint32_t l2 = e - 2;                            // table.replace(cursor - 2) :218
                             if (!((endmask >> l2) & 1u)) ins |= 1u << l2;
                             else late_q2 = base + l2;
                             s = e;
                         }
-                        if (W) {
-                            // write_group :150-163 of every sequence found, one byte per lane and role
-                            uint8_t* o = out + opos;
-                            const uint32_t wm = W & ~lower_mask;                                  // winners at or above this lane
-                            const uint32_t m = __shfl_sync(LZF_FULL_MASK, mine, wm ? __ffs(wm) - 1 : 0);
-                            if (wm) {
-                                const uint32_t sw = (m >> 8) & 31u, idx = lane - sw + ((m >> 13) & 31u);
-                                if (lane >= sw && idx < ((m >> 18) & 15u)) o[(m & 0xffu) + 1 + idx] = (uint8_t)v32;
-                            }
-                            if ((W >> lane) & 1u) {
-                                const uint32_t L = (mine >> 18) & 15u, tok = mine & 0xffu;
-                                o[tok] = (uint8_t)((L << 4) | ((mine >> 22) & 15u));
-                                o[tok + 1 + L] = (uint8_t)tdist;
-                                o[tok + 2 + L] = (uint8_t)(tdist >> 8);
-                            }
-                            // literals of the first run that lie in front of the batch
-                            if (lane < min(pre0, l_first)) o[1 + lane] = __ldg(in + lit0 + lane);
-                            opos += orel;
-                            lit_start = base + (end == 2 ? e : s);
-                            j = 0;
-                        }
+                        if (base + e != lit_start) { lit_start = base + e; j = 0; }
                         if (end == 1) {
                             ins |= ~((1u << s) - 1u);                         // every lane from s on probed and missed
                             j += 32 - s;

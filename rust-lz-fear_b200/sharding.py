@@ -2,9 +2,16 @@
 
 Independent-block frames never communicate, so a batch of frames is split into contiguous ranges of
 WHOLE frames, one per rank (each rank's content-checksum chains stay local), and the only exchange
-step is moving the results: an all-gather of per-frame byte counts followed by a variable-length
-gather of the frame bytes to a root.  `torch.distributed` is the plumbing (NCCL over NVLink on the
-GPUs, gloo in the CPU tests).
+steps move whole frames at the edges of the path:
+
+  compress    all-gather of per-frame byte counts, then a variable-length GATHER of the frame bytes to a root
+  decompress  the root walks the frame boundaries, SCATTERS contiguous ranges of whole frames, every rank
+              decodes its own, and the plaintext comes back with a (fixed- or variable-length) gather
+
+NCCL has no gatherv / scatterv: both are ONE grouped batch of point-to-point operations
+(`batch_isend_irecv` = ncclGroupStart .. ncclGroupEnd), so the transfers of all peers run side by side over
+NVLink instead of one after the other.  `torch.distributed` is the plumbing (NCCL on the GPUs, gloo in the
+CPU tests).
 """
 import torch
 import torch.distributed as dist
@@ -34,24 +41,70 @@ def all_gather_sizes(local_sizes, group=None):
     return out
 
 
-def gather_bytes(local, sizes_per_rank, dst=0, group=None):
-    """Variable-length gather (NCCL has no gatherv: grouped send/recv).  `local` = this rank's packed
-    uint8 payload; returns the concatenation in rank order on `dst`, None elsewhere."""
+def _run(ops):
+    if ops:
+        for q in dist.batch_isend_irecv(ops):
+            q.wait()
+
+
+def _peer(group, r):
+    return r if group is None else dist.get_global_rank(group, r)
+
+
+def gather_bytes(local, sizes_per_rank, dst=0, group=None, out=None):
+    """Variable-length gather.  `local` = this rank's packed uint8 payload, `sizes_per_rank[r]` = byte counts
+    of rank r's items; returns the concatenation in rank order on `dst` (into `out` when given), None elsewhere."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    totals = [int(s.sum().item()) for s in sizes_per_rank]
+    totals = [int(s.sum().item()) if torch.is_tensor(s) else int(s) for s in sizes_per_rank]
     if rank == dst:
-        out = torch.empty(sum(totals), dtype=torch.uint8, device=local.device)
-        pos, reqs = 0, []
+        if out is None:
+            out = torch.empty(sum(totals), dtype=torch.uint8, device=local.device)
+        pos, ops = 0, []
         for r in range(world):
             view = out[pos: pos + totals[r]]
             if r == dst:
                 view.copy_(local[: totals[r]])
             elif totals[r]:
-                reqs.append(dist.irecv(view, src=r, group=group))
+                ops.append(dist.P2POp(dist.irecv, view, _peer(group, r), group))
             pos += totals[r]
-        for q in reqs:
-            q.wait()
-        return out
+        _run(ops)
+        return out[: sum(totals)]
     if totals[rank]:
-        dist.send(local[: totals[rank]].contiguous(), dst=dst, group=group)
+        _run([dist.P2POp(dist.isend, local[: totals[rank]].contiguous(), _peer(group, dst), group)])
     return None
+
+
+def scatter_bytes(packed, totals, src=0, group=None, device=None, out=None):
+    """Variable-length scatter: rank `src` holds `packed` = the concatenation, in rank order, of every rank's byte
+    range (`totals[r]` bytes for rank r, known on every rank); every rank gets its own range back."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    totals = [int(t) for t in totals]
+    if rank == src:
+        pos, ops, mine = 0, [], None
+        for r in range(world):
+            view = packed[pos: pos + totals[r]]
+            if r == src:
+                mine = view
+            elif totals[r]:
+                ops.append(dist.P2POp(dist.isend, view, _peer(group, r), group))
+            pos += totals[r]
+        _run(ops)
+        if out is not None:
+            out[: totals[rank]].copy_(mine)
+            return out[: totals[rank]]
+        return mine
+    if out is None:
+        out = torch.empty(totals[rank], dtype=torch.uint8, device=device if device is not None else (packed.device if packed is not None else None))
+    if totals[rank]:
+        _run([dist.P2POp(dist.irecv, out[: totals[rank]], _peer(group, src), group)])
+    return out[: totals[rank]]
+
+
+def payload_digest(t):
+    """A cheap order-sensitive digest of a uint8 tensor computed where it lives (exchange verification: every rank
+    digests what it sent, the receiver digests each slice it got): sum of bytes and sum of byte * (index mod 65521 + 1)."""
+    if t is None or t.numel() == 0:
+        return (0, 0)
+    x = t.to(torch.int64)
+    w = torch.arange(t.numel(), device=t.device, dtype=torch.int64) % 65521 + 1
+    return (int(x.sum().item()), int((x * w).sum().item()))

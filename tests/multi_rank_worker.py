@@ -48,6 +48,24 @@ def main():
             st, det, plain, _c = ctx.frame_decompress(got[pos: pos + s].numpy(), cap=len(d) + 16)
             assert (st, plain) == (0, d)
             pos += s
+    # decompress direction (§8(e)): rank 0 walks the frame boundaries and scatters contiguous ranges of whole frames;
+    # every rank decodes its own and the plaintext is gathered back, variable length
+    all_sizes = torch.cat(per_rank).tolist()
+    ranges = [sharding.shard_range(nframes, world, r) for r in range(world)]
+    totals = [sum(all_sizes[a:b]) for a, b in ranges]
+    mine_packed = sharding.scatter_bytes(got if rank == 0 else None, totals, src=0, device="cpu")
+    assert sharding.payload_digest(mine_packed) == sharding.payload_digest(local[: totals[rank]])
+    pos, plains = 0, []
+    for i in range(lo, hi):
+        st, det, plain, _c = ctx.frame_decompress(mine_packed[pos: pos + all_sizes[i]].numpy(), cap=len(datas[i]) + 16)
+        assert (st, plain) == (0, datas[i])
+        plains.append(plain)
+        pos += all_sizes[i]
+    pl = torch.from_numpy(np.frombuffer(b"".join(plains) or b"\0", dtype=np.uint8).copy())
+    psz = [torch.tensor([len(datas[i]) for i in range(a, b)], dtype=torch.int64) for a, b in ranges]
+    back = sharding.gather_bytes(pl, psz, dst=0)
+    if rank == 0:
+        assert back.numpy().tobytes() == b"".join(datas), "scattered -> decoded -> gathered plaintext differs"
         print("MULTI-RANK-OK")
     dist.barrier()
     dist.destroy_process_group()

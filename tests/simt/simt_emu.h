@@ -122,7 +122,7 @@ extern State g;
 inline const uint3& thread_idx() { return g.fibres[g.cur].tid; }
 inline void yield() { int me = g.cur; swapcontext(&g.fibres[me].ctx, &g.sched); g.cur = me; }
 
-enum Op { OP_BALLOT, OP_SHFL, OP_SHFL_UP, OP_SHFL_DOWN, OP_SHFL_XOR, OP_MATCH_ANY, OP_ANY, OP_ALL, OP_SYNC };
+enum Op { OP_BALLOT, OP_SHFL, OP_SHFL_UP, OP_SHFL_DOWN, OP_SHFL_XOR, OP_MATCH_ANY, OP_ANY, OP_ALL, OP_SYNC, OP_REDUCE_OR };
 
 // All 32 lanes of a warp must call with the full mask (our kernels only ever use full masks).
 inline uint64_t collective(Op op, uint64_t value, uint32_t arg) {
@@ -160,6 +160,7 @@ inline uint64_t collective(Op op, uint64_t value, uint32_t arg) {
                 case OP_SHFL_XOR: r = w.in[(l ^ a) & 31]; break;
                 case OP_MATCH_ANY: for (int k = 0; k < kWarp; k++) if (w.in[k] == w.in[l]) r |= (1ull << k); break;
                 case OP_SYNC: break;
+                case OP_REDUCE_OR: for (int k = 0; k < kWarp; k++) r |= w.in[k]; break;
             }
             w.out[l] = r;
         }
@@ -195,6 +196,7 @@ static inline void __syncthreads() { simt::cta_barrier(); }
 static inline unsigned __ballot_sync(unsigned, int pred) { return (unsigned)simt::collective(simt::OP_BALLOT, pred != 0, 0); }
 static inline int __any_sync(unsigned, int pred) { return (int)simt::collective(simt::OP_ANY, pred != 0, 0); }
 static inline int __all_sync(unsigned, int pred) { return (int)simt::collective(simt::OP_ALL, pred != 0, 0); }
+static inline unsigned __reduce_or_sync(unsigned, unsigned v) { return (unsigned)simt::collective(simt::OP_REDUCE_OR, v, 0); }
 template <typename T> static inline T __shfl_sync(unsigned, T v, int src) {
     static_assert(sizeof(T) <= 8, "shfl width");
     uint64_t raw = 0; memcpy(&raw, &v, sizeof(T));
