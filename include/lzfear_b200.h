@@ -22,6 +22,25 @@
  *   - batched device calls are asynchronous on `stream` (a cudaStream_t passed as void*);
  *     host-buffer calls synchronise before returning
  *   - nothing here throws or aborts across the ABI
+ *
+ * Buffers
+ *   - blocks and frames may start at ANY byte address; lengths are arbitrary
+ *   - the kernels read whole aligned words / 16-byte TMA granules: of a block's input (and of the history in
+ *     front of it) they may READ — never write — the other bytes of the aligned 16-byte granules that hold its
+ *     first and its last byte.  Every allocator whose alignment and granularity are at least 16 bytes satisfies
+ *     this (cudaMalloc: 256, pinned host pages, the usual sub-allocators); a buffer whose first or last granule is
+ *     cut by an allocation boundary finer than 16 bytes must be padded by the caller
+ *   - output bytes between out_len and the capacity of a block / frame are unspecified after a call
+ *
+ * Concurrency
+ *   - a ctx may be used from several host threads; calls that share a pipeline slot serialise internally
+ *   - batched device calls of one ctx run one after the other even when given different streams (they share the
+ *     ctx's work queue and table scratch): a launch on another stream first waits for the previous one.  Use one
+ *     ctx per stream for independent queues
+ *
+ * Environment (read ONCE, by lzf_create; tuning and test knobs, never needed for correct results)
+ *     LZF_B200_CHUNK_BYTES, LZF_B200_FEED_SLICE, LZF_B200_FEED_MIN_BLOCKS, LZF_B200_ENC_U32,
+ *     LZF_B200_ENC_SMEM_WARPS, LZF_B200_DEC_CTAS_PER_SM, LZF_B200_TRACE
  */
 #ifndef LZFEAR_B200_H
 #define LZFEAR_B200_H
@@ -33,7 +52,7 @@
 extern "C" {
 #endif
 
-#define LZF_ABI_VERSION 2
+#define LZF_ABI_VERSION 3
 
 /* ---- call-level return codes ---- */
 enum {
@@ -188,6 +207,22 @@ int lzf_raw_compress_into(lzf_ctx* ctx, const uint8_t* in, size_t n, uint32_t ta
                           uint8_t* out, size_t cap, size_t* written, int32_t* status);
 int lzf_raw_decompress(lzf_ctx* ctx, const uint8_t* in, size_t n, const uint8_t* prefix, size_t plen,
                        uint8_t* out, size_t out_cap, size_t out_limit, size_t* out_len, int32_t* status);
+/* compress2 with history and a carried table — the full signature of src/raw/compress/mod.rs:165-170,
+ *     compress2(input, cursor, &mut table, NoPartialWrites(out[..cap]))
+ * as src/framed/compress.rs:220,243,270-275 uses it for dependent blocks: input[..cursor] is match-only history,
+ * `table` keeps its entries from call to call.  The table is a device-resident EncoderTable (:19-25):
+ *   lzf_table_create   U32Table::default() / U16Table::default()  (:32-36,83-87); hashlog 0/12 = reference
+ *   lzf_table_reset    *table = T::default()
+ *   lzf_table_offset   EncoderTable::offset(by)  (:72-74): positions of later calls are shifted by `by`
+ * *status: LZF_OK, LZF_WRITER_FULL, or LZF_PANIC where the reference would panic (:67 "EncoderTable contract
+ * violated", :167).  A refused write leaves the table as the reference leaves it (updated up to that point). */
+typedef struct lzf_table lzf_table;
+int lzf_table_create(lzf_ctx* ctx, uint32_t table_kind, uint32_t hashlog, lzf_table** table);
+void lzf_table_destroy(lzf_ctx* ctx, lzf_table* table);
+int lzf_table_reset(lzf_ctx* ctx, lzf_table* table);
+int lzf_table_offset(lzf_ctx* ctx, lzf_table* table, uint64_t by);
+int lzf_raw_compress2(lzf_ctx* ctx, const uint8_t* in, size_t n, size_t cursor, lzf_table* table,
+                      uint8_t* out, size_t cap, size_t* written, int32_t* status);
 /* worst-case compress2 output for n input bytes into an unbounded writer */
 size_t lzf_compress_bound(size_t n);
 

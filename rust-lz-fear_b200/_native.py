@@ -24,7 +24,7 @@ F_INVALID_BLOCK_SIZE, F_WRITE_ERROR, F_PANIC = 20, 21, 22
 P_UNIMPLEMENTED_BLOCKSIZE, P_UNSUPPORTED_VERSION, P_RESERVED_FLAG_BITS, P_RESERVED_BD_BITS = 1, 2, 3, 4
 TABLE_U32, TABLE_U16 = 0, 1
 INCOMPRESSIBLE = 0x80000000
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class NativeLibraryError(RuntimeError):
@@ -75,6 +75,12 @@ _PROTOTYPES = {
                                         C.POINTER(C.c_size_t), C.POINTER(C.c_int32)]),
     "lzf_raw_decompress": (C.c_int, [_P, _P, C.c_size_t, _P, C.c_size_t, _P, C.c_size_t, C.c_size_t,
                                      C.POINTER(C.c_size_t), C.POINTER(C.c_int32)]),
+    "lzf_table_create": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.POINTER(_P)]),
+    "lzf_table_destroy": (None, [_P, _P]),
+    "lzf_table_reset": (C.c_int, [_P, _P]),
+    "lzf_table_offset": (C.c_int, [_P, _P, C.c_uint64]),
+    "lzf_raw_compress2": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, _P, _P, C.c_size_t,
+                                    C.POINTER(C.c_size_t), C.POINTER(C.c_int32)]),
     "lzf_compress_bound": (C.c_size_t, [C.c_size_t]),
     "lzf_settings_default": (None, [C.POINTER(Settings)]),
     "lzf_frame_bound": (C.c_size_t, [C.POINTER(Settings), C.c_size_t]),
@@ -212,6 +218,32 @@ class Context:
         st = C.c_int32(0)
         self._check(self._lib.lzf_raw_compress_into(self._h, _np_ptr(a), a.size, table, hashlog, out.ctypes.data,
                                                     int(cap), C.byref(w), C.byref(st)))
+        return st.value, out[: w.value].tobytes()
+
+    def table_new(self, table=TABLE_U32, hashlog=12):
+        """A device-resident EncoderTable (U32Table::default() / U16Table::default())."""
+        h = _P()
+        self._check(self._lib.lzf_table_create(self._h, table, hashlog, C.byref(h)))
+        return h
+
+    def table_free(self, t):
+        self._lib.lzf_table_destroy(self._h, t)
+
+    def table_reset(self, t):
+        self._check(self._lib.lzf_table_reset(self._h, t))
+
+    def table_offset(self, t, by):
+        self._check(self._lib.lzf_table_offset(self._h, t, by))
+
+    def raw_compress2(self, data, cursor, table, cap=None):
+        """raw::compress2(input, cursor, &mut table, writer) -> (status, compressed bytes)."""
+        a = _as_u8(data)
+        if cap is None:
+            cap = self._lib.lzf_compress_bound(a.size)
+        out = np.empty(max(int(cap), 1), dtype=np.uint8)
+        w, st = C.c_size_t(0), C.c_int32(0)
+        self._check(self._lib.lzf_raw_compress2(self._h, _np_ptr(a), a.size, int(cursor), table, out.ctypes.data, int(cap),
+                                                C.byref(w), C.byref(st)))
         return st.value, out[: w.value].tobytes()
 
     def raw_decompress(self, data, prefix=b"", out_limit=None, cap=None):

@@ -86,6 +86,15 @@ struct lzf_ctx {
     // compress: plaintext bytes.  0 = one full wave of the block kernel (one warp per block, 28 warps per SM;
     // the parse is latency-bound, so a chunk with fewer blocks takes just as long), at most 24 GiB
     uint64_t compress_chunk_bytes = 0;
+    // tuning / test knobs.  The environment is read ONCE, in lzf_create (LZF_B200_*); nothing on a call path calls getenv.
+    struct Tuning {
+        bool trace = false;                     // LZF_B200_TRACE: phase times of the host-buffer compress chunks on stderr
+        uint64_t feed_slice = 64 << 10;         // LZF_B200_FEED_SLICE: slice of the H2D feed under the encode kernel (0 = off)
+        uint64_t feed_min_blocks = 64;          // LZF_B200_FEED_MIN_BLOCKS
+        uint32_t enc_u32_slots = 0;             // LZF_B200_ENC_U32
+        uint32_t enc_smem_warps_p1 = 0;         // LZF_B200_ENC_SMEM_WARPS + 1
+        uint32_t dec_ctas_per_sm = 0;           // LZF_B200_DEC_CTAS_PER_SM
+    } tune;
 };
 
 // slot of the calling thread: worker threads of the host-buffer pipelines bind their own, every other
@@ -172,10 +181,16 @@ extern "C" int lzf_create(int device, lzf_ctx** out) {
     }
     for (int i = 0; i < kSlots && ok; i++)
         for (uint32_t k = 0; k < kMaxSlices; k++) c->slots[i].h_seq[k] = k + 1;
-    if (const char* e = getenv("LZF_B200_CHUNK_BYTES")) {       // tuning / test knob
+    if (const char* e = getenv("LZF_B200_CHUNK_BYTES")) {       // tuning / test knobs, all read here and only here
         const unsigned long long v = strtoull(e, nullptr, 10);
         if (v) c->chunk_bytes = c->compress_chunk_bytes = v;
     }
+    c->tune.trace = getenv("LZF_B200_TRACE") != nullptr;
+    if (const char* e = getenv("LZF_B200_FEED_SLICE")) c->tune.feed_slice = strtoull(e, nullptr, 10);
+    if (const char* e = getenv("LZF_B200_FEED_MIN_BLOCKS")) c->tune.feed_min_blocks = strtoull(e, nullptr, 10);
+    c->tune.enc_u32_slots = getenv("LZF_B200_ENC_U32") != nullptr;
+    if (const char* e = getenv("LZF_B200_ENC_SMEM_WARPS")) { const int v = atoi(e); if (v >= 0) c->tune.enc_smem_warps_p1 = (uint32_t)v + 1; }
+    if (const char* e = getenv("LZF_B200_DEC_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1) c->tune.dec_ctas_per_sm = (uint32_t)v; }
     if (!ok) { lzf_destroy(c); return LZF_ERR_CUDA; }
     *out = c;
     return LZF_SUCCESS;
@@ -257,7 +272,7 @@ int compress_blocks_impl(lzf_ctx* c, const uint8_t* d_in, const uint64_t* d_in_o
     if (chains) {
         a.prefix_len = chains->prefix_len; a.abs_base = chains->abs_base; a.prime_len = chains->prime_len;
         a.chain_first = chains->chain_first; a.chain_count = chains->chain_count; a.nchains = chains->nchains;
-        a.max_pos = chains->max_pos;
+        a.max_pos = chains->max_pos; a.table_io = chains->table_io;
     }
     a.in = d_in; a.in_off = d_in_off; a.in_len = d_in_len; a.nblocks = nblocks;
     a.hashlog = hashlog; a.table_kind = table_kind;
@@ -265,6 +280,7 @@ int compress_blocks_impl(lzf_ctx* c, const uint8_t* d_in, const uint64_t* d_in_o
     a.xxh_plain = d_xxh_plain; a.xxh_stored = d_xxh_stored;
     a.work_counter = cur_slot(c)->d_counter;
     a.max_block_len = max_block_len;
+    a.tune_u32_slots = c->tune.enc_u32_slots; a.tune_smem_warps_p1 = c->tune.enc_smem_warps_p1;
     if (const size_t scratch = lzf_encode_global_table_bytes(&a, c->num_sms)) {   // tables that do not fit shared memory
         const int rc = ensure_dev(c, cur_slot(c)->d_tables, scratch);
         if (rc) return rc;
@@ -301,6 +317,7 @@ int decompress_blocks_impl(lzf_ctx* c, const uint8_t* d_in, const uint64_t* d_in
     a.out_len = d_out_len; a.status = d_status; a.xxh_plain = d_xxh_plain;
     a.prefix_abs = prefix_abs ? 1 : 0; a.wait_for = d_wait_for; a.done = d_done;
     a.work_counter = cur_slot(c)->d_counter + 16;
+    a.tune_ctas_per_sm = c->tune.dec_ctas_per_sm;
     LaunchOrder order(cur_slot(c), s);
     LZF_CU(c, order.begin());
     LZF_CU(c, cudaMemsetAsync(cur_slot(c)->d_counter + 16, 0, 4, s));
@@ -437,6 +454,109 @@ extern "C" int lzf_raw_compress_into(lzf_ctx* c, const uint8_t* in, size_t n, ui
     rc = compress_blocks_impl(c, (const uint8_t*)cur_slot(c)->d_io_in.p, (const uint64_t*)d, (const uint32_t*)(d + 16), 1, hashlog,
                               table_kind, (uint32_t)n, (uint8_t*)cur_slot(c)->d_io_out.p, (const uint64_t*)(d + 8),
                               (const uint32_t*)(d + 20), (uint32_t*)(d + 64), (int32_t*)(d + 68), nullptr, nullptr, s);
+    if (rc) return rc;
+    LZF_CU(c, cudaMemcpyAsync(h + 64, d + 64, 8, cudaMemcpyDeviceToHost, s));
+    LZF_CU(c, cudaStreamSynchronize(s));
+    const uint32_t olen = *(uint32_t*)(h + 64);
+    *status = *(int32_t*)(h + 68);
+    if (*status == LZF_OK && olen) {
+        LZF_CU(c, cudaMemcpyAsync(out, cur_slot(c)->d_io_out.p, olen, cudaMemcpyDeviceToHost, s));
+        LZF_CU(c, cudaStreamSynchronize(s));
+    }
+    *written = *status == LZF_OK ? olen : 0;
+    return LZF_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------------------------
+// compress2 with history and a carried table (src/raw/compress/mod.rs:165-170): the EncoderTable lives on the device
+// ------------------------------------------------------------------------------------------------
+struct lzf_table {
+    uint32_t kind = LZF_TABLE_U32, hashlog = 12, nslots = 4096;
+    uint64_t offset = 0;                // U32Table::offset / U16Table::offset (:30,81)
+    uint32_t* d_slots = nullptr;        // dict, one u32 per slot (:29,80)
+};
+
+extern "C" int lzf_table_create(lzf_ctx* c, uint32_t table_kind, uint32_t hashlog, lzf_table** out) {
+    if (!c || !out) return LZF_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (hashlog == 0) hashlog = 12;
+    if (hashlog < 8 || hashlog > 16) return fail(c, LZF_ERR_INVALID_ARG, "hashlog must be 0 or 8..16");
+    if (table_kind != LZF_TABLE_U32 && table_kind != LZF_TABLE_U16) return fail(c, LZF_ERR_INVALID_ARG, "table_kind");
+    LZF_CU(c, cudaSetDevice(c->device));
+    lzf_table* t = new (std::nothrow) lzf_table();
+    if (!t) return LZF_ERR_OOM;
+    t->kind = table_kind; t->hashlog = hashlog;
+    t->nslots = table_kind == LZF_TABLE_U16 ? (2u << hashlog) : (1u << hashlog);      // :28,79
+    if (cudaMalloc((void**)&t->d_slots, (size_t)t->nslots * 4) != cudaSuccess) { delete t; return fail(c, LZF_ERR_OOM, "cudaMalloc"); }
+    if (cudaMemsetAsync(t->d_slots, 0, (size_t)t->nslots * 4, cur_slot(c)->stream) != cudaSuccess ||
+        cudaStreamSynchronize(cur_slot(c)->stream) != cudaSuccess) { cudaFree(t->d_slots); delete t; return fail(c, LZF_ERR_CUDA, "cudaMemset"); }
+    *out = t;
+    return LZF_SUCCESS;
+}
+
+extern "C" void lzf_table_destroy(lzf_ctx* c, lzf_table* t) {
+    if (!t) return;
+    if (c) cudaSetDevice(c->device);
+    if (t->d_slots) cudaFree(t->d_slots);
+    delete t;
+}
+
+extern "C" int lzf_table_reset(lzf_ctx* c, lzf_table* t) {        // *table = T::default()  :32-36,83-87
+    if (!c || !t) return LZF_ERR_INVALID_ARG;
+    LZF_CU(c, cudaSetDevice(c->device));
+    LZF_CU(c, cudaMemsetAsync(t->d_slots, 0, (size_t)t->nslots * 4, cur_slot(c)->stream));
+    LZF_CU(c, cudaStreamSynchronize(cur_slot(c)->stream));
+    t->offset = 0;
+    return LZF_SUCCESS;
+}
+
+extern "C" int lzf_table_offset(lzf_ctx* c, lzf_table* t, uint64_t by) {      // EncoderTable::offset  :72-74,97-99
+    if (!c || !t) return LZF_ERR_INVALID_ARG;
+    t->offset += by;
+    return LZF_SUCCESS;
+}
+
+extern "C" int lzf_raw_compress2(lzf_ctx* c, const uint8_t* in, size_t n, size_t cursor, lzf_table* t,
+                                 uint8_t* out, size_t cap, size_t* written, int32_t* status) {
+    if (!c || !t || !written || !status || (n && !in) || (cap && !out) || cursor > n) return LZF_ERR_INVALID_ARG;
+    *written = 0;
+    *status = LZF_OK;
+    // assert!(input.len() <= T::payload_size_limit())   :167
+    if (n > 0xffffffffull || (t->kind == LZF_TABLE_U16 && n > 0xffffull)) { *status = LZF_PANIC; return LZF_SUCCESS; }
+    if (cursor == n) return LZF_SUCCESS;                               // while cursor < input.len() :171 never runs
+    // "EncoderTable contract violated" (:67,92): every position this call can insert must fit the slot
+    if (t->offset + n > (t->kind == LZF_TABLE_U16 ? 0xffffull : 0xffffffffull)) { *status = LZF_PANIC; return LZF_SUCCESS; }
+    LZF_CU(c, cudaSetDevice(c->device));
+    const size_t capc = cap > 0xffffffffull ? 0xffffffffull : cap;
+    int rc;
+    if ((rc = ensure_dev(c, cur_slot(c)->d_io_in, n + 64))) return rc;
+    if ((rc = ensure_dev(c, cur_slot(c)->d_io_out, capc + 64))) return rc;
+    if ((rc = ensure_dev(c, cur_slot(c)->d_desc, 4096))) return rc;
+    if ((rc = ensure_host(c, cur_slot(c)->h_desc, 4096))) return rc;
+    uint8_t* h = (uint8_t*)cur_slot(c)->h_desc.p;
+    uint8_t* d = (uint8_t*)cur_slot(c)->d_desc.p;
+    // in_off u64 @0, out_off u64 @8, in_len u32 @16, out_cap u32 @20, prefix_len @24, abs_base @28, chain_first @32,
+    // chain_count @36 | results: out_len u32 @64, status i32 @68
+    memset(h, 0, 128);
+    *(uint64_t*)(h + 0) = cursor;
+    *(uint32_t*)(h + 16) = (uint32_t)(n - cursor);
+    *(uint32_t*)(h + 20) = (uint32_t)capc;
+    *(uint32_t*)(h + 24) = (uint32_t)cursor;
+    *(uint32_t*)(h + 28) = (uint32_t)t->offset;
+    *(uint32_t*)(h + 32) = 0;
+    *(uint32_t*)(h + 36) = 1;
+    cudaStream_t s = cur_slot(c)->stream;
+    LZF_CU(c, cudaMemcpyAsync(d, h, 128, cudaMemcpyHostToDevice, s));
+    LZF_CU(c, cudaMemcpyAsync(cur_slot(c)->d_io_in.p, in, n, cudaMemcpyHostToDevice, s));
+    lzf::EncodeArgs ch;
+    memset(&ch, 0, sizeof(ch));
+    ch.prefix_len = (const uint32_t*)(d + 24); ch.abs_base = (const uint32_t*)(d + 28);
+    ch.chain_first = (const uint32_t*)(d + 32); ch.chain_count = (const uint32_t*)(d + 36); ch.nchains = 1;
+    ch.table_io = t->d_slots;
+    // max_block_len 0 ("unknown") keeps plain slots: the carried dict is the reference's, value for value
+    rc = compress_blocks_impl(c, (const uint8_t*)cur_slot(c)->d_io_in.p, (const uint64_t*)d, (const uint32_t*)(d + 16), 1, t->hashlog,
+                              t->kind, 0, (uint8_t*)cur_slot(c)->d_io_out.p, (const uint64_t*)(d + 8),
+                              (const uint32_t*)(d + 20), (uint32_t*)(d + 64), (int32_t*)(d + 68), nullptr, nullptr, s, &ch);
     if (rc) return rc;
     LZF_CU(c, cudaMemcpyAsync(h + 64, d + 64, 8, cudaMemcpyDeviceToHost, s));
     LZF_CU(c, cudaStreamSynchronize(s));
@@ -1207,7 +1327,7 @@ int compress_chunk(lzf_ctx* c, lzf_slot& sl, const lzf_settings* s, uint32_t f0,
     const HostLayout li = plan_layout(in_off + f0, in_len + f0, n);
     const HostLayout lo = plan_layout(out_off + f0, dcap.data(), n);
     int rc;
-    const bool trace = getenv("LZF_B200_TRACE") != nullptr;           // phase times of the chunk on stderr
+    const bool trace = c->tune.trace;                                 // phase times of the chunk on stderr
     const auto t_begin = std::chrono::steady_clock::now();
     auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
     if ((rc = ensure_dev(c, sl.d_io_in, li.span + 256))) return rc;
@@ -1218,9 +1338,7 @@ int compress_chunk(lzf_ctx* c, lzf_slot& sl, const lzf_settings* s, uint32_t f0,
     // independent blocks is fed while the kernel already runs: slice k of EVERY block travels before slice k + 1
     // of any (one strided copy per slice), followed by a 4-byte copy that bumps the progress word the warps poll.
     const uint64_t bs = s->block_size;
-    uint64_t slice = 64 << 10, min_blocks = 64;     // 64 KiB: the first slice of 4096 blocks is there after 5 ms
-    if (const char* e = getenv("LZF_B200_FEED_SLICE")) slice = strtoull(e, nullptr, 10);       // tuning / test knobs; 0 = off
-    if (const char* e = getenv("LZF_B200_FEED_MIN_BLOCKS")) min_blocks = strtoull(e, nullptr, 10);
+    const uint64_t slice = c->tune.feed_slice, min_blocks = c->tune.feed_min_blocks;   // 64 KiB: the first slice of 4096 blocks is there after 5 ms
     bool sliced = li.dense && s->independent_blocks && !(s->dictionary && s->dictionary_len) && slice >= 4096 &&
                   bs >= 4 * slice && bs % slice == 0 && bs / slice <= kMaxSlices && li.span >= min_blocks * bs;
     for (uint32_t f = 0; f < n && sliced; f++) sliced = in_len[f0 + f] % bs == 0;

@@ -240,6 +240,7 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int n_smem_warps) {
         const uint32_t b_first = a.chain_first ? a.chain_first[chain] : chain;
         const uint32_t b_count = a.chain_first ? a.chain_count[chain] : 1u;
         uint32_t last_sweep = 0;        // packed tables: every slot is exact for stream positions below last_sweep + 65536
+        bool carried_in = false;        // the table came from EncodeArgs::table_io and goes back there
 
       for (uint32_t bi = 0; bi < b_count; bi++) {
         const uint32_t b = b_first + bi;
@@ -268,9 +269,15 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int n_smem_warps) {
         } else if (own_len) {
             if (bi == 0) {
                 // fresh zeroed table (U32Table::default :32-36 / template_table.clone() compress.rs:270)
-                uint4* t4 = reinterpret_cast<uint4*>(table_mem);
-                const uint32_t nvec = (uint32_t)(table_bytes / 16);
-                for (uint32_t i = lane; i < nvec; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
+                if (!kPacked && a.table_io && chain == 0) {
+                    // a table carried over from an earlier call (compress2's `table: &mut T`, :165-170)
+                    if constexpr (!kPacked) for (uint32_t i = lane; i < nslots; i += 32) table.t[i] = (Slot)a.table_io[i];
+                    carried_in = true;
+                } else {
+                    uint4* t4 = reinterpret_cast<uint4*>(table_mem);
+                    const uint32_t nvec = (uint32_t)(table_bytes / 16);
+                    for (uint32_t i = lane; i < nvec; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
+                }
                 __syncwarp();
                 last_sweep = 0;
                 // dictionary priming: template_table.replace(dict, off) for off = 0, 3, 6, ... while 8 bytes
@@ -346,6 +353,7 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int n_smem_warps) {
                     }
                     h = kHash4 ? hash4(v32, hashlog) : hash5(v32, (w1 >> sh) & 0xffu, hashlog);
                     tdist = table.dist(h, p + ab);                            // table.replace :196 (read half)
+                    if (ab && tdist > p) tdist = p;                           // old.saturating_sub(self.offset) :70 -> candidate 0
                     tcand = p - tdist;
                 }
                 const uint32_t same = __match_any_sync(LZF_FULL_MASK, h);
@@ -721,6 +729,12 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int n_smem_warps) {
             else hash_queue_push(&hashq, in + cursor0, own_len, a.xxh_stored + b);
         }
       }   // blocks of the chain
+        if constexpr (!kPacked) {
+            if (carried_in) {
+                __syncwarp();
+                for (uint32_t i = lane; i < nslots; i += 32) a.table_io[i] = (uint32_t)table.t[i];
+            }
+        }
     }
     hash_queue_finish(&hashq, kEncodeWarpsPerCta);
 }
@@ -751,7 +765,7 @@ static EncodePlan plan_encode(const EncodeArgs* args) {
     p.table_bytes = slot16 ? (size_t)p.nslots * 2 : packed ? (size_t)p.nslots * 2 + p.nslots / 8 : (size_t)p.nslots * 4;
     p.variant = hash4 ? 3 : slot16 ? 1 : packed ? 2 : 0;
     bool big = p.variant == 1 || p.variant == 2;
-    if (p.variant == 2 && getenv("LZF_B200_ENC_U32")) {               // tuning knob: plain u32 slots in the global scratch
+    if (p.variant == 2 && args->tune_u32_slots) {                     // tuning knob: plain u32 slots in the global scratch
         p.variant = 0;
         p.table_bytes = (size_t)p.nslots * 4;
     }
@@ -761,9 +775,9 @@ static EncodePlan plan_encode(const EncodeArgs* args) {
         p.warps = kEncodeBigWarps;
         int fit = (int)(smem_budget / p.table_bytes);
         if (fit > kEncodeSmemWarpsMax) fit = kEncodeSmemWarpsMax;
-        if (const char* e = getenv("LZF_B200_ENC_SMEM_WARPS")) {      // test / tuning knob: fewer shared-memory tables
-            const int v = atoi(e);
-            if (v >= 0 && v < fit) fit = v;
+        if (args->tune_smem_warps_p1) {                               // test / tuning knob: fewer shared-memory tables
+            const int v = (int)args->tune_smem_warps_p1 - 1;
+            if (v < fit) fit = v;
         }
         p.n_smem_warps = fit < p.warps ? fit : p.warps;
         p.global_warps_per_sm = 2 * (p.warps - p.n_smem_warps);       // 2: small tables could make two CTAs resident

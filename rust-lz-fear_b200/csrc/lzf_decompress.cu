@@ -577,12 +577,7 @@ extern "C" int lzf_launch_decode(const lzf::DecodeArgs* args, int num_sms, cudaS
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, decode_blocks_kernel, kDecodeWarpsPerCta * 32, dyn);
     if (e != cudaSuccess) return (int)e;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
-#ifndef LZF_SIMT_EMU
-    if (const char* e = getenv("LZF_B200_DEC_CTAS_PER_SM")) {     // tuning knob: cap the resident CTAs per SM
-        const int v = atoi(e);
-        if (v >= 1 && v < ctas_per_sm) ctas_per_sm = v;
-    }
-#endif
+    if (args->tune_ctas_per_sm >= 1 && (int)args->tune_ctas_per_sm < ctas_per_sm) ctas_per_sm = (int)args->tune_ctas_per_sm;   // tuning knob
     unsigned grid = (unsigned)(num_sms * ctas_per_sm);
     const unsigned need = (args->nblocks + kDecodeWarpsPerCta - 1) / kDecodeWarpsPerCta;
     if (grid > need) grid = need;

@@ -26,6 +26,12 @@ struct EncodeArgs {
     // [0, *progress * slice_bytes) of EVERY block are in place (the host copies one slice of all blocks after the
     // other and bumps *progress after each); a warp waits before it reads past that.  null = everything is there.
     const uint32_t* progress; uint32_t slice_bytes;
+    // internal (raw API with a carried table, lzf_raw_compress2): the first chain starts from these slots (one u32
+    // stream position per slot) instead of a zeroed table and writes them back when its last block is done
+    uint32_t* table_io;
+    // tuning knobs, read from the environment ONCE by lzf_create (0 = default): plain u32 slots where packed ones
+    // would do / 1 + the number of warps per CTA whose table may live in shared memory
+    uint32_t tune_u32_slots; uint32_t tune_smem_warps_p1;
 };
 struct StageArgs {      // [dictionary | block] staging copies for blocks whose history is the dictionary
     uint32_t n; const uint8_t* dict; uint32_t dlen;
@@ -41,6 +47,7 @@ struct DecodeArgs {
     // (history of a dependent block = the previous blocks' output in front of its own).  wait_for[b] >= 0:
     // block b may only start once block wait_for[b] (always a lower index) has set done[wait_for[b]].
     int prefix_abs; const int32_t* wait_for; uint32_t* done;
+    uint32_t tune_ctas_per_sm;      // tuning knob read once by lzf_create: cap of the resident CTAs per SM (0 = occupancy)
 };
 struct LayoutArgs {
     uint32_t nframes;

@@ -92,6 +92,21 @@ class _Backend:
     def __init__(self, name, ctx, scale):
         self.name, self.ctx, self.scale = name, ctx, scale
 
+    def fresh(self):
+        """A second Context of the same build, created NOW: lzf_create reads the LZF_B200_* tuning knobs once, so a test
+        that sets one with monkeypatch.setenv takes its context from here (use as a context manager)."""
+        import contextlib
+        from lz_fear_b200 import _native
+
+        @contextlib.contextmanager
+        def cm():
+            ctx = _native.Context(0)
+            try:
+                yield _Backend(self.name, ctx, self.scale)
+            finally:
+                ctx.close()
+        return cm()
+
 
 @pytest.fixture(scope="session")
 def emu(simt_lib_path):

@@ -32,7 +32,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), "liblzfear_b200.so does not export %s" % name
     lib.lzf_abi_version.restype = ctypes.c_int
-    assert lib.lzf_abi_version() == 2
+    assert lib.lzf_abi_version() == 3
 
 
 def test_python_binding_covers_the_header():

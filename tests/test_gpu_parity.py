@@ -161,8 +161,9 @@ def test_config3_text_compress_vs_oracle(gpu, oracle, monkeypatch, variant):
     comp = torch.empty(nb * B, dtype=torch.uint8, device="cuda")
     olen = torch.zeros(nb, dtype=torch.int32, device="cuda")
     st = torch.zeros(nb, dtype=torch.int32, device="cuda")
-    gpu.ctx.compress_blocks(data, off, ln, nb, comp, off, None, olen, st, max_block_len=mbl)
-    torch.cuda.synchronize()
+    with gpu.fresh() as g:                                   # the knobs are read when the context is created
+        g.ctx.compress_blocks(data, off, ln, nb, comp, off, None, olen, st, max_block_len=mbl)
+        torch.cuda.synchronize()
     assert int(st.abs().sum()) == 0
     h = data.cpu().numpy()
     ref = np.empty(nb * B, dtype=np.uint8)
@@ -254,8 +255,9 @@ def test_sliced_input_feed(gpu, oracle, monkeypatch):
     s, keep = N.make_settings(block_size=1 << 20, block_checksums=True)
     bound = gpu.ctx.frame_bound(s, fp)
     out = np.zeros(nf * bound, dtype=np.uint8)
-    fl, fs = gpu.ctx.frames_compress(src, np.arange(nf, dtype=np.uint64) * fp, np.full(nf, fp, np.uint64), out,
-                                     np.arange(nf, dtype=np.uint64) * bound, np.full(nf, bound, np.uint64), s)
+    with gpu.fresh() as g:
+        fl, fs = g.ctx.frames_compress(src, np.arange(nf, dtype=np.uint64) * fp, np.full(nf, fp, np.uint64), out,
+                                       np.arange(nf, dtype=np.uint64) * bound, np.full(nf, bound, np.uint64), s)
     assert not fs.any()
     for f in range(nf):
         want = oracle.frame_compress(src[f * fp:(f + 1) * fp].tobytes(), block_size=1 << 20, block_checksums=True)
@@ -263,8 +265,9 @@ def test_sliced_input_feed(gpu, oracle, monkeypatch):
     # 4 KiB slices (256 per block): the warps outrun the feed all the time and wait on the progress word
     monkeypatch.setenv("LZF_B200_FEED_SLICE", "4096")
     out2 = np.zeros_like(out)
-    fl2, fs2 = gpu.ctx.frames_compress(src, np.arange(nf, dtype=np.uint64) * fp, np.full(nf, fp, np.uint64), out2,
-                                       np.arange(nf, dtype=np.uint64) * bound, np.full(nf, bound, np.uint64), s)
+    with gpu.fresh() as g:
+        fl2, fs2 = g.ctx.frames_compress(src, np.arange(nf, dtype=np.uint64) * fp, np.full(nf, fp, np.uint64), out2,
+                                         np.arange(nf, dtype=np.uint64) * bound, np.full(nf, bound, np.uint64), s)
     assert not fs2.any() and np.array_equal(fl2, fl)
     for f in range(nf):
         assert np.array_equal(out2[f * bound:f * bound + int(fl[f])], out[f * bound:f * bound + int(fl[f])]), f
@@ -305,3 +308,8 @@ def test_packed17_long_matches_never_alias(gpu, oracle):            # ADVICE r1,
 
 def test_short_nonfinal_blocks_with_exact_capacity(gpu, oracle):
     parity.check_short_block_frames(gpu, oracle)
+
+
+def test_raw_compress2_with_history_and_carried_table(gpu, oracle):  # src/raw/compress/mod.rs:165-170
+    parity.check_raw_compress2_with_history(gpu, oracle)
+    parity.check_raw_compress2_with_history(gpu, oracle, table_kind=N.TABLE_U16)

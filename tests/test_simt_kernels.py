@@ -89,8 +89,9 @@ def test_batched_blocks_tables_in_global_scratch(emu, oracle, monkeypatch):
             monkeypatch.delenv("LZF_B200_ENC_SMEM_WARPS", raising=False)
         else:
             monkeypatch.setenv("LZF_B200_ENC_SMEM_WARPS", smem_warps)
-        parity.check_batched_blocks(emu, oracle, inputs, max_block_len=max(len(b) for b in inputs))     # packed slots
-        parity.check_batched_blocks(emu, oracle, small, max_block_len=65536)                            # u16 slots
+        with emu.fresh() as b:
+            parity.check_batched_blocks(b, oracle, inputs, max_block_len=max(len(x) for x in inputs))     # packed slots
+            parity.check_batched_blocks(b, oracle, small, max_block_len=65536)                            # u16 slots
 
 
 def test_frame_compress_with_sliced_input_feed(emu, oracle, monkeypatch, scale=1):
@@ -103,10 +104,11 @@ def test_frame_compress_with_sliced_input_feed(emu, oracle, monkeypatch, scale=1
     data = (W.text(bs + bs // 2, 21).numpy().tobytes() + W.random_bytes(bs, 22).numpy().tobytes() +
             W.lowent(bs // 2, 23).numpy().tobytes() + bytes(bs)) * scale
     assert len(data) % bs == 0
-    for kw in (dict(block_size=bs), dict(block_size=bs, block_checksums=True, content_checksum=False)):
-        st, frame = emu.ctx.frame_compress(data, **kw)
-        assert (st, frame) == oracle.frame_compress(data, **kw)
-    assert emu.ctx.frame_decompress(frame, cap=len(data) + 16)[:3] == (0, 0, data)
+    with emu.fresh() as b:
+        for kw in (dict(block_size=bs), dict(block_size=bs, block_checksums=True, content_checksum=False)):
+            st, frame = b.ctx.frame_compress(data, **kw)
+            assert (st, frame) == oracle.frame_compress(data, **kw)
+        assert b.ctx.frame_decompress(frame, cap=len(data) + 16)[:3] == (0, 0, data)
 
 
 def test_batched_host_frames_with_a_refused_frame(emu, oracle):
@@ -361,3 +363,8 @@ def test_packed17_long_matches_never_alias(emu, oracle):            # ADVICE r1,
 
 def test_short_nonfinal_blocks_with_exact_capacity(emu, oracle):
     parity.check_short_block_frames(emu, oracle)
+
+
+def test_raw_compress2_with_history_and_carried_table(emu, oracle):  # src/raw/compress/mod.rs:165-170
+    parity.check_raw_compress2_with_history(emu, oracle)
+    parity.check_raw_compress2_with_history(emu, oracle, table_kind=N.TABLE_U16)
