@@ -293,6 +293,27 @@ def main():
 
     ctx = N.Context(local_rank)
     peak_gbs, peak_src = measured_peak()
+
+    def copy_ceiling(host_in, dev_in, host_out, dev_out, h2d_bytes, d2h_bytes, reps=3):
+        """What the box's host<->device copy path allows for one e2e step: EVERY rank moves the step's H2D bytes and its
+        D2H bytes at the same time (two streams, pinned memory, nothing else running), released together by a barrier;
+        -> seconds per step (max over ranks).  e2e can not be faster than this, whatever the kernels do."""
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def once():
+            with torch.cuda.stream(s1):
+                dev_in[:h2d_bytes].copy_(host_in[:h2d_bytes], non_blocking=True)
+            with torch.cuda.stream(s2):
+                host_out[:d2h_bytes].copy_(dev_out[:d2h_bytes], non_blocking=True)
+        once(); torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            once()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+        barrier()
+        return max_over_ranks(dt)
     K, Wm = args.steps, max(args.warmup, 3)
     stream = torch.cuda.current_stream().cuda_stream
 
@@ -408,6 +429,14 @@ def main():
                    "d2h_bytes_per_step": int(nb * BLOCK2), "ms_per_step": dt / K * 1e3,
                    "api": "lzf_frames_decompress (host buffers, %d frames of %d blocks, content checksum verified)"
                           % (nframes, BLOCKS_PER_FRAME2)}
+        # the copy ceiling of this box for exactly these bytes (all ranks copying at once, no kernels)
+        h2d_tmp = torch.empty(int(fr_len.sum()), dtype=torch.uint8, device=dev)
+        cdt = copy_ceiling(frames_t, h2d_tmp, out_t, plain, int(fr_len.sum()), int(nb * BLOCK2))
+        del h2d_tmp
+        dec_e2e["ceiling_gbs"] = total_plain / GiB / cdt
+        dec_e2e["ceiling_note"] = ("plaintext GiB/s if the step were ONLY its pinned H2D + D2H copies, both directions at once on "
+                                   "all %d ranks (measured in this run); frac_of_ceiling = value / ceiling_gbs" % world)
+        dec_e2e["frac_of_ceiling"] = dec_e2e["value"] / dec_e2e["ceiling_gbs"]
         del frames_t, out_t
 
     # ---- CPU baseline (rank 0, bounded sample)
@@ -580,6 +609,12 @@ def main():
             # the frames must decode back to the input (checked through the host frame API on 2 frames)
             st_, det_, pl_, _c = ctx.frame_decompress(out_h[: int(fl[0])], cap=fp + 16)
             assert st_ == 0 and np.array_equal(np.frombuffer(pl_, dtype=np.uint8), in_h[:fp])
+            h2d_tmp = torch.empty(e2e_blocks * BLOCK3, dtype=torch.uint8, device=dev)
+            cdt = copy_ceiling(in_t, h2d_tmp, out_t, cbuf, int(e2e_blocks * BLOCK3), min(int(fl.sum()), cbuf.numel(), out_t.numel()))
+            del h2d_tmp
+            comp_section["e2e"]["ceiling_gbs"] = tot / GiB / cdt
+            comp_section["e2e"]["frac_of_ceiling"] = comp_section["e2e"]["value"] / comp_section["e2e"]["ceiling_gbs"]
+            comp_section["e2e"]["ceiling_note"] = "as for decompress: the step's pinned H2D + D2H bytes only, all %d ranks at once" % world
             del in_t, out_t
         if world > 1 and not args.no_gather:
             try:
@@ -823,10 +858,82 @@ def main():
                         "cpu_baseline": {"value": ns5 * BLOCK3 / GiB / t5, "unit": "GiB/s", "cores": cores, "kind": "port",
                                          "sample": "first %d blocks, one run, C port of compress2 with the same HASHLOG" % ns5}})
                     del out5, gbytes
+            # the same 256 blocks with the segmented parse (LZF_OPT_SEGMENT_BYTES): 256 blocks fill 6 % of the warp slots, so every
+            # block is cut into segments parsed side by side and stitched into one LZ4 block — valid LZ4 of the reference's
+            # size (north_star: within 1 %), not its bytes
+            exact_total = None
+            try:
+                run_exact = lambda: ctx.compress_blocks(low, off5, len5, nb5, c5, off5, None, cl5, cs5, None, None, hashlog=12, stream=stream, max_block_len=BLOCK3)
+                run_exact(); torch.cuda.synchronize()
+                exact_total = int(cl5.to(torch.int64).sum().item())
+                ctx.set_option(N.OPT_SEGMENT_BYTES, 65536)
+                for _ in range(2):
+                    run_exact()
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(K):
+                    run_exact()
+                e1.record()
+                torch.cuda.synchronize()
+                seg_ms = e0.elapsed_time(e1)
+                assert int(cs5.abs().sum().item()) == 0
+                seg_total = int(cl5.to(torch.int64).sum().item())
+                ctx.decompress_blocks(c5, off5, cl5, nb5, back5, off5, len5, len5, torch.zeros_like(cl5), cs5, None, stream=stream)
+                torch.cuda.synchronize()
+                assert int(cs5.abs().sum().item()) == 0 and torch.equal(back5, low), "segmented parse round trip failed"
+                res5["hashlog12_segmented"] = {"compress_GiB_per_s": nb5 * BLOCK3 * K / GiB / (seg_ms / 1e3),
+                                               "ratio": float(nb5 * BLOCK3) / float(seg_total),
+                                               "size_vs_exact_parse": seg_total / float(exact_total) - 1.0,
+                                               "note": "LZF_OPT_SEGMENT_BYTES=65536: segments parsed side by side + stitch; round trip bit-exact on the "
+                                                       "device; size relative to the byte-identical parse above"}
+            except Exception as e:
+                res5["hashlog12_segmented"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+            finally:
+                ctx.set_option(N.OPT_SEGMENT_BYTES, 0)
             extra["config5"] = {"workload": "%d x 4 MiB low-entropy blocks (4-symbol alphabet, runs U{1..64}); HASHLOG 12 is the reference's table, "
                                             "14 / 16 are the large-table extension (parity against the oracle run with the same HASHLOG)" % nb5,
                                 "results": res5}
             del low, c5, back5
+
+    # =========================================================================================
+    # the drop-in case: ONE file through CompressionSettings::compress / decompress_frame (host buffers, 64 MiB of text)
+    # =========================================================================================
+    single = None
+    if rank == 0 and not args.no_extra and not args.no_e2e:
+        try:
+            sf = W.TextSource(seed=0x4C5A0006, device="cpu").make(64 << 20).numpy()
+            sset, _ks = N.make_settings()
+            cap_sf = ctx.frame_bound(sset, sf.size)
+
+            def timed(fn, reps=3):
+                fn()
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    r = fn()
+                return (time.perf_counter() - t0) / reps, r
+            t_exact, (st_e, fr_e) = timed(lambda: ctx.frame_compress(sf))
+            ctx.set_option(N.OPT_SEGMENT_BYTES, 65536)
+            try:
+                t_seg, (st_s, fr_s) = timed(lambda: ctx.frame_compress(sf))
+            finally:
+                ctx.set_option(N.OPT_SEGMENT_BYTES, 0)
+            assert st_e == 0 and st_s == 0
+            t_dec, (dst_, ddet_, dplain_, _dc) = timed(lambda: ctx.frame_decompress(fr_s, cap=sf.size + 16))
+            assert dst_ == 0 and np.array_equal(np.frombuffer(dplain_, dtype=np.uint8), sf), "single-file round trip failed"
+            import oracle
+            t0 = time.perf_counter()
+            orc, ofr = oracle.frame_compress(sf.tobytes())
+            t_cpu = time.perf_counter() - t0
+            assert (orc, ofr) == (0, fr_e), "single-file frame differs from the oracle"
+            single = {"workload": "one 64 MiB text file, default CompressionSettings (16 blocks of 4 MiB), host buffers in and out",
+                      "compress_exact_GiB_per_s": sf.size / GiB / t_exact, "compress_segmented_GiB_per_s": sf.size / GiB / t_seg,
+                      "segmented_size_vs_exact": len(fr_s) / float(len(fr_e)) - 1.0,
+                      "decompress_GiB_per_s": sf.size / GiB / t_dec,
+                      "cpu_baseline": {"compress_GiB_per_s": sf.size / GiB / t_cpu, "cores": 1, "kind": "port",
+                                       "sample": "the same file through the C port of compress_internal, one thread (the reference is single-threaded)"},
+                      "note": "exact = byte-identical to the reference (16 warps busy); segmented = LZF_OPT_SEGMENT_BYTES=65536"}
+        except Exception as e:
+            single = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
 
     if rank == 0:
         line = {
@@ -844,6 +951,8 @@ def main():
         }
         if extra is not None:
             line["extra_configs"] = extra
+        if single is not None:
+            line["single_file"] = single
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

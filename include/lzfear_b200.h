@@ -122,6 +122,17 @@ int lzf_create(int device, lzf_ctx** ctx);
 void lzf_destroy(lzf_ctx* ctx);
 /* Human-readable text for the last failing call on this ctx (valid until the next call). */
 const char* lzf_last_error(const lzf_ctx* ctx);
+/* Options of a ctx.
+ *   LZF_OPT_SEGMENT_BYTES   0 (default): every block is parsed exactly like the reference, by one warp; output bytes are
+ *                           the reference's.  >= 65536: a compress call whose blocks cannot fill the GPU (fewer than half
+ *                           the resident warps, e.g. one 64 MiB file = 16 blocks) cuts every block into segments of at
+ *                           least this many bytes, parses them side by side — each from a table primed with the 64 KiB
+ *                           in front of it — and stitches the sequence streams back into ONE LZ4 block.  The result is
+ *                           valid LZ4 that decodes to the input, within a fraction of a percent of the reference's size,
+ *                           but NOT its bytes (BASELINE.json north_star: "compressed size within 1 %"); launches that
+ *                           fill the GPU are unaffected.  Applies to independent blocks without a dictionary. */
+enum { LZF_OPT_SEGMENT_BYTES = 1 };
+int lzf_set_option(lzf_ctx* ctx, int option, uint64_t value);
 /* Number of kernels this ctx has launched so far (bench.py's gpu_launches). */
 uint64_t lzf_launch_count(const lzf_ctx* ctx);
 

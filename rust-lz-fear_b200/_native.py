@@ -25,6 +25,7 @@ P_UNIMPLEMENTED_BLOCKSIZE, P_UNSUPPORTED_VERSION, P_RESERVED_FLAG_BITS, P_RESERV
 TABLE_U32, TABLE_U16 = 0, 1
 INCOMPRESSIBLE = 0x80000000
 ABI_VERSION = 3
+OPT_SEGMENT_BYTES = 1
 
 
 class NativeLibraryError(RuntimeError):
@@ -68,6 +69,7 @@ _PROTOTYPES = {
     "lzf_destroy": (None, [_P]),
     "lzf_last_error": (C.c_char_p, [_P]),
     "lzf_launch_count": (C.c_uint64, [_P]),
+    "lzf_set_option": (C.c_int, [_P, C.c_int, C.c_uint64]),
     "lzf_compress_blocks": (C.c_int, [_P, _P, _P, _P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "lzf_decompress_blocks": (C.c_int, [_P, _P, _P, _P, C.c_uint32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "lzf_xxh32_ranges": (C.c_int, [_P, _P, _P, _P, C.c_uint32, _P, _P]),
@@ -219,6 +221,9 @@ class Context:
         self._check(self._lib.lzf_raw_compress_into(self._h, _np_ptr(a), a.size, table, hashlog, out.ctypes.data,
                                                     int(cap), C.byref(w), C.byref(st)))
         return st.value, out[: w.value].tobytes()
+
+    def set_option(self, option, value):
+        self._check(self._lib.lzf_set_option(self._h, int(option), int(value)))
 
     def table_new(self, table=TABLE_U32, hashlog=12):
         """A device-resident EncoderTable (U32Table::default() / U16Table::default())."""

@@ -68,6 +68,7 @@ struct lzf_slot {
     Buf d_comp;                         // compressed-block scratch (frame compress)
     Buf d_io_in, d_io_out;              // staging of host-buffer calls
     Buf d_dict, d_aux;                  // dictionary copy / dependent-block descriptors and window scratch
+    Buf d_seg;                          // segmented parse: segment descriptors, results and sequence streams
 };
 constexpr int kSlots = 4;
 constexpr uint32_t kMaxSlices = 256;
@@ -86,6 +87,9 @@ struct lzf_ctx {
     // compress: plaintext bytes.  0 = one full wave of the block kernel (one warp per block, 28 warps per SM;
     // the parse is latency-bound, so a chunk with fewer blocks takes just as long), at most 24 GiB
     uint64_t compress_chunk_bytes = 0;
+    // LZF_OPT_SEGMENT_BYTES: 0 = every block is parsed exactly like the reference, by one warp (default).  > 0: a compress
+    // launch that cannot fill the GPU cuts its blocks into segments of at least this many bytes (see SegmentPlanArgs)
+    std::atomic<uint64_t> segment_bytes{0};
     // tuning / test knobs.  The environment is read ONCE, in lzf_create (LZF_B200_*); nothing on a call path calls getenv.
     struct Tuning {
         bool trace = false;                     // LZF_B200_TRACE: phase times of the host-buffer compress chunks on stderr
@@ -207,7 +211,7 @@ extern "C" void lzf_destroy(lzf_ctx* c) {
         if (sl.ev_feed0) cudaEventDestroy(sl.ev_feed0);
         if (sl.ev_feed1) cudaEventDestroy(sl.ev_feed1);
         if (sl.h_seq) cudaFreeHost(sl.h_seq);
-        Buf* dev[] = {&sl.d_tables, &sl.d_desc, &sl.d_res, &sl.d_comp, &sl.d_io_in, &sl.d_io_out, &sl.d_dict, &sl.d_aux};
+        Buf* dev[] = {&sl.d_tables, &sl.d_desc, &sl.d_res, &sl.d_comp, &sl.d_io_in, &sl.d_io_out, &sl.d_dict, &sl.d_aux, &sl.d_seg};
         for (Buf* b : dev) if (b->p) cudaFree(b->p);
         Buf* host[] = {&sl.h_desc, &sl.h_res};
         for (Buf* b : host) if (b->p) cudaFreeHost(b->p);
@@ -219,6 +223,17 @@ extern "C" void lzf_destroy(lzf_ctx* c) {
         if (sl.side) cudaStreamDestroy(sl.side);
     }
     delete c;
+}
+
+extern "C" int lzf_set_option(lzf_ctx* c, int option, uint64_t value) {
+    if (!c) return LZF_ERR_INVALID_ARG;
+    switch (option) {
+        case LZF_OPT_SEGMENT_BYTES:
+            if (value && value < 65536) return fail(c, LZF_ERR_INVALID_ARG, "segments are at least 64 KiB");
+            c->segment_bytes.store(value);
+            return LZF_SUCCESS;
+        default: return fail(c, LZF_ERR_INVALID_ARG, "unknown option");
+    }
 }
 
 extern "C" const char* lzf_last_error(const lzf_ctx* c) { return c ? c->err.c_str() : "null ctx"; }
@@ -256,23 +271,102 @@ struct InputFeed {
     std::function<int()> start;
 };
 
+// Segments per block for a launch of `nblocks` independent blocks of at most max_block_len bytes (1 = no segmentation):
+// as many as it takes to offer the block kernel one warp per resident slot, segments no shorter than the option asks.
+uint32_t plan_segments(const lzf_ctx* c, uint32_t nblocks, uint32_t max_block_len, uint32_t table_kind) {
+    const uint64_t seg_min = c->segment_bytes.load();
+    if (!seg_min || !nblocks || table_kind != LZF_TABLE_U32 || max_block_len < 2 * seg_min || max_block_len > (16u << 20)) return 1;
+    const uint64_t wave = (uint64_t)c->num_sms * 28;              // kEncodeBigWarps resident warps per SM
+    if ((uint64_t)nblocks * 2 > wave) return 1;
+    uint64_t S = (wave + nblocks - 1) / nblocks;
+    if (S > max_block_len / seg_min) S = max_block_len / seg_min;
+    if (S > 64) S = 64;
+    return S < 2 ? 1u : (uint32_t)S;
+}
+
 int compress_blocks_impl(lzf_ctx* c, const uint8_t* d_in, const uint64_t* d_in_off, const uint32_t* d_in_len,
                          uint32_t nblocks, uint32_t hashlog, uint32_t table_kind, uint32_t max_block_len,
                          uint8_t* d_out, const uint64_t* d_out_off, const uint32_t* d_out_cap,
                          uint32_t* d_out_len, int32_t* d_status, uint32_t* d_xxh_plain, uint32_t* d_xxh_stored,
-                         cudaStream_t s, const lzf::EncodeArgs* chains = nullptr, const InputFeed* feed = nullptr) {
+                         cudaStream_t s, const lzf::EncodeArgs* chains = nullptr, const InputFeed* feed = nullptr);
+
+// The segmented parse of SegmentPlanArgs: plan -> one encode launch over all segments -> stitch (-> block checksums).
+int compress_blocks_segmented(lzf_ctx* c, const uint8_t* d_in, const uint64_t* d_in_off, const uint32_t* d_in_len,
+                              uint32_t nblocks, uint32_t hashlog, uint32_t max_block_len, uint32_t S,
+                              uint8_t* d_out, const uint64_t* d_out_off, const uint32_t* d_out_cap,
+                              uint32_t* d_out_len, int32_t* d_status, uint32_t* d_xxh_plain, uint32_t* d_xxh_stored,
+                              cudaStream_t s) {
+    const uint32_t seg_len = (uint32_t)((((uint64_t)max_block_len + S - 1) / S + 15) / 16 * 16);
+    const uint32_t seg_cap = (uint32_t)((lzf_compress_bound(seg_len) + 15) / 16 * 16);
+    const size_t N = (size_t)nblocks * S;
+    Arena ar;
+    const size_t o_in_off = ar.take(N * 8), o_out_off = ar.take(N * 8);
+    const size_t o_in_len = ar.take(N * 4), o_pfx = ar.take(N * 4), o_cap = ar.take(N * 4), o_cf = ar.take(N * 4), o_cc = ar.take(N * 4);
+    const size_t o_abs = ar.take(N * 4), o_olen = ar.take(N * 4), o_st = ar.take(N * 4), o_fp = ar.take(N * 4), o_fl = ar.take(N * 4);
+    const size_t o_jobs = ar.take((size_t)nblocks * (S + 1) * sizeof(lzf::StitchJob));
+    const size_t o_h = ar.take((size_t)nblocks * 8 * 4);
+    const size_t o_streams = ar.take(N * seg_cap + 64);
+    lzf_slot* sl = cur_slot(c);
+    int rc;
+    if ((rc = ensure_dev(c, sl->d_seg, ar.used))) return rc;
+    uint8_t* g = (uint8_t*)sl->d_seg.p;
+    lzf::SegmentPlanArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.nblocks = nblocks; pa.nseg = S; pa.seg_len = seg_len; pa.seg_cap = seg_cap;
+    pa.in_off = d_in_off; pa.in_len = d_in_len;
+    pa.seg_in_off = (uint64_t*)(g + o_in_off); pa.seg_in_len = (uint32_t*)(g + o_in_len); pa.seg_prefix = (uint32_t*)(g + o_pfx);
+    pa.seg_out_off = (uint64_t*)(g + o_out_off); pa.seg_out_cap = (uint32_t*)(g + o_cap);
+    pa.seg_chain_first = (uint32_t*)(g + o_cf); pa.seg_chain_count = (uint32_t*)(g + o_cc); pa.seg_abs = (uint32_t*)(g + o_abs);
+    LZF_LAUNCHED(c, lzf_launch_segment_plan(&pa, s), 1);
+    lzf::EncodeArgs ch;
+    memset(&ch, 0, sizeof(ch));
+    ch.prefix_len = pa.seg_prefix; ch.abs_base = pa.seg_abs; ch.prime_len = pa.seg_prefix;
+    ch.chain_first = pa.seg_chain_first; ch.chain_count = pa.seg_chain_count; ch.nchains = (uint32_t)N;
+    ch.max_pos = (uint64_t)LZF_WINDOW_SIZE + seg_len;
+    ch.fin_pos = (uint32_t*)(g + o_fp); ch.fin_lit = (uint32_t*)(g + o_fl);
+    rc = compress_blocks_impl(c, d_in, pa.seg_in_off, pa.seg_in_len, (uint32_t)N, hashlog, LZF_TABLE_U32, seg_len, g + o_streams,
+                              pa.seg_out_off, pa.seg_out_cap, (uint32_t*)(g + o_olen), (int32_t*)(g + o_st), nullptr, nullptr, s, &ch);
+    if (rc) return rc;
+    lzf::StitchArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    sa.nblocks = nblocks; sa.nseg = S; sa.seg_len = seg_len;
+    sa.in = d_in; sa.in_off = d_in_off; sa.in_len = d_in_len;
+    sa.seg = g + o_streams; sa.seg_out_off = pa.seg_out_off; sa.seg_out_len = (const uint32_t*)(g + o_olen);
+    sa.seg_status = (const int32_t*)(g + o_st); sa.fin_pos = ch.fin_pos; sa.fin_lit = ch.fin_lit;
+    sa.out = d_out; sa.out_off = d_out_off; sa.out_cap = d_out_cap; sa.out_len = d_out_len; sa.status = d_status;
+    sa.jobs = (lzf::StitchJob*)(g + o_jobs);
+    uint64_t* hh = (uint64_t*)(g + o_h);
+    if (d_xxh_stored) { sa.hash_off = hh; sa.hash_len = hh + nblocks; }
+    if (d_xxh_plain) { sa.plain_off = hh + 2 * (size_t)nblocks; sa.plain_len = hh + 3 * (size_t)nblocks; }
+    LZF_LAUNCHED(c, lzf_launch_stitch(&sa, s), 2);
+    if (d_xxh_stored) LZF_LAUNCHED(c, lzf_launch_xxh32_ranges(nullptr, sa.hash_off, sa.hash_len, nblocks, d_xxh_stored, s), 1);
+    if (d_xxh_plain) LZF_LAUNCHED(c, lzf_launch_xxh32_ranges(nullptr, sa.plain_off, sa.plain_len, nblocks, d_xxh_plain, s), 1);
+    return LZF_SUCCESS;
+}
+
+int compress_blocks_impl(lzf_ctx* c, const uint8_t* d_in, const uint64_t* d_in_off, const uint32_t* d_in_len,
+                         uint32_t nblocks, uint32_t hashlog, uint32_t table_kind, uint32_t max_block_len,
+                         uint8_t* d_out, const uint64_t* d_out_off, const uint32_t* d_out_cap,
+                         uint32_t* d_out_len, int32_t* d_status, uint32_t* d_xxh_plain, uint32_t* d_xxh_stored,
+                         cudaStream_t s, const lzf::EncodeArgs* chains, const InputFeed* feed) {
     if (hashlog == 0) hashlog = 12;
     if (hashlog < 8 || hashlog > 16) return fail(c, LZF_ERR_INVALID_ARG, "hashlog must be 0 or 8..16");
     if (table_kind != LZF_TABLE_U32 && table_kind != LZF_TABLE_U16) return fail(c, LZF_ERR_INVALID_ARG, "table_kind");
     if (nblocks == 0) return LZF_SUCCESS;
     if ((!d_in && !chains) || !d_in_off || !d_in_len || !d_out || !d_out_off || !d_out_len || !d_status)
         return fail(c, LZF_ERR_INVALID_ARG, "null pointer");
+    if (!chains && !feed) {
+        const uint32_t S = plan_segments(c, nblocks, max_block_len, table_kind);
+        if (S > 1) return compress_blocks_segmented(c, d_in, d_in_off, d_in_len, nblocks, hashlog, max_block_len, S, d_out, d_out_off,
+                                                    d_out_cap, d_out_len, d_status, d_xxh_plain, d_xxh_stored, s);
+    }
     lzf::EncodeArgs a;
     memset(&a, 0, sizeof(a));
     if (chains) {
         a.prefix_len = chains->prefix_len; a.abs_base = chains->abs_base; a.prime_len = chains->prime_len;
         a.chain_first = chains->chain_first; a.chain_count = chains->chain_count; a.nchains = chains->nchains;
         a.max_pos = chains->max_pos; a.table_io = chains->table_io;
+        a.fin_pos = chains->fin_pos; a.fin_lit = chains->fin_lit;
     }
     a.in = d_in; a.in_off = d_in_off; a.in_len = d_in_len; a.nblocks = nblocks;
     a.hashlog = hashlog; a.table_kind = table_kind;
@@ -812,7 +906,8 @@ int frames_compress_core(lzf_ctx* c, const lzf_settings* s, const uint8_t* d_in,
 
     LZF_CU(c, cudaMemcpyAsync(d, h, da.used, cudaMemcpyHostToDevice, st));
     if (s->content_checksum) LZF_CU(c, cudaEventRecord(cur_slot(c)->ev_fork, st));
-    const bool fed = feed && !chained && nblocks;       // the slice feed only serves independent blocks without history
+    // the slice feed only serves independent blocks without history, parsed one warp per block
+    const bool fed = feed && !chained && nblocks && plan_segments(c, nblocks, max_block_len, LZF_TABLE_U32) == 1;
     if (feed && !fed) { if ((rc = feed->start())) return rc; LZF_CU(c, cudaStreamWaitEvent(st, feed->ready, 0)); }
     if (nblocks) {
         lzf::EncodeArgs ch;

@@ -491,6 +491,7 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int n_smem_warps) {
                         if ((endmask >> w) & 1u) {
                             // final literal-only sequence  :178-190.  The probes before the end lane did their
                             // table.replace: a later block of the same chain (dependent blocks) sees them.
+                            if (a.fin_pos && lane == 0) { a.fin_pos[b] = opos; a.fin_lit[b] = len - lit_start; }
                             if (!emit_sequence(out, opos, cap, in, lit_start, len - lit_start, 0, 0, true, false, 0, 0)) status = LZF_WRITER_FULL;
                             ins |= ((1u << w) - 1u) & ~((1u << s) - 1u);
                             done = true;
@@ -518,6 +519,7 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int n_smem_warps) {
                         }
                         w = __ffs(trig) - 1;
                         if ((endmask >> w) & 1u) {
+                            if (a.fin_pos && lane == 0) { a.fin_pos[b] = opos; a.fin_lit[b] = len - lit_start; }
                             if (!emit_sequence(out, opos, cap, in, lit_start, len - lit_start, 0, 0, true, false, 0, 0)) status = LZF_WRITER_FULL;
                             ins |= ((1u << w) - 1u) & ~((1u << s) - 1u);
                             done = true;

@@ -276,7 +276,141 @@ __global__ void __launch_bounds__(64) frame_walk_kernel(WalkArgs a) {
     if (a.mode == 0) a.frames[f] = w;
 }
 
+// ------------------------------------------------------------------------------------------
+// segmented parse: descriptors of the segments, and stitching their sequence streams into one block
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) segment_plan_kernel(SegmentPlanArgs a) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.nblocks * a.nseg) return;
+    const uint32_t b = i / a.nseg, k = i % a.nseg;
+    const uint64_t start = (uint64_t)k * a.seg_len;
+    const uint32_t n = a.in_len[b];
+    a.seg_in_off[i] = a.in_off[b] + (start < n ? start : n);
+    a.seg_in_len[i] = start < n ? (uint32_t)min((uint64_t)a.seg_len, (uint64_t)n - start) : 0u;
+    a.seg_prefix[i] = start < n ? (uint32_t)min(start, (uint64_t)LZF_WINDOW_SIZE) : 0u;   // the window in front of the segment primes its table
+    a.seg_out_off[i] = (uint64_t)i * a.seg_cap;
+    a.seg_out_cap[i] = a.seg_cap;
+    a.seg_chain_first[i] = i; a.seg_chain_count[i] = 1; a.seg_abs[i] = 0;
+}
+
+__device__ __forceinline__ uint32_t lsic_bytes(uint32_t v) { return v < 15 ? 0u : (v - 15u) / 255u + 1u; }
+__device__ __forceinline__ uint8_t* put_lsic(uint8_t* o, uint32_t v) {          // write_lsic_tail, compress/mod.rs:243-260
+    if (v < 15) return o;
+    v -= 15;
+    while (v >= 255) { *o++ = 0xff; v -= 255; }
+    *o++ = (uint8_t)v;
+    return o;
+}
+
+// One thread per block walks its S segment streams in order.  Every stream is a complete LZ4 block of its own: it ends
+// in a literal-only sequence.  Those closing literals become the head of the next stream's first sequence, whose token
+// and length bytes are rewritten for the joint count (a segment without any match just passes its bytes on); the block
+// ends with one closing sequence.  Literal bytes are always taken from the plaintext: they ARE the input bytes.
+// Pass 0 sizes everything (NoPartialWrites: a block that does not fit its capacity is refused as a whole, compress.rs:
+// 242-256,298-301), pass 1 writes the headers and the copy jobs.
+__global__ void __launch_bounds__(64) stitch_plan_kernel(StitchArgs a) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.nblocks) return;
+    const uint32_t n = a.in_len[b];
+    const uint32_t cap = a.out_cap ? a.out_cap[b] : n;
+    uint8_t* out = a.out + a.out_off[b];
+    StitchJob* jobs = a.jobs + (size_t)b * (a.nseg + 1);
+    const uint64_t in0 = a.in_off[b];
+    int status = LZF_OK;
+    uint64_t total = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        uint64_t o = 0;            // output position
+        uint32_t carry = 0;        // literals waiting for the next match: the input bytes right in front of `pos`
+        uint64_t pos = 0;          // input position where the current segment starts
+        for (uint32_t k = 0; k <= a.nseg; k++) {
+            StitchJob j{0, 0, 0, 0, 0, 0};
+            const uint32_t i = b * a.nseg + k;
+            const uint64_t left = pos < n ? (uint64_t)n - pos : 0;
+            const uint32_t slen = k < a.nseg ? (uint32_t)(left < a.seg_len ? left : a.seg_len) : 0u;
+            if (k < a.nseg && slen) {
+                if (a.seg_status[i] != LZF_OK) status = LZF_PANIC;       // (scratch is sized by the worst case: cannot happen)
+                const uint8_t* x = a.seg + a.seg_out_off[i];
+                const uint32_t f = a.fin_pos[i];
+                if (f == 0) {
+                    carry += slen;                                       // no match in this segment: all of it is literals
+                } else {
+                    // first sequence: token, literal length A (read_lsic), header bytes h
+                    const uint32_t tok = x[0];
+                    uint32_t A = tok >> 4, h = 1;
+                    if (A == 15) { uint32_t e; do { e = x[h++]; A += e; } while (e == 255); }
+                    const uint32_t L = carry + A;
+                    const uint64_t hdr = 1 + lsic_bytes(L);
+                    if (pass) {
+                        uint8_t* q = out + o;
+                        *q++ = (uint8_t)(((L < 15 ? L : 15) << 4) | (tok & 15u));
+                        put_lsic(q, L);
+                        j.lit_src = in0 + pos - carry; j.lit_dst = a.out_off[b] + o + hdr; j.lit_len = carry;
+                        j.body_src = a.seg_out_off[i] + h; j.body_dst = a.out_off[b] + o + hdr + carry; j.body_len = f - h;
+                    }
+                    o += hdr + carry + (f - h);
+                    carry = a.fin_lit[i];
+                }
+                pos += slen;
+            } else if (k == a.nseg && n) {
+                // the block's closing literal-only sequence (:178-190)
+                const uint64_t hdr = 1 + lsic_bytes(carry);
+                if (pass) {
+                    uint8_t* q = out + o;
+                    *q++ = (uint8_t)((carry < 15 ? carry : 15) << 4);
+                    put_lsic(q, carry);
+                    j.lit_src = in0 + n - carry; j.lit_dst = a.out_off[b] + o + hdr; j.lit_len = carry;
+                }
+                o += hdr + carry;
+            }
+            if (pass) jobs[k] = j;
+        }
+        if (pass == 0) {
+            total = o;
+            if (status == LZF_OK && total > cap) status = LZF_WRITER_FULL;
+            if (status != LZF_OK) {
+                for (uint32_t k = 0; k <= a.nseg; k++) jobs[k] = StitchJob{0, 0, 0, 0, 0, 0};
+                break;
+            }
+        }
+    }
+    a.out_len[b] = status == LZF_OK ? (uint32_t)total : 0u;
+    a.status[b] = status;
+    if (a.hash_off) {        // what the frame stores for this block: the compressed bytes, or the plaintext (compress.rs:259-263)
+        a.hash_off[b] = status == LZF_OK ? (uint64_t)(uintptr_t)(a.out + a.out_off[b]) : (uint64_t)(uintptr_t)(a.in + in0);
+        a.hash_len[b] = status == LZF_OK ? total : n;
+    }
+    if (a.plain_off) { a.plain_off[b] = (uint64_t)(uintptr_t)(a.in + in0); a.plain_len[b] = n; }
+}
+
+// grid = (blocks * (S + 1) jobs, 64 KiB slices): the carried literals (from the plaintext) and the body (from the segment's stream)
+__global__ void __launch_bounds__(256) stitch_copy_kernel(StitchArgs a) {
+    const StitchJob j = a.jobs[blockIdx.x];
+    const unsigned warp = threadIdx.x >> 5;
+    const uint32_t longest = j.lit_len > j.body_len ? j.lit_len : j.body_len;
+    for (uint64_t s0 = (uint64_t)blockIdx.y * kSliceBytes + (uint64_t)warp * 8192; s0 < longest; s0 += (uint64_t)gridDim.y * kSliceBytes) {
+        if (s0 < j.lit_len) warp_copy(a.out + j.lit_dst + s0, a.in + j.lit_src + s0, min((uint64_t)8192, (uint64_t)j.lit_len - s0));
+        if (s0 < j.body_len) warp_copy(a.out + j.body_dst + s0, a.seg + j.body_src + s0, min((uint64_t)8192, (uint64_t)j.body_len - s0));
+    }
+}
+
 }  // namespace lzf
+
+extern "C" int lzf_launch_segment_plan(const lzf::SegmentPlanArgs* a, cudaStream_t s) {
+    const uint32_t n = a->nblocks * a->nseg;
+    if (!n) return 0;
+    LZF_LAUNCH(lzf::segment_plan_kernel, (n + 127) / 128, 128, 0, s, *a);
+    return (int)cudaGetLastError();
+}
+extern "C" int lzf_launch_stitch(const lzf::StitchArgs* a, cudaStream_t s) {
+    if (!a->nblocks) return 0;
+    LZF_LAUNCH(lzf::stitch_plan_kernel, (a->nblocks + 63) / 64, 64, 0, s, *a);
+    // a job usually moves one segment's stream; literals that several all-literal segments passed on take more trips
+    uint32_t slices = (uint32_t)(((uint64_t)a->seg_len + lzf::kSliceBytes - 1) / lzf::kSliceBytes);
+    if (slices == 0) slices = 1;
+    dim3 grid(a->nblocks * (a->nseg + 1), slices);
+    LZF_LAUNCH(lzf::stitch_copy_kernel, grid, 256, 0, s, *a);
+    return (int)cudaGetLastError();
+}
 
 extern "C" int lzf_launch_xxh32_ranges(const uint8_t* data, const uint64_t* off, const uint64_t* len,
                                        uint32_t nranges, uint32_t* hash, cudaStream_t s) {

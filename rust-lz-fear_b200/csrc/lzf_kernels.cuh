@@ -32,6 +32,29 @@ struct EncodeArgs {
     // tuning knobs, read from the environment ONCE by lzf_create (0 = default): plain u32 slots where packed ones
     // would do / 1 + the number of warps per CTA whose table may live in shared memory
     uint32_t tune_u32_slots; uint32_t tune_smem_warps_p1;
+    // internal (segmented parse): where the closing literal-only sequence of block b starts in its output, and how
+    // many literals it holds (null = not wanted)
+    uint32_t* fin_pos; uint32_t* fin_lit;
+};
+// Segmented parse (lzf_set_option LZF_OPT_SEGMENT_BYTES): a launch with too few blocks to fill the GPU cuts every block
+// into S segments that are parsed side by side, each from a table primed with the 64 KiB in front of it, and stitches
+// the S sequence streams back into one LZ4 block.  Valid LZ4 of (almost) the reference's size — not its bytes.
+struct SegmentPlanArgs {
+    uint32_t nblocks, nseg, seg_len, seg_cap;            // S segments per block of seg_len bytes, seg_cap bytes of scratch each
+    const uint64_t* in_off; const uint32_t* in_len;      // the blocks
+    uint64_t* seg_in_off; uint32_t* seg_in_len; uint32_t* seg_prefix; uint64_t* seg_out_off; uint32_t* seg_out_cap;
+    uint32_t* seg_chain_first; uint32_t* seg_chain_count; uint32_t* seg_abs;
+};
+struct StitchJob { uint64_t lit_src, lit_dst, body_src, body_dst; uint32_t lit_len, body_len; };
+struct StitchArgs {
+    uint32_t nblocks, nseg, seg_len;
+    const uint8_t* in; const uint64_t* in_off; const uint32_t* in_len;                   // plaintext blocks
+    const uint8_t* seg; const uint64_t* seg_out_off; const uint32_t* seg_out_len;        // per-segment streams
+    const int32_t* seg_status; const uint32_t* fin_pos; const uint32_t* fin_lit;
+    uint8_t* out; const uint64_t* out_off; const uint32_t* out_cap;                      // the blocks' outputs
+    uint32_t* out_len; int32_t* status;
+    StitchJob* jobs;                                                                     // nblocks * (nseg + 1)
+    uint64_t* hash_off; uint64_t* hash_len; uint64_t* plain_off; uint64_t* plain_len;    // nullable: absolute ranges for the block checksums
 };
 struct StageArgs {      // [dictionary | block] staging copies for blocks whose history is the dictionary
     uint32_t n; const uint8_t* dict; uint32_t dlen;
@@ -99,5 +122,7 @@ int lzf_launch_stage_dict(const lzf::StageArgs* a, uint32_t max_block_len, cudaS
 int lzf_launch_layout(const lzf::LayoutArgs* a, cudaStream_t s);
 int lzf_launch_assemble(const lzf::AssembleArgs* a, uint32_t max_block_len, cudaStream_t s);
 int lzf_launch_walk(const lzf::WalkArgs* a, cudaStream_t s);
+int lzf_launch_segment_plan(const lzf::SegmentPlanArgs* a, cudaStream_t s);
+int lzf_launch_stitch(const lzf::StitchArgs* a, cudaStream_t s);
 }
 

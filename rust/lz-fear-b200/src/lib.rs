@@ -1,0 +1,317 @@
+//! Safe wrappers over `lz-fear-b200-sys`.  The names, argument meaning and error behaviour are the ones of
+//! `lz-fear` 0.2 (reference: /root/reference/src), so that `lz-fear` itself can keep `#![forbid(unsafe_code)]` and only
+//! swap the bodies of its two hot call sites behind a cargo feature (see rust/patches/lz-fear-b200-feature.patch):
+//!
+//!   * `compress2(&in_buffer, window_offset, &mut table, &mut NoPartialWrites(..))`   src/framed/compress.rs:242-243
+//!   * `raw::decompress_raw(buf, dec_prefix, output, self.block_maxsize)`             src/framed/decompress.rs:247-248
+//!
+//! There is no CPU fallback: every call needs a CUDA device and fails with an `io::Error` otherwise.
+//! (Written for a toolchain this repository's build image does not have — it is checked against the C header by
+//! tests/test_abi.py, not compiled here.)
+use lz_fear_b200_sys as sys;
+use std::ffi::CStr;
+use std::io;
+use std::sync::Mutex;
+
+/// One context (CUDA device 0 unless `LZFEAR_B200_DEVICE` says otherwise) shared by the process; calls serialise on it.
+struct Ctx(*mut sys::lzf_ctx);
+unsafe impl Send for Ctx {}
+
+fn with_ctx<R>(f: impl FnOnce(*mut sys::lzf_ctx) -> R) -> io::Result<R> {
+    static CTX: Mutex<Option<Ctx>> = Mutex::new(None);
+    let mut guard = CTX.lock().unwrap();
+    if guard.is_none() {
+        let device = std::env::var("LZFEAR_B200_DEVICE").ok().and_then(|v| v.parse().ok()).unwrap_or(0);
+        let mut p: *mut sys::lzf_ctx = std::ptr::null_mut();
+        let rc = unsafe { sys::lzf_create(device, &mut p) };
+        if rc != sys::LZF_SUCCESS {
+            return Err(io::Error::new(io::ErrorKind::Other, format!("lzf_create failed ({}): no CUDA device / driver — there is no CPU fallback", rc)));
+        }
+        *guard = Some(Ctx(p));
+    }
+    Ok(f(guard.as_ref().unwrap().0))
+}
+
+fn call_error(ctx: *mut sys::lzf_ctx, rc: i32) -> io::Error {
+    let msg = unsafe { CStr::from_ptr(sys::lzf_last_error(ctx)) }.to_string_lossy().into_owned();
+    io::Error::new(io::ErrorKind::Other, format!("liblzfear_b200 call failed ({}): {}", rc, msg))
+}
+
+pub mod raw {
+    use super::*;
+
+    /// `raw::DecodeError` (src/raw/decompress.rs:7-17), same variants, same order as the C status codes 1..4.
+    #[derive(Debug, thiserror::Error, PartialEq, Eq)]
+    pub enum DecodeError {
+        #[error("input ended prematurely")]
+        UnexpectedEnd,
+        #[error("the output would exceed the configured limit")]
+        MemoryLimitExceeded,
+        #[error("deduplication offset of zero")]
+        ZeroDeduplicationOffset,
+        #[error("deduplication offset points before the start of the history")]
+        InvalidDeduplicationOffset,
+    }
+
+    /// Which `EncoderTable` of the reference a device table mirrors (src/raw/compress/mod.rs:27-36,78-101).
+    pub trait EncoderTable {
+        const KIND: u32;
+        fn payload_size_limit() -> usize;
+        #[doc(hidden)]
+        fn handle(&mut self) -> io::Result<*mut sys::lzf_table>;
+        /// `EncoderTable::offset` (:72-74)
+        fn offset(&mut self, offset: usize);
+    }
+
+    macro_rules! device_table {
+        ($name:ident, $kind:expr, $limit:expr) => {
+            /// A device-resident table with the reference's semantics; `Default` = a zeroed table.
+            pub struct $name { h: *mut sys::lzf_table, pending_offset: u64 }
+            unsafe impl Send for $name {}
+            impl Default for $name {
+                fn default() -> Self { $name { h: std::ptr::null_mut(), pending_offset: 0 } }
+            }
+            impl EncoderTable for $name {
+                const KIND: u32 = $kind;
+                fn payload_size_limit() -> usize { $limit }
+                fn handle(&mut self) -> io::Result<*mut sys::lzf_table> {
+                    if self.h.is_null() {
+                        let mut h: *mut sys::lzf_table = std::ptr::null_mut();
+                        let rc = with_ctx(|c| unsafe { sys::lzf_table_create(c, $kind, 12, &mut h) })?;
+                        if rc != sys::LZF_SUCCESS { return Err(io::Error::new(io::ErrorKind::Other, "lzf_table_create")); }
+                        self.h = h;
+                    }
+                    if self.pending_offset != 0 {
+                        let by = std::mem::take(&mut self.pending_offset);
+                        let h = self.h;
+                        with_ctx(|c| unsafe { sys::lzf_table_offset(c, h, by) })?;
+                    }
+                    Ok(self.h)
+                }
+                fn offset(&mut self, offset: usize) { self.pending_offset += offset as u64; }
+            }
+            impl Drop for $name {
+                fn drop(&mut self) {
+                    if !self.h.is_null() {
+                        let h = self.h;
+                        let _ = with_ctx(|c| unsafe { sys::lzf_table_destroy(c, h) });
+                    }
+                }
+            }
+        };
+    }
+    device_table!(U32Table, sys::LZF_TABLE_U32 as u32, std::u32::MAX as usize);
+    device_table!(U16Table, sys::LZF_TABLE_U16 as u32, std::u16::MAX as usize);
+
+    /// `compress2(input, cursor, &mut table, NoPartialWrites(out))` (src/raw/compress/mod.rs:165-238 with the bounded
+    /// writer of src/framed/compress.rs:294-308): `input[..cursor]` is match-only history, the table keeps its entries.
+    /// `Err(ConnectionAborted)` = the writer refused a write: the caller stores the block raw (compress.rs:250-255).
+    pub fn compress2<T: EncoderTable>(input: &[u8], cursor: usize, table: &mut T, out: &mut [u8]) -> io::Result<usize> {
+        let h = table.handle()?;
+        let (mut written, mut status) = (0usize, 0i32);
+        let rc = with_ctx(|c| {
+            let rc = unsafe { sys::lzf_raw_compress2(c, input.as_ptr(), input.len(), cursor, h, out.as_mut_ptr(), out.len(), &mut written, &mut status) };
+            if rc != sys::LZF_SUCCESS { Err(call_error(c, rc)) } else { Ok(()) }
+        })?;
+        rc?;
+        match status {
+            sys::LZF_OK => Ok(written),
+            sys::LZF_WRITER_FULL => Err(io::ErrorKind::ConnectionAborted.into()),
+            _ => panic!("EncoderTable contract violated"),          // src/raw/compress/mod.rs:67,92,167
+        }
+    }
+
+    /// The name BASELINE.json's north_star uses: `compress2` from a fresh `U32Table` at cursor 0 into a slice.
+    pub fn compress_into(input: &[u8], out: &mut [u8]) -> io::Result<usize> {
+        let (mut written, mut status) = (0usize, 0i32);
+        let rc = with_ctx(|c| {
+            let rc = unsafe { sys::lzf_raw_compress_into(c, input.as_ptr(), input.len(), sys::LZF_TABLE_U32 as u32, 12, out.as_mut_ptr(), out.len(), &mut written, &mut status) };
+            if rc != sys::LZF_SUCCESS { Err(call_error(c, rc)) } else { Ok(()) }
+        })?;
+        rc?;
+        match status {
+            sys::LZF_OK => Ok(written),
+            sys::LZF_WRITER_FULL => Err(io::ErrorKind::ConnectionAborted.into()),
+            _ => panic!("EncoderTable contract violated"),
+        }
+    }
+
+    /// `raw::decompress_raw(input, prefix, output, output_limit)` (src/raw/decompress.rs:58-138): appends to `output`;
+    /// bytes already in it are addressable history, `prefix` lies behind them.
+    pub fn decompress_raw(input: &[u8], prefix: &[u8], output: &mut Vec<u8>, output_limit: usize) -> Result<(), DecodeError> {
+        // history = prefix ++ what is already in the Vec; the limit counts the whole Vec (:72)
+        let joined: Vec<u8>;
+        let hist: &[u8] = if output.is_empty() { prefix } else { joined = [prefix, &output[..]].concat(); &joined };
+        let old = output.len();
+        let limit = output_limit.saturating_sub(old);
+        // literals are not limit-checked (:65-67): at most input.len() of them on top of the limit
+        let cap = limit.saturating_add(input.len());
+        output.resize(old + cap, 0);
+        let (mut n, mut status) = (0usize, 0i32);
+        let res = with_ctx(|c| unsafe {
+            sys::lzf_raw_decompress(c, input.as_ptr(), input.len(), hist.as_ptr(), hist.len(), output[old..].as_mut_ptr(), cap, limit, &mut n, &mut status)
+        });
+        let rc = res.expect("liblzfear_b200: no CUDA device (there is no CPU fallback)");
+        assert_eq!(rc, sys::LZF_SUCCESS, "liblzfear_b200 call failed");
+        output.truncate(old + n.min(cap));
+        match status {
+            sys::LZF_OK => Ok(()),
+            sys::LZF_UNEXPECTED_END => Err(DecodeError::UnexpectedEnd),
+            sys::LZF_MEMORY_LIMIT_EXCEEDED => Err(DecodeError::MemoryLimitExceeded),
+            sys::LZF_ZERO_DEDUP_OFFSET => Err(DecodeError::ZeroDeduplicationOffset),
+            _ => Err(DecodeError::InvalidDeduplicationOffset),
+        }
+    }
+}
+
+pub mod framed {
+    use super::*;
+    use std::io::{Read, Write};
+
+    /// `CompressionError` (src/framed/compress.rs:15-23)
+    #[derive(Debug, thiserror::Error)]
+    pub enum CompressionError {
+        #[error("error reading from the input you gave me")]
+        ReadError(io::Error),
+        #[error("error writing to the output you gave me")]
+        WriteError(#[from] io::Error),
+        #[error("the block size you asked for is not supported")]
+        InvalidBlockSize,
+    }
+
+    /// `DecompressionError` (src/framed/decompress.rs:16-36)
+    #[derive(Debug, thiserror::Error)]
+    pub enum DecompressionError {
+        #[error("error reading from the input you gave me")]
+        InputError(#[from] io::Error),
+        #[error("the raw LZ4 decompression failed (data corruption?)")]
+        CodecError(raw::DecodeError),
+        #[error("invalid header")]
+        HeaderParseError(i32),
+        #[error("wrong magic number in file header")]
+        WrongMagic(u32),
+        #[error("the header checksum was invalid")]
+        HeaderChecksumFail,
+        #[error("a block checksum was invalid")]
+        BlockChecksumFail,
+        #[error("the frame checksum was invalid")]
+        FrameChecksumFail,
+        #[error("stream contains a compressed block with a size so large we can't even compute it")]
+        BlockLengthOverflow,
+        #[error("a block decompressed to more data than allowed")]
+        BlockSizeOverflow,
+    }
+
+    /// `CompressionSettings` (src/framed/compress.rs:36-133): same builder, same defaults (:44-55).
+    #[derive(Clone)]
+    pub struct CompressionSettings<'a> {
+        independent_blocks: bool,
+        block_checksums: bool,
+        content_checksum: bool,
+        block_size: usize,
+        dictionary: Option<&'a [u8]>,
+        dictionary_id: Option<u32>,
+    }
+    impl<'a> Default for CompressionSettings<'a> {
+        fn default() -> Self {
+            Self { independent_blocks: true, block_checksums: false, content_checksum: true, block_size: 4 * 1024 * 1024, dictionary: None, dictionary_id: None }
+        }
+    }
+    impl<'a> CompressionSettings<'a> {
+        pub fn independent_blocks(&mut self, v: bool) -> &mut Self { self.independent_blocks = v; self }
+        pub fn block_checksums(&mut self, v: bool) -> &mut Self { self.block_checksums = v; self }
+        pub fn content_checksum(&mut self, v: bool) -> &mut Self { self.content_checksum = v; self }
+        pub fn block_size(&mut self, v: usize) -> &mut Self { self.block_size = v; self }
+        pub fn dictionary(&mut self, id: u32, dict: &'a [u8]) -> &mut Self { self.dictionary_id = Some(id); self.dictionary = Some(dict); self }
+        pub fn dictionary_id_nonsense_override(&mut self, id: Option<u32>) -> &mut Self { self.dictionary_id = id; self }
+
+        fn settings(&self, content_size: Option<u64>) -> sys::lzf_settings {
+            let mut s: sys::lzf_settings = unsafe { std::mem::zeroed() };
+            unsafe { sys::lzf_settings_default(&mut s) };
+            s.independent_blocks = self.independent_blocks as i32;
+            s.block_checksums = self.block_checksums as i32;
+            s.content_checksum = self.content_checksum as i32;
+            s.block_size = self.block_size as u64;
+            if let Some(d) = self.dictionary { s.dictionary = d.as_ptr(); s.dictionary_len = d.len() as u64; }
+            if let Some(id) = self.dictionary_id { s.has_dictionary_id = 1; s.dictionary_id = id; }
+            if let Some(n) = content_size { s.has_content_size = 1; s.content_size = n; }
+            s
+        }
+
+        /// `compress` (:137-140).  The whole input goes through ONE batched launch, so the reader is read to its end first.
+        pub fn compress<R: Read, W: Write>(&self, mut reader: R, writer: W) -> Result<(), CompressionError> {
+            let mut input = Vec::new();
+            reader.read_to_end(&mut input).map_err(CompressionError::ReadError)?;
+            self.compress_buffer(&input, writer, None)
+        }
+        /// `compress_with_size_unchecked` (:142-145)
+        pub fn compress_with_size_unchecked<R: Read, W: Write>(&self, mut reader: R, writer: W, content_size: u64) -> Result<(), CompressionError> {
+            let mut input = Vec::new();
+            reader.read_to_end(&mut input).map_err(CompressionError::ReadError)?;
+            self.compress_buffer(&input, writer, Some(content_size))
+        }
+        /// `compress_with_size` (:147-157): the length comes from seeking, as in the reference
+        pub fn compress_with_size<R: Read + io::Seek, W: Write>(&self, mut reader: R, writer: W) -> Result<(), CompressionError> {
+            let start = reader.seek(io::SeekFrom::Current(0)).map_err(CompressionError::ReadError)?;
+            let end = reader.seek(io::SeekFrom::End(0)).map_err(CompressionError::ReadError)?;
+            reader.seek(io::SeekFrom::Start(start)).map_err(CompressionError::ReadError)?;
+            self.compress_with_size_unchecked(reader, writer, end - start)
+        }
+
+        fn compress_buffer<W: Write>(&self, input: &[u8], mut writer: W, content_size: Option<u64>) -> Result<(), CompressionError> {
+            let s = self.settings(content_size);
+            let cap = unsafe { sys::lzf_frame_bound(&s, input.len()) };
+            let mut out = vec![0u8; cap];
+            let (mut written, mut status) = (0usize, 0i32);
+            let rc = with_ctx(|c| {
+                let rc = unsafe { sys::lzf_frame_compress(c, &s, input.as_ptr(), input.len(), out.as_mut_ptr(), cap, &mut written, &mut status) };
+                if rc != sys::LZF_SUCCESS { Err(call_error(c, rc)) } else { Ok(()) }
+            })?;
+            rc?;
+            match status {
+                sys::LZF_F_OK => { writer.write_all(&out[..written])?; Ok(()) }
+                sys::LZF_F_INVALID_BLOCK_SIZE => Err(CompressionError::InvalidBlockSize),
+                sys::LZF_F_PANIC => panic!("called `Option::unwrap()` on a `None` value"),   // src/framed/header.rs:55
+                _ => Err(CompressionError::WriteError(io::ErrorKind::WriteZero.into())),
+            }
+        }
+    }
+
+    /// `decompress_frame` (src/framed/decompress.rs:283-288): reads one frame from `reader`, returns its plaintext.
+    pub fn decompress_frame<R: Read>(mut reader: R) -> Result<Vec<u8>, DecompressionError> {
+        let mut input = Vec::new();
+        reader.read_to_end(&mut input)?;
+        decompress_frame_with_dictionary(&input, &[]).map(|(plain, _consumed)| plain)
+    }
+
+    /// One frame from a buffer -> (plaintext, bytes of `input` the frame occupied).  The capacity grows until the frame
+    /// fits (the frame header's content size is a hint the reference never verifies, decompress.rs:165-166).
+    pub fn decompress_frame_with_dictionary(input: &[u8], dictionary: &[u8]) -> Result<(Vec<u8>, usize), DecompressionError> {
+        let mut cap = input.len().saturating_mul(4).max(1 << 16);
+        loop {
+            let mut out = vec![0u8; cap];
+            let (mut written, mut consumed, mut status, mut detail) = (0usize, 0usize, 0i32, 0i32);
+            let rc = with_ctx(|c| {
+                let rc = unsafe { sys::lzf_frame_decompress(c, input.as_ptr(), input.len(), dictionary.as_ptr(), dictionary.len(),
+                                                            out.as_mut_ptr(), cap, &mut written, &mut consumed, &mut status, &mut detail) };
+                if rc != sys::LZF_SUCCESS { Err(call_error(c, rc)) } else { Ok(()) }
+            })?;
+            rc?;
+            return match status {
+                sys::LZF_F_OK => { out.truncate(written); Ok((out, consumed)) }
+                sys::LZF_F_WRITE_ERROR => { cap = cap.saturating_mul(4); continue; }
+                sys::LZF_F_INPUT_ERROR => Err(DecompressionError::InputError(io::ErrorKind::UnexpectedEof.into())),
+                sys::LZF_F_CODEC_ERROR => Err(DecompressionError::CodecError(match detail {
+                    1 => raw::DecodeError::UnexpectedEnd, 2 => raw::DecodeError::MemoryLimitExceeded,
+                    3 => raw::DecodeError::ZeroDeduplicationOffset, _ => raw::DecodeError::InvalidDeduplicationOffset })),
+                sys::LZF_F_HEADER_PARSE_ERROR => Err(DecompressionError::HeaderParseError(detail)),
+                sys::LZF_F_WRONG_MAGIC => Err(DecompressionError::WrongMagic(u32::from_le_bytes([input[0], input[1], input[2], input[3]]))),
+                sys::LZF_F_HEADER_CHECKSUM_FAIL => Err(DecompressionError::HeaderChecksumFail),
+                sys::LZF_F_BLOCK_CHECKSUM_FAIL => Err(DecompressionError::BlockChecksumFail),
+                sys::LZF_F_FRAME_CHECKSUM_FAIL => Err(DecompressionError::FrameChecksumFail),
+                sys::LZF_F_BLOCK_LENGTH_OVERFLOW => Err(DecompressionError::BlockLengthOverflow),
+                _ => Err(DecompressionError::BlockSizeOverflow),
+            };
+        }
+    }
+}

@@ -272,3 +272,51 @@ def check_raw_compress2_with_history(backend, oracle, table_kind=N.TABLE_U32):
     ctx.table_offset(tab, (1 << 32) - 1000)
     assert ctx.raw_compress2(stream[:70000], 0, tab)[0] == N.PANIC
     ctx.table_free(tab)
+
+
+def check_segmented_parse(backend, oracle, sizes=(70001, 131072, 300000, 600000), scale=1):
+    """LZF_OPT_SEGMENT_BYTES: blocks of an under-filled launch are cut into segments parsed side by side and stitched
+    into one LZ4 block.  Contract (BASELINE.json north_star): valid LZ4 that decodes to the input bit-exactly with the
+    reference decoder, compressed size within 1 % of the reference's; refused (stored) blocks stay refused."""
+    ctx = backend.ctx
+    rnd = lambda n, s: W.random_bytes(n, seed=s).numpy().tobytes()
+    t = lambda n, s: W.text(n, seed=s).numpy().tobytes()
+    lo = lambda n, s: W.lowent(n, seed=s).numpy().tobytes()
+    inputs = []
+    for n in sizes:
+        n *= scale
+        inputs += [t(n, n), lo(n, n + 1), bytes(n), rnd(n // 3, n) + t(n - n // 3, n + 2), t(n // 2, n + 3) + rnd(n - n // 2, n + 4)]
+    inputs += [rnd(200000 * scale, 9), t(65536 * 2 * scale, 5)[:-1], (t(1000, 6) * 400)[: 262144 * scale + 13]]
+    ctx.set_option(N.OPT_SEGMENT_BYTES, 65536)
+    try:
+        worst = 0.0
+        for data in inputs:
+            for cap in (None, len(data)):
+                st, out = ctx.raw_compress_into(data, cap=cap)
+                ost, oout = oracle.compress_block(data, cap=cap)
+                if ost != 0:
+                    # incompressible: the reference refuses; the stitched stream may only be refused too or (rarely) just fit
+                    assert st in (0, N.WRITER_FULL)
+                if st == 0:
+                    dst, plain, dlen = oracle.decompress_raw(out, out_limit=len(data), cap=len(data) + 64)
+                    assert (dst, plain) == (0, data), "segmented stream does not decode to the input (len %d)" % len(data)
+                    if ost == 0:
+                        # a segment boundary costs up to ~16 bytes (the closing 12-byte / 5-literal rule applies at every
+                        # segment end); beyond that fixed cost the size must be within 1 % of the reference's
+                        slack = 16 * (len(data) // 65536 + 1)
+                        worst = max(worst, (len(out) - slack) / max(len(oout), 1) - 1.0)
+                        assert len(out) <= len(oout) * 1.01 + slack, "size %d vs reference %d (len %d)" % (len(out), len(oout), len(data))
+                else:
+                    assert st == N.WRITER_FULL and ost == N.WRITER_FULL
+        # whole frames through the host API: block checksums over the stitched bytes, content checksum, stored blocks
+        data = inputs[0] + inputs[3] + inputs[-3]
+        for kw in (dict(block_size=256 << 10, block_checksums=True), dict(block_size=1 << 20)):
+            st, frame = ctx.frame_compress(data, **kw)
+            assert st == 0
+            assert oracle.frame_decompress(frame, cap=len(data) + 16)[:3] == (0, 0, data)
+            assert len(frame) <= len(oracle.frame_compress(data, **kw)[1]) * 1.01 + 16 * (len(data) // 65536 + 1)
+    finally:
+        ctx.set_option(N.OPT_SEGMENT_BYTES, 0)
+    # option off again: byte-identical to the reference
+    assert ctx.raw_compress_into(inputs[0]) == oracle.compress_block(inputs[0])
+    return worst

@@ -81,3 +81,62 @@ def test_product_sources_never_touch_the_oracle_or_the_emulator():
                 txt = open(os.path.join(base, f), errors="replace").read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "lzf_oracle" not in txt, f
                 assert "simt_emu.h\"" not in txt and "libsimt" not in txt, f
+
+
+def _rust_externs(path):
+    """{name: [rust param types], ...} of the `extern "C"` block of a Rust source file."""
+    import re
+    txt = open(path).read()
+    block = txt[txt.index('extern "C" {'):]
+    out = {}
+    for m in re.finditer(r"pub fn (\w+)\((.*?)\)\s*(?:->\s*([^;]+))?;", block, flags=re.S):
+        params = [p.split(":", 1)[1].strip() for p in m.group(2).split(",") if ":" in p]
+        out[m.group(1)] = (params, (m.group(3) or "").strip())
+    return out
+
+
+def test_rust_sys_crate_matches_the_header():
+    """rust/lz-fear-b200-sys/src/lib.rs declares every symbol of include/lzfear_b200.h with the header's parameter
+    list (count, pointer depth, constness, integer width), and is exactly what rust/gen_sys.py generates."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_sys", os.path.join(ROOT, "rust", "gen_sys.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    lib_rs = os.path.join(ROOT, "rust", "lz-fear-b200-sys", "src", "lib.rs")
+    assert open(lib_rs).read() == gen.generate(), "lib.rs is stale: run python rust/gen_sys.py"
+    rust = _rust_externs(lib_rs)
+    protos = gen.c_prototypes()
+    assert sorted(rust) == sorted(p[0] for p in protos) == sorted(declared_symbols())
+    width = {"u8": "uint8_t", "u32": "uint32_t", "u64": "uint64_t", "i32": "int32_t", "usize": "size_t", "c_int": "int",
+             "c_void": "void", "c_char": "char"}
+    for name, ret, params in protos:
+        rparams, rret = rust[name]
+        assert len(rparams) == len(params), name
+        for (ctype, _pn), rt in zip(params, rparams):
+            assert rt.count("*") == ctype.count("*"), (name, ctype, rt)
+            base = rt.replace("*const ", "").replace("*mut ", "")
+            cbase = ctype.replace("const", "").replace("*", "").strip()
+            assert width.get(base, base) == cbase, (name, ctype, rt)
+            if ctype.count("*") == 1:
+                assert rt.startswith("*const ") == ctype.startswith("const "), (name, ctype, rt)
+        assert (rret == "") == (ret == "void"), name
+    # the safe crate only calls functions that exist
+    import re
+    safe = open(os.path.join(ROOT, "rust", "lz-fear-b200", "src", "lib.rs")).read()
+    for fn in set(re.findall(r"sys::(lzf_\w+)\(", safe)):
+        assert fn in rust, fn
+    for const in set(re.findall(r"sys::(LZF_\w+)", safe)):
+        assert ("pub const %s:" % const) in open(lib_rs).read(), const
+
+
+def test_rust_struct_layouts_match_the_header():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_sys", os.path.join(ROOT, "rust", "gen_sys.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    from lz_fear_b200 import _native
+    # field names and order of the ctypes structures (what the tests exercise) = the header's = the generated Rust
+    cs = gen.c_structs()
+    assert [f[1] for f in cs["lzf_settings"]] == [f[0] for f in _native.Settings._fields_]
+    assert [f[1] for f in cs["lzf_frame_info"]] == [f[0] for f in _native.FrameInfo._fields_]
+    assert [f[1] for f in cs["lzf_xxh32_state"]] == [f[0] for f in _native.Xxh32State._fields_]

@@ -313,3 +313,8 @@ def test_short_nonfinal_blocks_with_exact_capacity(gpu, oracle):    # ADVICE r1,
 def test_raw_compress2_with_history_and_carried_table(gpu, oracle):  # src/raw/compress/mod.rs:165-170
     parity.check_raw_compress2_with_history(gpu, oracle)
     parity.check_raw_compress2_with_history(gpu, oracle, table_kind=N.TABLE_U16)
+
+
+def test_segmented_parse_is_valid_lz4_of_reference_size(gpu, oracle):
+    worst = parity.check_segmented_parse(gpu, oracle, sizes=(70001, 300000, 4 << 20, (4 << 20) - 77), scale=1)
+    assert worst < 0.01

@@ -368,3 +368,8 @@ def test_short_nonfinal_blocks_with_exact_capacity(emu, oracle):    # ADVICE r1,
 def test_raw_compress2_with_history_and_carried_table(emu, oracle):  # src/raw/compress/mod.rs:165-170
     parity.check_raw_compress2_with_history(emu, oracle)
     parity.check_raw_compress2_with_history(emu, oracle, table_kind=N.TABLE_U16)
+
+
+def test_segmented_parse_is_valid_lz4_of_reference_size(emu, oracle):
+    worst = parity.check_segmented_parse(emu, oracle)
+    assert worst < 0.01
