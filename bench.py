@@ -684,6 +684,10 @@ def main():
     # config 4 (mixed-entropy frames, this rank's shard) and config 5 (large hash tables) — opt-in
     # =========================================================================================
     extra = None
+    if not args.no_compress:
+        del data, cbuf, off3, len3, clen, cst, cxx
+    ctx.trim()                              # the e2e pipelines left tens of GiB of staging scratch in the context
+    torch.cuda.empty_cache()
     if not args.no_extra:
         extra = {}
         torch.cuda.empty_cache()

@@ -133,6 +133,9 @@ const char* lzf_last_error(const lzf_ctx* ctx);
  *                           fill the GPU are unaffected.  Applies to independent blocks without a dictionary. */
 enum { LZF_OPT_SEGMENT_BYTES = 1 };
 int lzf_set_option(lzf_ctx* ctx, int option, uint64_t value);
+/* Releases the ctx's grow-only scratch (device staging buffers, descriptor arenas, table / segment scratch) — e.g.
+ * after one very large call.  No call may be in flight on the ctx. */
+int lzf_trim(lzf_ctx* ctx);
 /* Number of kernels this ctx has launched so far (bench.py's gpu_launches). */
 uint64_t lzf_launch_count(const lzf_ctx* ctx);
 

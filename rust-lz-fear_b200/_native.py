@@ -70,6 +70,7 @@ _PROTOTYPES = {
     "lzf_last_error": (C.c_char_p, [_P]),
     "lzf_launch_count": (C.c_uint64, [_P]),
     "lzf_set_option": (C.c_int, [_P, C.c_int, C.c_uint64]),
+    "lzf_trim": (C.c_int, [_P]),
     "lzf_compress_blocks": (C.c_int, [_P, _P, _P, _P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "lzf_decompress_blocks": (C.c_int, [_P, _P, _P, _P, C.c_uint32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "lzf_xxh32_ranges": (C.c_int, [_P, _P, _P, _P, C.c_uint32, _P, _P]),
@@ -221,6 +222,10 @@ class Context:
         self._check(self._lib.lzf_raw_compress_into(self._h, _np_ptr(a), a.size, table, hashlog, out.ctypes.data,
                                                     int(cap), C.byref(w), C.byref(st)))
         return st.value, out[: w.value].tobytes()
+
+    def trim(self):
+        """Gives the context's grow-only device / pinned scratch back to the driver."""
+        self._check(self._lib.lzf_trim(self._h))
 
     def set_option(self, option, value):
         self._check(self._lib.lzf_set_option(self._h, int(option), int(value)))

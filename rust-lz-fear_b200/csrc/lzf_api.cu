@@ -225,6 +225,26 @@ extern "C" void lzf_destroy(lzf_ctx* c) {
     delete c;
 }
 
+// Gives the grow-only scratch of every pipeline slot back to the driver (device staging, descriptor arenas, segment
+// streams, table scratch); the next call allocates what it needs again.  No call may be in flight on the ctx.
+extern "C" int lzf_trim(lzf_ctx* c) {
+    if (!c) return LZF_ERR_INVALID_ARG;
+    LZF_CU(c, cudaSetDevice(c->device));
+    for (int i = 0; i < kSlots; i++) {
+        lzf_slot& sl = c->slots[i];
+        std::lock_guard<std::mutex> lock(sl.launch_mu);
+        if (sl.stream) cudaStreamSynchronize(sl.stream);
+        if (sl.side) cudaStreamSynchronize(sl.side);
+        if (sl.copy) cudaStreamSynchronize(sl.copy);
+        Buf* dev[] = {&sl.d_tables, &sl.d_desc, &sl.d_res, &sl.d_comp, &sl.d_io_in, &sl.d_io_out, &sl.d_dict, &sl.d_aux, &sl.d_seg};
+        for (Buf* b : dev) if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
+        Buf* host[] = {&sl.h_desc, &sl.h_res};
+        for (Buf* b : host) if (b->p) { cudaFreeHost(b->p); b->p = nullptr; b->cap = 0; }
+        sl.has_last = false;
+    }
+    return LZF_SUCCESS;
+}
+
 extern "C" int lzf_set_option(lzf_ctx* c, int option, uint64_t value) {
     if (!c) return LZF_ERR_INVALID_ARG;
     switch (option) {
@@ -937,8 +957,10 @@ int frames_compress_core(lzf_ctx* c, const lzf_settings* s, const uint8_t* d_in,
     if (s->content_checksum) {
         LZF_CU(c, cudaStreamWaitEvent(cur_slot(c)->side, cur_slot(c)->ev_fork, 0));
         if (fed) LZF_CU(c, cudaStreamWaitEvent(cur_slot(c)->side, feed->ready, 0));       // the whole plaintext
+        uint64_t plain_total = 0;
+        for (uint32_t f = 0; f < nframes; f++) plain_total += in_len[f];
         LZF_LAUNCHED(c, lzf_launch_xxh32_ranges(d_in, (const uint64_t*)(d + o_hoff), (const uint64_t*)(d + o_hlen), nframes,
-                                               (uint32_t*)(r + r_chash), cur_slot(c)->side), 1);
+                                               (uint32_t*)(r + r_chash), cur_slot(c)->side, plain_total / nframes >= (1u << 20)), 1);
         LZF_CU(c, cudaEventRecord(cur_slot(c)->ev_join, cur_slot(c)->side));
     }
     if (s->content_checksum) {
@@ -1312,8 +1334,10 @@ int frames_decompress_core(lzf_ctx* c, const uint8_t* d_in, const uint64_t* in_o
     }
     if (any_hash) {       // content checksum over the frame's plaintext (decompress.rs:207-211,276-278)
         LZF_CU(c, cudaMemcpyAsync(d + o_hoff, h + o_hoff, frame_desc_bytes - o_hoff, cudaMemcpyHostToDevice, st));
+        uint64_t plain_total = 0;
+        for (uint32_t f = 0; f < nframes; f++) plain_total += hlen[f];
         LZF_LAUNCHED(c, lzf_launch_xxh32_ranges(d_out, (const uint64_t*)(d + o_hoff), (const uint64_t*)(d + o_hlen), nframes,
-                                               (uint32_t*)(r + r_chash), st), 1);
+                                               (uint32_t*)(r + r_chash), st, plain_total / nframes >= (1u << 20)), 1);
         LZF_CU(c, cudaMemcpyAsync(hr + r_chash, r + r_chash, (size_t)nframes * 4, cudaMemcpyDeviceToHost, st));
         LZF_CU(c, cudaStreamSynchronize(st));
         const uint32_t* ch = (const uint32_t*)(hr + r_chash);
@@ -1366,12 +1390,27 @@ namespace {
 
 // Consecutive frames are grouped into chunks of roughly `target` payload bytes; chunk i runs in
 // pipeline slot i % kSlots.
-std::vector<uint32_t> plan_chunks(const uint64_t* len, uint32_t n, uint64_t target) {
+std::vector<uint32_t> plan_chunks(const uint64_t* len, uint32_t n, uint64_t target, bool ramp = false) {
     std::vector<uint32_t> start;
     uint64_t acc = 0;
+    // ramp (the decompress pipeline): the first chunks are short — 1/8, 1/4, 1/2 of the target — so that the first
+    // plaintext starts travelling back after a fraction of a chunk's H2D copy instead of a whole one, and so are the
+    // last ones, so that little is left to drain once the H2D engine has nothing more to send
+    uint64_t total = 0, done = 0;
+    for (uint32_t f = 0; f < n; f++) total += len[f];
+    uint64_t cur = ramp ? target / 8 : target;
     for (uint32_t f = 0; f < n; f++) {
-        if (f == 0 || acc >= target) { start.push_back(f); acc = 0; }
+        if (f == 0 || acc >= cur) {
+            start.push_back(f);
+            if (f != 0 && ramp) {
+                cur = cur * 2 < target ? cur * 2 : target;
+                const uint64_t left = total - done;
+                while (cur > target / 8 && left < 2 * cur) cur /= 2;       // the tail shrinks again
+            }
+            acc = 0;
+        }
         acc += len[f];
+        done += len[f];
     }
     start.push_back(n);
     return start;
@@ -1615,7 +1654,7 @@ int frames_decompress_host(lzf_ctx* c, const uint8_t* in, const uint64_t* in_off
         const uint64_t worst = (in_len[f] / 5 + 1) * (4ull << 20);
         weight[f] = in_len[f] + (out_cap[f] < worst ? out_cap[f] : worst);
     }
-    const std::vector<uint32_t> chunks = plan_chunks(weight.data(), nframes, c->chunk_bytes);
+    const std::vector<uint32_t> chunks = plan_chunks(weight.data(), nframes, c->chunk_bytes, true);
     return run_chunks(c, (uint32_t)chunks.size() - 1, [&](uint32_t i, lzf_slot& sl) {
         return decompress_chunk(c, sl, chunks[i], chunks[i + 1], in, in_off, in_len, out, out_off, out_cap, out_len, status,
                                 detail, consumed, dict, dlen);

@@ -35,6 +35,9 @@ namespace lzf {
 #ifndef LZF_DEC_WARPS
 #define LZF_DEC_WARPS 8
 #endif
+#ifndef LZF_DEC_EARLY_GATHER
+#define LZF_DEC_EARLY_GATHER 1
+#endif
 constexpr int kDecodeWarpsPerCta = LZF_DEC_WARPS;
 constexpr uint32_t kWin = LZF_DEC_WIN;     // staged bytes of compressed stream per refill
 constexpr uint32_t kStage = 2048;          // output staging ring (power of two, > 32 * 32 + 16)
@@ -450,6 +453,24 @@ decode_blocks_kernel(DecodeArgs a) {
                 const bool act = lane < cnt;
                 const uint32_t out_end = __shfl_sync(LZF_FULL_MASK, o_k + tot, cnt - 1);
 
+#if LZF_DEC_EARLY_GATHER
+                // ---- matches whose source lies completely in the flushed history (global memory) and is short: their
+                // bytes are asked for NOW, as aligned words, so that the round trip runs under the literal copies below
+                // instead of in the dependency rounds.  g_mis: 4 = not taken; else the source's misalignment (0..3)
+                const int64_t srcp_e = (int64_t)dstp - (int64_t)off;
+                uint32_t gw0 = 0, gw1 = 0, gw2 = 0, gw3 = 0, gw4 = 0, g_mis = 4;
+                if (act && ml <= 16u && srcp_e >= 0 && srcp_e + (int64_t)ml <= (int64_t)flushed) {
+                    const uintptr_t ga = reinterpret_cast<uintptr_t>(s.out + srcp_e);
+                    const uint32_t* gp = reinterpret_cast<const uint32_t*>(ga & ~uintptr_t(3));
+                    g_mis = (uint32_t)(ga & 3u);
+                    const uint32_t span = g_mis + ml;                         // bytes from the first aligned word on
+                    gw0 = gp[0];
+                    if (span > 4) gw1 = gp[1];
+                    if (span > 8) gw2 = gp[2];
+                    if (span > 12) gw3 = gp[3];
+                    if (span > 16) gw4 = gp[4];
+                }
+#endif
                 // ---- literals: every lane copies its own run into the staging ring
                 {
                     // trip counts follow the longest run / match of the step (warp-uniform), four bytes per check
@@ -506,6 +527,20 @@ decode_blocks_kernel(DecodeArgs a) {
                         if (srcp >= (int64_t)flushed) {
                             const uint8_t* sp = sm.stage + ((uint32_t)srcp - sbias);   // staged -> staged (in order: overlap-safe)
                             for (uint32_t i = 0; i < ml; i++) d[i] = sp[i];
+#if LZF_DEC_EARLY_GATHER
+                        } else if (g_mis < 4) {
+                            // the words fetched before the literal copies: up to 16 source bytes realigned in registers
+                            const uint32_t sh = g_mis * 8u;
+                            const uint32_t u0 = __funnelshift_r(gw0, gw1, sh), u1 = __funnelshift_r(gw1, gw2, sh), u2 = __funnelshift_r(gw2, gw3, sh),
+                                           u3 = __funnelshift_r(gw3, gw4, sh);
+#pragma unroll
+                            for (uint32_t c = 0; c < 16; c += 4) {
+                                if (c >= maxml) break;
+                                const uint32_t u = c == 0 ? u0 : c == 4 ? u1 : c == 8 ? u2 : u3;
+#pragma unroll
+                                for (uint32_t i = 0; i < 4; i++) if (c + i < ml) d[c + i] = (uint8_t)(u >> (8u * i));
+                            }
+#endif
                         } else if (srcp >= 0 && srcp + (int64_t)ml <= (int64_t)flushed) {
                             const uint8_t* g = s.out + srcp;                      // flushed history -> staged
                             // loads first, then stores: one round trip for matches up to 12 bytes, two beyond

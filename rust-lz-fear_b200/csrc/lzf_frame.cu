@@ -20,19 +20,26 @@ namespace lzf {
 // 2 KiB shared-memory window filled by TMA bulk copies (cp.async.bulk + mbarrier) while the previous window is
 // being hashed.  Loading straight from global memory instead (8 stripes in flight per lane) measured 5.2 ms per
 // MiB on B200 — every group of 8 stripes paid a full memory round trip.
-constexpr uint32_t kHashWin = 2048;
+// Measured on B200, one 64 MiB range (ms): 2 KiB windows x 2 in flight 43.7 (58 before the rolling register window),
+// x 4 in flight 43.8, with an L2 prefetch 16 windows ahead 45.0, 4 KiB x 2 38.8, 8 KiB x 2 36.3 — the chain, not memory,
+// is the limit (IMAD, SHF, IMAD ~ 15 cycles per stripe), so long ranges take larger windows (fewer window switches) and
+// batches of short ranges keep 2 KiB ones (more CTAs per SM: 4096 x 256 KiB in 0.36 ms instead of 0.83).
+constexpr uint32_t kHashDepth = 2;                    // windows of one range in flight
+template <uint32_t kHashWin>
 struct __align__(16) RangeHashSmem {
-    uint8_t buf[8][2][kHashWin];
-    uint64_t bar[8][2];
+    uint8_t buf[8][kHashDepth][kHashWin];
+    uint64_t bar[8][kHashDepth];
 };
 
+template <uint32_t kHashWin>
 #ifdef LZF_SIMT_EMU
 __global__ void
 #else
 __global__ void __maxnreg__(32)
 #endif
 xxh32_ranges_kernel(const uint8_t* data, const uint64_t* off, const uint64_t* len, uint32_t nranges, uint32_t* hash) {
-    __shared__ RangeHashSmem sm;
+    LZF_DYN_SMEM(smem_raw);
+    RangeHashSmem<kHashWin>& sm = *reinterpret_cast<RangeHashSmem<kHashWin>*>(smem_raw);
     const uint32_t warp = blockIdx.x;
     const unsigned lane = lane_id();
     const unsigned j = lane >> 2, a = lane & 3u;
@@ -54,36 +61,43 @@ xxh32_ranges_kernel(const uint8_t* data, const uint64_t* off, const uint64_t* le
         const uint64_t o = __shfl_xor_sync(LZF_FULL_MASK, nwin_max, sft);
         nwin_max = o > nwin_max ? o : nwin_max;
     }
-    if (a == 0) { mbar_init(&sm.bar[j][0], 1); mbar_init(&sm.bar[j][1], 1); }
+    if (a == 0) for (uint32_t d = 0; d < kHashDepth; d++) mbar_init(&sm.bar[j][d], 1);
     __syncwarp();
     auto issue = [&](uint64_t w) {                                                // leader lane of the range
         const uint64_t o = w * kHashWin;
         const uint64_t left = nstripes * 16 - o;
-        bulk_load(sm.buf[j][w & 1], p + o, (uint32_t)(left < kHashWin ? left : kHashWin), &sm.bar[j][w & 1]);
+        bulk_load(sm.buf[j][w % kHashDepth], p + o, (uint32_t)(left < kHashWin ? left : kHashWin), &sm.bar[j][w % kHashDepth]);
     };
-    if (a == 0) { if (nwin > 0) issue(0); if (nwin > 1) issue(1); }
+    if (a == 0) for (uint64_t w = 0; w < kHashDepth && w < nwin; w++) issue(w);
     __syncwarp();
     uint32_t acc = xxh32_seed_acc(a);
     for (uint64_t w = 0; w < nwin_max; w++) {
         if (w < nwin) {
 #ifndef LZF_SIMT_EMU   // (the CPU test harness copies synchronously, and its wait is a warp collective)
-            mbar_wait(&sm.bar[j][w & 1], (uint32_t)((w >> 1) & 1));
+            mbar_wait(&sm.bar[j][w % kHashDepth], (uint32_t)((w / kHashDepth) & 1));
 #endif
             const uint64_t left = nstripes - w * (kHashWin / 16);
             const uint32_t ns = (uint32_t)(left < kHashWin / 16 ? left : kHashWin / 16);
-            const uint32_t* q = reinterpret_cast<const uint32_t*>(sm.buf[j][w & 1]) + a;
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(sm.buf[j][w % kHashDepth]) + a;
+            // the four chains are serial (IMAD, SHF, IMAD per stripe): the words of the next 8 stripes are loaded
+            // while the current 8 are hashed, so the chain never waits for shared memory either
             uint32_t s = 0;
-            for (; s + 8 <= ns; s += 8) {
-                uint32_t x[8];
+            if (ns >= 8) {
+                uint32_t x[8];                                                    // a rolling window: each word is reloaded right after its round
 #pragma unroll
-                for (int i = 0; i < 8; i++) x[i] = q[(s + i) * 4];
+                for (int i = 0; i < 8; i++) x[i] = q[i * 4];
+                for (; s + 16 <= ns; s += 8) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) { acc = xxh_round(acc, x[i]); x[i] = q[(s + 8 + i) * 4]; }
+                }
 #pragma unroll
                 for (int i = 0; i < 8; i++) acc = xxh_round(acc, x[i]);
+                s += 8;
             }
             for (; s < ns; s++) acc = xxh_round(acc, q[s * 4]);
         }
         __syncwarp();                                                             // the window is free again
-        if (a == 0 && w + 2 < nwin) issue(w + 2);
+        if (a == 0 && w + kHashDepth < nwin) issue(w + kHashDepth);
     }
     const uint32_t h = warp_xxh32_x8_finish(acc, p, n);
     if (valid && a == 0) hash[r] = h;
@@ -412,11 +426,26 @@ extern "C" int lzf_launch_stitch(const lzf::StitchArgs* a, cudaStream_t s) {
     return (int)cudaGetLastError();
 }
 
-extern "C" int lzf_launch_xxh32_ranges(const uint8_t* data, const uint64_t* off, const uint64_t* len,
-                                       uint32_t nranges, uint32_t* hash, cudaStream_t s) {
-    if (!nranges) return 0;
-    LZF_LAUNCH(lzf::xxh32_ranges_kernel, (nranges + 7) / 8, 32, 0, s, data, off, len, nranges, hash);
+namespace lzf {
+template <uint32_t kHashWin>
+static int launch_xxh32_ranges(const uint8_t* data, const uint64_t* off, const uint64_t* len, uint32_t nranges, uint32_t* hash, cudaStream_t s) {
+    const size_t dyn = sizeof(RangeHashSmem<kHashWin>);
+    if (dyn > 48 * 1024) {
+        const cudaError_t e = cudaFuncSetAttribute(xxh32_ranges_kernel<kHashWin>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return (int)e;
+    }
+    LZF_LAUNCH(xxh32_ranges_kernel<kHashWin>, (nranges + 7) / 8, 32, dyn, s, data, off, len, nranges, hash);
     return (int)cudaGetLastError();
+}
+}  // namespace lzf
+
+// long_ranges: the caller knows that the ranges are few and long (whole frames of megabytes): 4 KiB windows — 64 KiB
+// of shared memory per CTA still fits beside the 28-warp encode CTA, 8 KiB windows (36.3 ms per 64 MiB) would not
+extern "C" int lzf_launch_xxh32_ranges(const uint8_t* data, const uint64_t* off, const uint64_t* len,
+                                       uint32_t nranges, uint32_t* hash, cudaStream_t s, int long_ranges) {
+    if (!nranges) return 0;
+    return long_ranges ? lzf::launch_xxh32_ranges<4096>(data, off, len, nranges, hash, s)
+                       : lzf::launch_xxh32_ranges<2048>(data, off, len, nranges, hash, s);
 }
 extern "C" int lzf_launch_xxh32_stripes(const uint8_t* data, uint64_t nstripes, uint32_t* acc, cudaStream_t s) {
     LZF_LAUNCH(lzf::xxh32_stripes_kernel, 1, 32, 0, s, data, nstripes, acc);

@@ -116,7 +116,7 @@ int lzf_launch_encode(const lzf::EncodeArgs* args, int num_sms, cudaStream_t str
 size_t lzf_encode_global_table_bytes(const lzf::EncodeArgs* args, int num_sms);
 int lzf_launch_decode(const lzf::DecodeArgs* args, int num_sms, cudaStream_t stream);
 int lzf_launch_xxh32_ranges(const uint8_t* data, const uint64_t* off, const uint64_t* len, uint32_t nranges,
-                            uint32_t* hash, cudaStream_t s);
+                            uint32_t* hash, cudaStream_t s, int long_ranges = 0);
 int lzf_launch_xxh32_stripes(const uint8_t* data, uint64_t nstripes, uint32_t* acc, cudaStream_t s);
 int lzf_launch_stage_dict(const lzf::StageArgs* a, uint32_t max_block_len, cudaStream_t s);
 int lzf_launch_layout(const lzf::LayoutArgs* a, cudaStream_t s);

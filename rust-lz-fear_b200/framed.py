@@ -151,20 +151,91 @@ class CompressionSettings:
                                dictionary=self._dictionary, dictionary_id=self._dictionary_id,
                                content_size=content_size)
 
+    # bytes of plaintext handed to the GPU per launch of the streaming path (whole blocks; >= one block)
+    STREAM_CHUNK_BYTES = 1 << 30
+
     def _compress_internal(self, reader, writer, content_size):
+        """compress_internal (compress.rs:159-282).  Independent blocks without a dictionary are STREAMED: the reader is
+        consumed in chunks of whole blocks, every chunk is one batched launch, and the next chunk is read and compressed
+        on a second thread while this one's bytes are written.  The block records of a chunk compressed on its own are
+        the records the whole frame would hold (independent blocks share nothing, compress.rs:265-270); the content
+        checksum runs over the plaintext as it streams by (compress.rs:172,233-235).  Dependent blocks and dictionaries
+        carry a table from block to block: they go through the one-shot call."""
         ctx = self._ctx or _raw.default_context()
+        s, keep = self._settings(content_size)
+        streamable = self._independent_blocks and not self._dictionary and self._block_size in (64 << 10, 256 << 10, 1 << 20, 4 << 20)
         try:
-            data = reader.read()
+            first = reader.read(self.STREAM_CHUNK_BYTES if streamable else -1)
         except OSError as e:
             raise ReadError(str(e)) from e
-        s, keep = self._settings(content_size)
-        status, frame = ctx.frame_compress(data, settings=s)
-        del keep
+        if not streamable or len(first) < self.STREAM_CHUNK_BYTES:
+            status, frame = ctx.frame_compress(first, settings=s)       # everything fits one call
+            del keep
+            _raise_frame_status(status)
+            try:
+                writer.write(frame)
+            except OSError as e:
+                raise WriteError(str(e)) from e
+            return
+        self._compress_streaming(ctx, reader, writer, first, content_size)
+
+    def _compress_streaming(self, ctx, reader, writer, first, content_size):
+        import threading
+        import queue
+        # the header as compress_internal writes it (:163-200): taken from an empty frame with the same settings
+        s_full, keep_full = self._settings(content_size)
+        status, empty = ctx.frame_compress(b"", settings=s_full)
         _raise_frame_status(status)
+        hlen = len(empty) - 4 - (4 if self._content_checksum else 0)
+        header = empty[:hlen]
+        # chunks are compressed as frames of their own without a content checksum: header | records | EndMark
+        s_chunk, keep_chunk = N.make_settings(independent_blocks=True, block_checksums=self._block_checksums, content_checksum=False,
+                                              block_size=self._block_size)
+        chunk_hlen = 7
+        hasher = ctx.xxh32_new() if self._content_checksum else None
+        q = queue.Queue(maxsize=2)
+        worker_ctx = N.Context(ctx.device) if hasattr(ctx, "device") else ctx
+
+        def produce():
+            try:
+                chunk = first
+                while chunk:
+                    st, fr = worker_ctx.frame_compress(chunk, settings=s_chunk)
+                    if hasher is not None and st == N.F_OK:
+                        worker_ctx.xxh32_update(hasher, chunk)
+                    q.put((st, fr))
+                    if st != N.F_OK:
+                        return
+                    chunk = reader.read(self.STREAM_CHUNK_BYTES)
+                q.put(None)
+            except OSError as e:
+                q.put(ReadError(str(e)))
+            except Exception as e:          # noqa: BLE001 — handed to the consumer
+                q.put(e)
+
+        t = threading.Thread(target=produce, daemon=True)
+        t.start()
         try:
-            writer.write(frame)
+            writer.write(header)
+            while True:
+                item = q.get()
+                if item is None:
+                    break
+                if isinstance(item, Exception):
+                    raise item
+                st, fr = item
+                _raise_frame_status(st)
+                writer.write(memoryview(fr)[chunk_hlen:len(fr) - 4])   # the block records between the chunk's header and EndMark
+            writer.write((0).to_bytes(4, "little"))                     # EndMark :277
+            if hasher is not None:
+                writer.write(ctx.xxh32_finish(hasher).to_bytes(4, "little"))   # :279-281
         except OSError as e:
             raise WriteError(str(e)) from e
+        finally:
+            t.join()
+            if worker_ctx is not ctx:
+                worker_ctx.close()
+            del keep_full, keep_chunk
 
     def compress_to_bytes(self, data):
         out = io.BytesIO()
@@ -280,20 +351,190 @@ class LZ4FrameReader:
             c.xxh32_update(self.content_hasher, output)
 
 
-class LZ4FrameIoReader:
-    """LZ4FrameIoReader (src/framed/decompress.rs:46-77): Read + BufRead over a frame."""
+class _ReadAhead:
+    """The streaming half of LZ4FrameIoReader: a second thread reads the compressed stream AHEAD of the caller, cuts it
+    at block boundaries (the length-word chase of decompress.rs:205-226), and decodes each batch of whole blocks with ONE
+    batched launch while the caller is still consuming the previous batch.  A batch travels as a frame of its own —
+    the original FLG/BD without the content-checksum flag, the block records as they are, an EndMark — so block
+    checksums, stored blocks, dependent blocks (their window = the `dictionary` of the batch frame, decompress.rs:
+    238-269) and every error keep the semantics of the frame decoder.  The content checksum runs over the plaintext
+    as it streams by (decompress.rs:276-278,207-211)."""
 
-    def __init__(self, frame_reader, dictionary):
+    def __init__(self, fr, dictionary, batch_bytes):
+        import queue
+        import threading
+        self.fr = fr
+        self.q = queue.Queue(maxsize=2)
+        self.batch_bytes = batch_bytes
+        base = fr._context()
+        self.ctx = N.Context(base.device) if hasattr(base, "device") else base
+        self.own_ctx = self.ctx is not base
+        flg = 0x40 | (fr.flags & 0x30)                       # version 1, independence and block-checksum bits only
+        bd = {64 << 10: 0x40, 256 << 10: 0x50, 1 << 20: 0x60, 4 << 20: 0x70}[fr.block_maxsize]
+        st = self.ctx.xxh32_new()
+        self.ctx.xxh32_update(st, bytes([flg, bd]))          # < 16 bytes: no launch, the stripes stay on the host side
+        self.header = (MAGIC).to_bytes(4, "little") + bytes([flg, bd, (self.ctx.xxh32_finish(st) >> 8) & 0xFF])
+        self.window = bytes(dictionary)                      # history in front of the next batch
+        self.dependent = not (fr.flags & 0x20)
+        self.thread = threading.Thread(target=self._produce, daemon=True)
+        self.thread.start()
+
+    def _read_batch(self, carried):
+        """Whole block records up to batch_bytes -> (records, number of blocks, tail); tail = "more" | ("end", content
+        checksum or None) | "overflow" (a length word beyond block_maxsize, decompress.rs:220-222) | ("error", exception)."""
+        r, fr = self.fr.reader, self.fr
+        parts, total, nblocks = ([carried] if carried else []), len(carried), 0
+        try:
+            while total < self.batch_bytes:
+                word = _read_exact(r, 4)
+                n = int.from_bytes(word, "little")
+                if n == 0:
+                    cks = int.from_bytes(_read_exact(r, 4), "little") if fr.flags & 0x04 else None
+                    return b"".join(parts), nblocks, ("end", cks)
+                n &= ~INCOMPRESSIBLE
+                if n > fr.block_maxsize:
+                    parts.append(word)                       # the frame decoder reports BlockSizeOverflow at this record
+                    return b"".join(parts), nblocks + 1, "overflow"
+                body = _read_exact(r, n + (4 if fr.flags & 0x10 else 0))
+                parts += [word, body]
+                total += 4 + len(body)
+                nblocks += 1
+        except InputError as e:
+            return b"".join(parts), nblocks, ("error", e)    # the whole blocks in front of the cut are still delivered
+        return b"".join(parts), nblocks, "more"
+
+    def _count_blocks(self, records):
+        n, p, extra = 0, 0, 4 if self.fr.flags & 0x10 else 0
+        while p + 4 <= len(records):
+            p += 4 + (int.from_bytes(records[p:p + 4], "little") & ~INCOMPRESSIBLE) + extra
+            n += 1
+        return n
+
+    def _produce(self):
+        fr = self.fr
+        carried = b""
+        try:
+            while True:
+                records, nblocks, tail = self._read_batch(carried)
+                if carried:
+                    nblocks += self._count_blocks(carried)
+                carried = b""
+                if records:
+                    frame = self.header + records + (b"" if tail == "overflow" else (0).to_bytes(4, "little"))
+                    status, detail, plain, consumed = self.ctx.frame_decompress(frame, dictionary=self.window,
+                                                                                cap=max(1, nblocks) * fr.block_maxsize)
+                    if plain:
+                        if fr.content_hasher is not None:
+                            self.ctx.xxh32_update(fr.content_hasher, plain)
+                        if self.dependent:
+                            self.window = (self.window + plain)[-WINDOW_SIZE:]
+                        self.q.put(("data", plain))
+                    if status != N.F_OK:
+                        self.q.put(("status", (status, detail)))
+                        return
+                    if consumed < len(frame) - 4:
+                        # a block that decoded to nothing: the reader hands an empty buffer to its caller (read_to_end
+                        # stops there, decompress.rs:54-61) and goes on with the next block if it is asked again
+                        self.q.put(("empty", None))
+                        carried = frame[consumed:len(frame) - 4]
+                        if tail == "more":
+                            continue
+                        # the stream's tail is already known: decode the rest before acting on it
+                        while carried:
+                            fr2 = self.header + carried + (0).to_bytes(4, "little")
+                            status, detail, plain, consumed = self.ctx.frame_decompress(
+                                fr2, dictionary=self.window, cap=max(1, self._count_blocks(carried)) * fr.block_maxsize)
+                            if plain:
+                                if fr.content_hasher is not None:
+                                    self.ctx.xxh32_update(fr.content_hasher, plain)
+                                if self.dependent:
+                                    self.window = (self.window + plain)[-WINDOW_SIZE:]
+                                self.q.put(("data", plain))
+                            if status != N.F_OK:
+                                self.q.put(("status", (status, detail)))
+                                return
+                            if consumed < len(fr2) - 4:
+                                self.q.put(("empty", None))
+                                carried = fr2[consumed:len(fr2) - 4]
+                            else:
+                                carried = b""
+                if tail == "more":
+                    continue
+                if tail == "overflow":
+                    self.q.put(("error", BlockSizeOverflow()))
+                    return
+                if tail[0] == "error":
+                    self.q.put(("error", tail[1]))
+                    return
+                cks = tail[1]                                # EndMark: verify the content checksum (:206-215)
+                if fr.content_hasher is not None and cks is not None:
+                    hasher, fr.content_hasher = fr.content_hasher, None
+                    if self.ctx.xxh32_finish(hasher) != cks:
+                        self.q.put(("error", FrameChecksumFail()))
+                        return
+                self.q.put(("end", None))
+                return
+        except Exception as e:           # noqa: BLE001 — handed to the consumer
+            self.q.put(("error", e))
+
+    def next(self):
+        """-> (plaintext of the next batch, frame finished?).  (b"", False) = a block that decoded to nothing; raises what
+        the frame decoder would."""
+        kind, val = self.q.get()
+        if kind == "data":
+            return val, False
+        if kind == "empty":
+            return b"", False
+        self.close()
+        if kind == "end":
+            self.fr.finished = True
+            return b"", True
+        if kind == "status":
+            _raise_frame_status(*val)
+        raise val
+
+    def close(self):
+        self.thread.join(timeout=60)
+        if self.own_ctx:
+            self.ctx.close()
+            self.own_ctx = False
+
+
+class LZ4FrameIoReader:
+    """LZ4FrameIoReader (src/framed/decompress.rs:46-77): Read + BufRead over a frame.  With `read_ahead` (default) the
+    compressed stream is read and decoded in batches of whole blocks ahead of the caller (see _ReadAhead); read_ahead=0
+    keeps the reference's one decode_block() per fill_buf()."""
+
+    READ_AHEAD_BYTES = 256 << 20
+
+    def __init__(self, frame_reader, dictionary, read_ahead=None):
         self.frame_reader = frame_reader
         self.bytes_taken = 0
         self.buffer = bytearray()
         self.dictionary = dictionary
+        self.read_ahead = self.READ_AHEAD_BYTES if read_ahead is None else int(read_ahead)
+        self._ahead = None
+        self._done = False
 
     def fill_buf(self):
         if self.bytes_taken == len(self.buffer):
             del self.buffer[:]
-            self.frame_reader.decode_block(self.buffer, self.dictionary)
             self.bytes_taken = 0
+            if self.read_ahead > 0 and self.frame_reader.block_maxsize in (64 << 10, 256 << 10, 1 << 20, 4 << 20):
+                if self._done or self.frame_reader.finished:
+                    return b""
+                if self._ahead is None:
+                    self._ahead = _ReadAhead(self.frame_reader, self.dictionary, self.read_ahead)
+                try:
+                    chunk, finished = self._ahead.next()
+                except Exception:
+                    self._done = True
+                    raise
+                if finished:
+                    self._done = True
+                self.buffer += chunk
+            else:
+                self.frame_reader.decode_block(self.buffer, self.dictionary)
         return bytes(self.buffer[self.bytes_taken:])
 
     def consume(self, amt):

@@ -94,6 +94,7 @@ extern "C" {
     pub fn lzf_destroy(ctx: *mut lzf_ctx);
     pub fn lzf_last_error(ctx: *const lzf_ctx) -> *const c_char;
     pub fn lzf_set_option(ctx: *mut lzf_ctx, option: c_int, value: u64) -> c_int;
+    pub fn lzf_trim(ctx: *mut lzf_ctx) -> c_int;
     pub fn lzf_launch_count(ctx: *const lzf_ctx) -> u64;
     pub fn lzf_compress_blocks(ctx: *mut lzf_ctx, d_in: *const u8, d_in_off: *const u64, d_in_len: *const u32, nblocks: u32, hashlog: u32, table_kind: u32, max_block_len: u32, d_out: *mut u8, d_out_off: *const u64, d_out_cap: *const u32, d_out_len: *mut u32, d_status: *mut i32, d_xxh_plain: *mut u32, d_xxh_stored: *mut u32, stream: *mut c_void) -> c_int;
     pub fn lzf_decompress_blocks(ctx: *mut lzf_ctx, d_in: *const u8, d_in_off: *const u64, d_in_len: *const u32, nblocks: u32, d_prefix: *const u8, d_prefix_off: *const u64, d_prefix_len: *const u32, d_out: *mut u8, d_out_off: *const u64, d_out_cap: *const u32, d_out_limit: *const u32, d_out_len: *mut u32, d_status: *mut i32, d_xxh_plain: *mut u32, stream: *mut c_void) -> c_int;

@@ -320,3 +320,78 @@ def check_segmented_parse(backend, oracle, sizes=(70001, 131072, 300000, 600000)
     # option off again: byte-identical to the reference
     assert ctx.raw_compress_into(inputs[0]) == oracle.compress_block(inputs[0])
     return worst
+
+
+def check_streaming_host_mirror(backend, oracle, scale=1):
+    """LZ4FrameIoReader with read-ahead (batches of whole blocks decoded ahead of the caller) and the chunked
+    CompressionSettings::compress: same bytes, same errors at the same point of the stream as the block-at-a-time
+    reader of src/framed/decompress.rs:46-77 / the one-shot writer."""
+    import io
+    import struct
+    import lz_fear_b200 as L
+    L.raw.set_default_context(backend.ctx)
+    try:
+        data = (W.text(200000 * scale, 5).numpy().tobytes() + W.random_bytes(70000, 6).numpy().tobytes() +
+                W.lowent(130000 * scale, 7).numpy().tobytes())
+        dic = W.text(5000, 8).numpy().tobytes()
+        cases = [dict(block_size=64 << 10), dict(block_size=64 << 10, block_checksums=True, content_checksum=False),
+                 dict(block_size=256 << 10, independent_blocks=False), dict(block_size=64 << 10, independent_blocks=False, block_checksums=True)]
+        for kw in cases:
+            rc, frame = oracle.frame_compress(data, **kw)
+            for ahead in (100000, 1 << 30, 0):           # several batches / one batch / the reference's block-at-a-time path
+                rd = L.LZ4FrameIoReader(L.LZ4FrameReader(io.BytesIO(frame)), b"", read_ahead=ahead)
+                got = bytearray()
+                while True:                              # examples/delz4.rs:13-20
+                    buf = rd.fill_buf()
+                    if not buf:
+                        break
+                    got += buf
+                    rd.consume(len(buf))
+                assert bytes(got) == data, (kw, ahead)
+            assert L.LZ4FrameReader(io.BytesIO(frame)).into_read().read(1000) == data[:1000]
+        # dictionary
+        rc, frame = oracle.frame_compress(data, dictionary=dic, dictionary_id=3, block_size=64 << 10)
+        rd = L.LZ4FrameIoReader(L.LZ4FrameReader(io.BytesIO(frame)), dic, read_ahead=150000)
+        assert rd.read_to_end() == data
+        # errors surface after the plaintext in front of them, as with the block-at-a-time reader
+        rc, frame = oracle.frame_compress(data, block_size=64 << 10, block_checksums=True)
+        bad = bytearray(frame); bad[len(frame) // 2] ^= 0x55
+        for blob in (bytes(bad), frame[:len(frame) // 2], frame[:-3], frame[:-4] + bytes([1, 2, 3, 4])):
+            outs = []
+            for ahead in (0, 90000, 1 << 30):
+                rd = L.LZ4FrameIoReader(L.LZ4FrameReader(io.BytesIO(blob)), b"", read_ahead=ahead)
+                got, err = bytearray(), None
+                try:
+                    while True:
+                        buf = rd.fill_buf()
+                        if not buf:
+                            break
+                        got += buf
+                        rd.consume(len(buf))
+                except L.DecompressionError as e:
+                    err = type(e).__name__
+                outs.append((bytes(got), err))
+            assert outs[0] == outs[1] == outs[2], [(len(g), e) for g, e in outs]
+            assert outs[0][1] is not None
+        # a block that decodes to nothing: read_to_end stops there, a persistent caller gets the rest
+        hdr = bytes([0x04, 0x22, 0x4D, 0x18, 0x60, 0x40, 0x82])
+        a = bytes([0x30]) + b"abc"
+        fr = hdr + struct.pack("<I", 4) + a + struct.pack("<I", 1) + bytes([0]) + struct.pack("<I", 4) + a + struct.pack("<I", 0)
+        for ahead in (0, 1 << 20):
+            rd = L.LZ4FrameIoReader(L.LZ4FrameReader(io.BytesIO(fr)), b"", read_ahead=ahead)
+            assert rd.read_to_end() == b"abc"
+            assert rd.fill_buf() == b"abc"               # the block behind the empty one
+        # chunked writer: several chunks, bytes identical to the one-shot frame
+        for kw, chunk in ((dict(block_size=64 << 10), 128 << 10), (dict(block_size=64 << 10, block_checksums=True, content_checksum=False), 64 << 10),
+                          (dict(block_size=256 << 10), 256 << 10)):
+            cs = L.CompressionSettings.default().block_size(kw["block_size"]).block_checksums(kw.get("block_checksums", False))
+            cs.content_checksum(kw.get("content_checksum", True))
+            cs.STREAM_CHUNK_BYTES = chunk
+            out = io.BytesIO()
+            cs.compress(io.BytesIO(data), out)
+            assert out.getvalue() == oracle.frame_compress(data, **kw)[1], kw
+            out = io.BytesIO()
+            cs.compress_with_size(io.BytesIO(data), out)
+            assert out.getvalue() == oracle.frame_compress(data, content_size=len(data), **kw)[1], kw
+    finally:
+        L.raw.set_default_context(None)

@@ -318,3 +318,7 @@ def test_raw_compress2_with_history_and_carried_table(gpu, oracle):  # src/raw/c
 def test_segmented_parse_is_valid_lz4_of_reference_size(gpu, oracle):
     worst = parity.check_segmented_parse(gpu, oracle, sizes=(70001, 300000, 4 << 20, (4 << 20) - 77), scale=1)
     assert worst < 0.01
+
+
+def test_streaming_reader_and_writer(gpu, oracle):               # src/framed/decompress.rs:46-77, examples/delz4.rs
+    parity.check_streaming_host_mirror(gpu, oracle, scale=8)

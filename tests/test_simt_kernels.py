@@ -373,3 +373,7 @@ def test_raw_compress2_with_history_and_carried_table(emu, oracle):  # src/raw/c
 def test_segmented_parse_is_valid_lz4_of_reference_size(emu, oracle):
     worst = parity.check_segmented_parse(emu, oracle)
     assert worst < 0.01
+
+
+def test_streaming_reader_and_writer(emu, oracle):               # src/framed/decompress.rs:46-77, examples/delz4.rs
+    parity.check_streaming_host_mirror(emu, oracle)
