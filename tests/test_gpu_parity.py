@@ -182,9 +182,9 @@ def test_config3_text_compress_vs_oracle(gpu, oracle, monkeypatch, variant):
     assert int(st.abs().sum()) == 0 and torch.equal(plain, data)
 
 
-def test_mixed_entropy_frames_roundtrip_property(gpu):
-    """config-4 style: random / text / lowent blocks; encode -> decode is the identity, stored blocks
-    appear exactly for the random class."""
+def test_mixed_entropy_frames_roundtrip_property(gpu, oracle):
+    """config-4 style: random / text / lowent blocks; every frame byte-identical to the oracle's, encode -> decode is
+    the identity, stored blocks appear exactly for the random class."""
     import torch
     B, nb = 1 << 20, 48
     data = W.mixed_blocks(nb, B, device="cuda")
@@ -204,6 +204,11 @@ def test_mixed_entropy_frames_roundtrip_property(gpu):
     f0 = frames[: int(flen[0])].cpu().numpy()
     first_word = int.from_bytes(f0[7:11].tobytes(), "little")
     assert first_word == (B | 0x80000000)                         # block 0 is random -> stored
+    h, fr = data.cpu().numpy(), frames.cpu().numpy()
+    for f in range(nframes):                                      # every frame against the oracle, byte for byte
+        want = oracle.frame_compress(h[f * per:(f + 1) * per].tobytes(), block_size=B)
+        assert (0, fr[int(out_off[f]): int(out_off[f]) + int(flen[f])].tobytes()) == want, f
+        assert oracle.frame_decompress(want[1], cap=per)[:3] == (0, 0, h[f * per:(f + 1) * per].tobytes())
 
 
 def test_streaming_xxh32_and_host_mirror(gpu, oracle):
@@ -322,3 +327,39 @@ def test_segmented_parse_is_valid_lz4_of_reference_size(gpu, oracle):
 
 def test_streaming_reader_and_writer(gpu, oracle):               # src/framed/decompress.rs:46-77, examples/delz4.rs
     parity.check_streaming_host_mirror(gpu, oracle, scale=8)
+
+
+def test_batched_calls_on_two_streams_do_not_race(gpu, oracle):       # shared work counter / table scratch
+    """Two lzf_compress_blocks and two lzf_decompress_blocks calls queued back to back on DIFFERENT streams of one ctx:
+    the second launch of each pair must wait for the first (they share the ctx's work queue), results as for one stream."""
+    import torch
+    B, nb = 256 << 10, 96
+    datas = [W.TextSource(seed=900 + k, device="cuda").make(nb * B) for k in range(2)]
+    off = torch.arange(nb, device="cuda", dtype=torch.int64) * B
+    ln = torch.full((nb,), B, dtype=torch.int32, device="cuda")
+    comps = [torch.zeros(nb * B, dtype=torch.uint8, device="cuda") for _ in range(2)]
+    olens = [torch.zeros(nb, dtype=torch.int32, device="cuda") for _ in range(2)]
+    sts = [torch.ones(nb, dtype=torch.int32, device="cuda") for _ in range(2)]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for k in range(2):
+            gpu.ctx.compress_blocks(datas[k], off, ln, nb, comps[k], off, None, olens[k], sts[k], None, None,
+                                    stream=streams[k].cuda_stream, max_block_len=B)
+    torch.cuda.synchronize()
+    for k in range(2):
+        assert int(sts[k].abs().sum()) == 0
+        h = datas[k].cpu().numpy()
+        g = comps[k].cpu().numpy()
+        gl = olens[k].cpu().numpy().view(np.uint32)
+        for b in range(0, nb, 7):
+            want = oracle.compress_block(h[b * B:(b + 1) * B].tobytes(), cap=B)
+            assert (0, g[b * B: b * B + int(gl[b])].tobytes()) == want, (k, b)
+    backs = [torch.zeros(nb * B, dtype=torch.uint8, device="cuda") for _ in range(2)]
+    dl = [torch.zeros(nb, dtype=torch.int32, device="cuda") for _ in range(2)]
+    for rep in range(3):
+        for k in range(2):
+            gpu.ctx.decompress_blocks(comps[k], off, olens[k], nb, backs[k], off, ln, ln, dl[k], sts[k], None, stream=streams[k].cuda_stream)
+    torch.cuda.synchronize()
+    for k in range(2):
+        assert int(sts[k].abs().sum()) == 0 and torch.equal(backs[k], datas[k])
