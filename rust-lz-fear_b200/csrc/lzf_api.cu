@@ -83,7 +83,9 @@ struct lzf_ctx {
     // payload per pipeline chunk of the host-buffer frame calls.  A chunk is one kernel launch and one
     // warp owns one block, so the chunks in flight together must hold enough blocks to fill the GPU
     // (148 SMs x tens of warps): up to kSlots chunks run concurrently, one host thread + stream each.
-    uint64_t chunk_bytes = 512ull << 20;            // decompress: compressed + plaintext bytes
+    // decompress: compressed + plaintext bytes.  Measured on B200 (config 2 e2e, GiB/s): 256 MiB 41.6, 512 MiB 40.3,
+    // 1 GiB 39.2 once the host-consumed results no longer queue behind the bulk D2H copies
+    uint64_t chunk_bytes = 256ull << 20;
     // compress: plaintext bytes.  0 = one full wave of the block kernel (one warp per block, 28 warps per SM;
     // the parse is latency-bound, so a chunk with fewer blocks takes just as long), at most 24 GiB
     uint64_t compress_chunk_bytes = 0;
@@ -840,7 +842,6 @@ int frames_compress_core(lzf_ctx* c, const lzf_settings* s, const uint8_t* d_in,
     const size_t r_xs = ra.take((size_t)nblocks * 4), r_dst = ra.take((size_t)nblocks * 8);
     const size_t r_chash = ra.take((size_t)nframes * 4);
     const size_t r_flen = ra.take((size_t)nframes * 8), r_fst = ra.take((size_t)nframes * 4);
-    const size_t r_host_lo = r_flen, r_host_hi = ra.used;   // only frame_len + frame_status travel back
 
     int rc;
     if ((rc = ensure_host(c, cur_slot(c)->h_desc, da.used))) return rc;
@@ -978,7 +979,9 @@ int frames_compress_core(lzf_ctx* c, const lzf_settings* s, const uint8_t* d_in,
     la.out = d_out; la.out_off = (const uint64_t*)(d + o_foff); la.out_cap = (const uint64_t*)(d + o_fcap);
     la.content_hash = (const uint32_t*)(r + r_chash);
     la.blk_dst = (uint64_t*)(r + r_dst);
-    la.frame_len = (uint64_t*)(r + r_flen); la.frame_status = (int32_t*)(r + r_fst);
+    // frame lengths and statuses are only read by the host: written straight into its pinned, device-visible arena
+    uint8_t* hr = (uint8_t*)cur_slot(c)->h_res.p;
+    la.frame_len = (uint64_t*)(hr + r_flen); la.frame_status = (int32_t*)(hr + r_fst);
     LZF_LAUNCHED(c, lzf_launch_layout(&la, st), 1);
     if (nblocks) {
         lzf::AssembleArgs aa;
@@ -991,8 +994,6 @@ int frames_compress_core(lzf_ctx* c, const lzf_settings* s, const uint8_t* d_in,
         aa.blk_dst = (const uint64_t*)(r + r_dst); aa.out = d_out;
         LZF_LAUNCHED(c, lzf_launch_assemble(&aa, max_block_len, st), 1);
     }
-    uint8_t* hr = (uint8_t*)cur_slot(c)->h_res.p;
-    LZF_CU(c, cudaMemcpyAsync(hr + r_host_lo, r + r_host_lo, r_host_hi - r_host_lo, cudaMemcpyDeviceToHost, st));
     LZF_CU(c, cudaStreamSynchronize(st));
     const uint64_t* flen = (const uint64_t*)(hr + r_flen);
     const int32_t* fst = (const int32_t*)(hr + r_fst);
@@ -1055,13 +1056,15 @@ int frames_decompress_core(lzf_ctx* c, const uint8_t* d_in, const uint64_t* in_o
     memset(&wa, 0, sizeof(wa));
     wa.nframes = nframes; wa.mode = 0;
     wa.in = d_in; wa.in_off = (const uint64_t*)(d + o_ioff); wa.in_len = (const uint64_t*)(d + o_ilen);
-    wa.frames = (lzf::WalkFrame*)((uint8_t*)cur_slot(c)->d_res.p + r_walk);
+    // Everything the HOST waits for in this function (walk results, per-block lengths and statuses, checksums) is written
+    // by the kernels straight into the slot's pinned, device-visible result arena (unified addressing: the host pointer
+    // is the device pointer).  A D2H copy of a few KiB would queue on the one D2H copy engine behind the hundreds of MiB
+    // of plaintext other chunks are sending home, and the next launch of this chunk would wait for them.
+    wa.frames = (lzf::WalkFrame*)((uint8_t*)cur_slot(c)->h_res.p + r_walk);
     LZF_LAUNCHED(c, lzf_launch_walk(&wa, st), 1);
     std::vector<lzf::WalkFrame> wf(nframes);
-    LZF_CU(c, cudaMemcpyAsync(cur_slot(c)->h_res.p, (uint8_t*)cur_slot(c)->d_res.p + r_walk, (size_t)nframes * sizeof(lzf::WalkFrame),
-                              cudaMemcpyDeviceToHost, st));
     LZF_CU(c, cudaStreamSynchronize(st));
-    memcpy(wf.data(), cur_slot(c)->h_res.p, (size_t)nframes * sizeof(lzf::WalkFrame));
+    memcpy(wf.data(), (uint8_t*)cur_slot(c)->h_res.p + r_walk, (size_t)nframes * sizeof(lzf::WalkFrame));
 
     uint64_t nblocks64 = 0;
     bool any_dependent = false;
@@ -1084,9 +1087,9 @@ int frames_decompress_core(lzf_ctx* c, const uint8_t* d_in, const uint64_t* in_o
     Arena ba;   // device-only block arrays
     ba.used = frame_desc_bytes;
     const size_t o_bin_off = ba.take((size_t)nblocks * 8), o_bword = ba.take((size_t)nblocks * 4);
-    const size_t o_bcks = ba.take((size_t)nblocks * 4), o_boff = ba.take((size_t)nblocks * 8);
+    const size_t o_boff = ba.take((size_t)nblocks * 8);
     const size_t o_bcap = ba.take((size_t)nblocks * 4), o_blim = ba.take((size_t)nblocks * 4);
-    const size_t o_bplen = ba.take((size_t)nblocks * 8), o_bend = ba.take((size_t)nblocks * 8);
+    const size_t o_bplen = ba.take((size_t)nblocks * 8);
     Arena rb;
     const size_t r_olen = rb.take((size_t)nblocks * 4), r_bst = rb.take((size_t)nblocks * 4);
     const size_t r_bxxh = rb.take((size_t)nblocks * 4), r_bcks = rb.take((size_t)nblocks * 4);
@@ -1099,9 +1102,7 @@ int frames_decompress_core(lzf_ctx* c, const uint8_t* d_in, const uint64_t* in_o
         LZF_CU(c, cudaMemcpyAsync(d, h, o_first, cudaMemcpyHostToDevice, st));
         wa.in_off = (const uint64_t*)(d + o_ioff); wa.in_len = (const uint64_t*)(d + o_ilen);
     }
-    if ((rc = ensure_dev(c, cur_slot(c)->d_res, rb.used))) return rc;
     if ((rc = ensure_host(c, cur_slot(c)->h_res, rb.used))) return rc;
-    uint8_t* r = (uint8_t*)cur_slot(c)->d_res.p;
     uint8_t* hr = (uint8_t*)cur_slot(c)->h_res.p;
     LZF_CU(c, cudaMemcpyAsync(d + o_first, h + o_first, o_hoff - o_first, cudaMemcpyHostToDevice, st));
 
@@ -1114,14 +1115,14 @@ int frames_decompress_core(lzf_ctx* c, const uint8_t* d_in, const uint64_t* in_o
         wa.first_block = (const uint32_t*)(d + o_first);
         wa.out_off = (const uint64_t*)(d + o_ooff); wa.out_cap = (const uint64_t*)(d + o_ocap);
         wa.blk_in_off = (uint64_t*)(d + o_bin_off); wa.blk_len_word = (uint32_t*)(d + o_bword);
-        wa.blk_checksum = (uint32_t*)(d + o_bcks);
+        wa.blk_checksum = (uint32_t*)(hr + r_bcks);
         wa.blk_out_off = (uint64_t*)(d + o_boff); wa.blk_out_cap = (uint32_t*)(d + o_bcap);
         wa.blk_out_limit = (uint32_t*)(d + o_blim); wa.blk_payload_len = (uint64_t*)(d + o_bplen);
-        wa.blk_end = (uint64_t*)(d + o_bend);
+        wa.blk_end = (uint64_t*)(hr + r_bend);
         LZF_LAUNCHED(c, lzf_launch_walk(&wa, st), 1);
         if (any_block_checksums)    // decompress.rs:228-235: hash of the stored payload
             LZF_LAUNCHED(c, lzf_launch_xxh32_ranges(d_in, (const uint64_t*)(d + o_bin_off), (const uint64_t*)(d + o_bplen),
-                                                   nblocks, (uint32_t*)(r + r_bxxh), st), 1);
+                                                   nblocks, (uint32_t*)(hr + r_bxxh), st), 1);
         // history of every block (src/framed/decompress.rs:238-248): the dictionary for independent blocks
         // and for the first block of a dependent frame; for block i > 0 of a dependent frame the 64 KiB of
         // output right in front of its own slot — exact whenever the blocks before it were full, which
@@ -1161,8 +1162,8 @@ int frames_decompress_core(lzf_ctx* c, const uint8_t* d_in, const uint64_t* in_o
         }
         rc = decompress_blocks_impl(c, d_in, (const uint64_t*)(d + o_bin_off), (const uint32_t*)(d + o_bword), nblocks,
                                     nullptr, d_pf_off, d_pf_len, d_out, (const uint64_t*)(d + o_boff),
-                                    (const uint32_t*)(d + o_bcap), (const uint32_t*)(d + o_blim), (uint32_t*)(r + r_olen),
-                                    (int32_t*)(r + r_bst), nullptr, st, use_hist, d_wait, d_done);
+                                    (const uint32_t*)(d + o_bcap), (const uint32_t*)(d + o_blim), (uint32_t*)(hr + r_olen),
+                                    (int32_t*)(hr + r_bst), nullptr, st, use_hist, d_wait, d_done);
         if (rc) return rc;
         if (extra.after_decode) {
             uint64_t expect = 0;
@@ -1172,13 +1173,7 @@ int frames_decompress_core(lzf_ctx* c, const uint8_t* d_in, const uint64_t* in_o
             }
             if ((rc = extra.after_decode(expect))) return rc;
         }
-        LZF_CU(c, cudaMemcpyAsync(hr + r_olen, r + r_olen, r_bxxh - r_olen, cudaMemcpyDeviceToHost, st));
-        if (any_block_checksums) {
-            LZF_CU(c, cudaMemcpyAsync(hr + r_bxxh, r + r_bxxh, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, st));
-            LZF_CU(c, cudaMemcpyAsync(hr + r_bcks, d + o_bcks, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, st));
-        }
-        LZF_CU(c, cudaMemcpyAsync(hr + r_bend, d + o_bend, (size_t)nblocks * 8, cudaMemcpyDeviceToHost, st));
-        LZF_CU(c, cudaStreamSynchronize(st));
+        LZF_CU(c, cudaStreamSynchronize(st));       // lengths, statuses, checksums and block ends are in hr already
     }
     uint32_t* b_olen = (uint32_t*)(hr + r_olen);
     int32_t* b_st = (int32_t*)(hr + r_bst);
@@ -1337,8 +1332,7 @@ int frames_decompress_core(lzf_ctx* c, const uint8_t* d_in, const uint64_t* in_o
         uint64_t plain_total = 0;
         for (uint32_t f = 0; f < nframes; f++) plain_total += hlen[f];
         LZF_LAUNCHED(c, lzf_launch_xxh32_ranges(d_out, (const uint64_t*)(d + o_hoff), (const uint64_t*)(d + o_hlen), nframes,
-                                               (uint32_t*)(r + r_chash), st, plain_total / nframes >= (1u << 20)), 1);
-        LZF_CU(c, cudaMemcpyAsync(hr + r_chash, r + r_chash, (size_t)nframes * 4, cudaMemcpyDeviceToHost, st));
+                                               (uint32_t*)(hr + r_chash), st, plain_total / nframes >= (1u << 20)), 1);
         LZF_CU(c, cudaStreamSynchronize(st));
         const uint32_t* ch = (const uint32_t*)(hr + r_chash);
         for (uint32_t f = 0; f < nframes; f++)

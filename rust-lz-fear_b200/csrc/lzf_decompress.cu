@@ -38,6 +38,9 @@ namespace lzf {
 #ifndef LZF_DEC_EARLY_GATHER
 #define LZF_DEC_EARLY_GATHER 1
 #endif
+#ifndef LZF_DEC_GATHER_MAX
+#define LZF_DEC_GATHER_MAX 12          // 12 (4 words) or 20 (6 words): longest match fetched ahead of the literal copies
+#endif
 constexpr int kDecodeWarpsPerCta = LZF_DEC_WARPS;
 constexpr uint32_t kWin = LZF_DEC_WIN;     // staged bytes of compressed stream per refill
 constexpr uint32_t kStage = 2048;          // output staging ring (power of two, > 32 * 32 + 16)
@@ -460,7 +463,10 @@ decode_blocks_kernel(DecodeArgs a) {
                 const int64_t srcp_e = (int64_t)dstp - (int64_t)off;
                 // (up to 12 bytes: measured on B200, config 2 435 GiB/s against 421 with 16 and 375 without)
                 uint32_t gw0 = 0, gw1 = 0, gw2 = 0, gw3 = 0, g_mis = 4;
-                if (act && ml <= 12u && srcp_e >= 0 && srcp_e + (int64_t)ml <= (int64_t)flushed) {
+#if LZF_DEC_GATHER_MAX > 12
+                uint32_t gw4 = 0, gw5 = 0;
+#endif
+                if (act && ml <= (uint32_t)LZF_DEC_GATHER_MAX && srcp_e >= 0 && srcp_e + (int64_t)ml <= (int64_t)flushed) {
                     const uintptr_t ga = reinterpret_cast<uintptr_t>(s.out + srcp_e);
                     const uint32_t* gp = reinterpret_cast<const uint32_t*>(ga & ~uintptr_t(3));
                     g_mis = (uint32_t)(ga & 3u);
@@ -469,6 +475,10 @@ decode_blocks_kernel(DecodeArgs a) {
                     if (span > 4) gw1 = gp[1];
                     if (span > 8) gw2 = gp[2];
                     if (span > 12) gw3 = gp[3];
+#if LZF_DEC_GATHER_MAX > 12
+                    if (span > 16) gw4 = gp[4];
+                    if (span > 20) gw5 = gp[5];
+#endif
                 }
 #endif
                 // ---- literals: every lane copies its own run into the staging ring
@@ -532,10 +542,15 @@ decode_blocks_kernel(DecodeArgs a) {
                             // the words fetched before the literal copies: up to 12 source bytes realigned in registers
                             const uint32_t sh = g_mis * 8u;
                             const uint32_t u0 = __funnelshift_r(gw0, gw1, sh), u1 = __funnelshift_r(gw1, gw2, sh), u2 = __funnelshift_r(gw2, gw3, sh);
+#if LZF_DEC_GATHER_MAX > 12
+                            const uint32_t u3 = __funnelshift_r(gw3, gw4, sh), u4 = __funnelshift_r(gw4, gw5, sh);
+#else
+                            const uint32_t u3 = 0, u4 = 0;
+#endif
 #pragma unroll
-                            for (uint32_t c = 0; c < 12; c += 4) {
+                            for (uint32_t c = 0; c < (uint32_t)LZF_DEC_GATHER_MAX; c += 4) {
                                 if (c >= maxml) break;
-                                const uint32_t u = c == 0 ? u0 : c == 4 ? u1 : u2;
+                                const uint32_t u = c == 0 ? u0 : c == 4 ? u1 : c == 8 ? u2 : c == 12 ? u3 : u4;
 #pragma unroll
                                 for (uint32_t i = 0; i < 4; i++) if (c + i < ml) d[c + i] = (uint8_t)(u >> (8u * i));
                             }
