@@ -924,6 +924,27 @@ def main():
             assert st_e == 0 and st_s == 0
             t_dec, (dst_, ddet_, dplain_, _dc) = timed(lambda: ctx.frame_decompress(fr_s, cap=sf.size + 16))
             assert dst_ == 0 and np.array_equal(np.frombuffer(dplain_, dtype=np.uint8), sf), "single-file round trip failed"
+            # the streaming host mirror on the same bytes (examples/delz4.rs: LZ4FrameReader::new(f)?.into_read(), fill_buf /
+            # consume): read-ahead batches of whole blocks, one launch each, decoded while the caller consumes the previous one
+            import io
+            import lz_fear_b200 as L
+            L.raw.set_default_context(ctx)
+            try:
+                def stream_read():
+                    rd = L.LZ4FrameReader(io.BytesIO(fr_e)).into_read()
+                    n = 0
+                    while True:
+                        buf = rd.fill_buf()
+                        if not buf:
+                            return n
+                        n += len(buf)
+                        rd.consume(len(buf))
+                t_stream, n_stream = timed(stream_read)
+                assert n_stream == sf.size
+                t_oneshot, (ost_, odet_, opl_, _oc) = timed(lambda: ctx.frame_decompress(fr_e, cap=sf.size + 16))
+                assert ost_ == 0 and len(opl_) == sf.size
+            finally:
+                L.raw.set_default_context(None)
             import oracle
             t0 = time.perf_counter()
             orc, ofr = oracle.frame_compress(sf.tobytes())
@@ -933,6 +954,7 @@ def main():
                       "compress_exact_GiB_per_s": sf.size / GiB / t_exact, "compress_segmented_GiB_per_s": sf.size / GiB / t_seg,
                       "segmented_size_vs_exact": len(fr_s) / float(len(fr_e)) - 1.0,
                       "decompress_GiB_per_s": sf.size / GiB / t_dec,
+                      "stream_reader_GiB_per_s": sf.size / GiB / t_stream, "stream_reader_vs_one_shot": t_stream / t_oneshot,
                       "cpu_baseline": {"compress_GiB_per_s": sf.size / GiB / t_cpu, "cores": 1, "kind": "port",
                                        "sample": "the same file through the C port of compress_internal, one thread (the reference is single-threaded)"},
                       "note": "exact = byte-identical to the reference (16 warps busy); segmented = LZF_OPT_SEGMENT_BYTES=65536"}

@@ -42,9 +42,6 @@ extern "C" { uint64_t lzf_enc_stats[32]; }
 #ifndef LZF_ENC_WALK
 #define LZF_ENC_WALK 1          // 0: the round-1 resolve loop only (A/B builds)
 #endif
-#ifndef LZF_ENC_WALK_CARRY
-#define LZF_ENC_WALK_CARRY 1    // the walk also takes a first sequence whose literals begin in front of the batch
-#endif
 
 
 namespace lzf {
@@ -424,7 +421,8 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int n_smem_warps) {
                 // registers.  The walk goes from run start to winner to match end with scalar (warp-uniform)
                 // arithmetic, one shuffle to fetch the winner's summary, one to gather the literal bytes and one
                 // store per sequence.  It stops in front of anything else (an end-of-block lane, a lane whose slot
-                // an earlier lane shares, length extensions, literals carried in from earlier batches): the serial
+                // an earlier lane shares, length extensions, literals carried in from earlier batches — letting the walk take
+                // those too measured 34.9 against 35.4 GiB/s): the serial
                 // step below resolves that one sequence and the walk resumes behind it.
                 //   pinfo: bits 0..5 lane where the match ends (4..47), 6..7 backtrack summary (0..3), 16..31 candidate distance
                 uint32_t pinfo = 0;
@@ -442,52 +440,10 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int n_smem_warps) {
 #endif
                 for (;;) {
 #if LZF_ENC_WALK
-                    if (consecutive && s < 32 && cap >= opos && cap - opos >= 128 && (LZF_ENC_WALK_CARRY || lit_start == base + s)) {
+                    if (consecutive && lit_start == base + s && s < 32 && cap >= opos && cap - opos >= 128) {
                         int end = 0;            // 0: stopped in front of a lane (serial step), 1: no trigger left, 2: match left the batch
                         bool wrote = false;     // at least one sequence was written: the run now starts where the last match ended
                         uint32_t e = s;
-#if LZF_ENC_WALK_CARRY
-                        // The run came in from the batch before (29 % of the batches of config 3): its first sequence takes
-                        // the literals in front of the batch from memory, everything else as in the loop below.
-                        if (lit_start != base + s) {
-                            const uint32_t pre = base + s - lit_start;
-                            const uint32_t t = trigmask & ~((1u << s) - 1u);
-                            end = 3;                                              // unless the sequence is taken below
-                            if (t == 0) {
-                                end = 1;
-                            } else {
-                                const uint32_t w = (uint32_t)__ffs((int)t) - 1u;
-                                if ((goodmask >> w) & 1u) {
-                                    const uint32_t info = __shfl_sync(LZF_FULL_MASK, pinfo, w);
-                                    const uint32_t lraw = w - s + pre;
-                                    const uint32_t bt = min((info >> 6) & 3u, lraw);
-                                    const uint32_t L = lraw - bt;
-                                    if (L < 15) {
-                                        e = info & 63u;
-                                        const uint32_t tl = lane - 1u;
-                                        const uint32_t litb = __shfl_sync(LZF_FULL_MASK, v32, s + tl - pre);
-                                        uint32_t v = lane == 0 ? ((L << 4) | (e - w - 4u + bt)) : (info >> 16) >> (8u * (tl - L));
-                                        if (lane != 0 && tl < L) v = tl < pre ? (uint32_t)__ldg(in + lit_start + tl) : litb;
-                                        if (lane < L + 3u) out[opos + lane] = (uint8_t)v;
-                                        opos += L + 3u;
-                                        ins |= ((2u << w) - 1u) & ~((1u << s) - 1u);
-                                        wrote = true;
-                                        LZF_STAT(4);
-                                        if (e >= 32) {
-                                            end = 2;
-                                        } else {
-                                            end = 0;
-                                            const uint32_t l2 = e - 2;
-                                            if (!((endmask >> l2) & 1u)) ins |= 1u << l2;
-                                            else late_q2 = base + l2;
-                                            s = e;
-                                        }
-                                    }
-                                }
-                            }
-                        }
-                        if (end == 0)
-#endif
                         for (;;) {
                             const uint32_t t = trigmask & ~((1u << s) - 1u);
                             if (t == 0) { end = 1; break; }

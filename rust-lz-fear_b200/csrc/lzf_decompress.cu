@@ -456,6 +456,7 @@ decode_blocks_kernel(DecodeArgs a) {
                 const bool act = lane < cnt;
                 const uint32_t out_end = __shfl_sync(LZF_FULL_MASK, o_k + tot, cnt - 1);
 
+                const uint32_t maxml = warp_max_u32((act && ml <= kLaneCopyMax) ? ml : 0u);   // longest lane-copied match of the step
 #if LZF_DEC_EARLY_GATHER
                 // ---- matches whose source lies completely in the flushed history (global memory) and is short: their
                 // bytes are asked for NOW, as aligned words, so that the round trip runs under the literal copies below
@@ -466,7 +467,10 @@ decode_blocks_kernel(DecodeArgs a) {
 #if LZF_DEC_GATHER_MAX > 12
                 uint32_t gw4 = 0, gw5 = 0;
 #endif
-                if (act && ml <= (uint32_t)LZF_DEC_GATHER_MAX && srcp_e >= 0 && srcp_e + (int64_t)ml <= (int64_t)flushed) {
+                // Only in steps whose lane-copied matches ALL fit the words fetched here: a step that also has longer ones
+                // would run this path and the byte-wise one below (text: 151 instead of 166 GiB/s when it did).
+                if (maxml <= (uint32_t)LZF_DEC_GATHER_MAX && act && ml <= (uint32_t)LZF_DEC_GATHER_MAX && srcp_e >= 0 &&
+                    srcp_e + (int64_t)ml <= (int64_t)flushed) {
                     const uintptr_t ga = reinterpret_cast<uintptr_t>(s.out + srcp_e);
                     const uint32_t* gp = reinterpret_cast<const uint32_t*>(ga & ~uintptr_t(3));
                     g_mis = (uint32_t)(ga & 3u);
@@ -495,7 +499,6 @@ decode_blocks_kernel(DecodeArgs a) {
                         for (uint32_t i = c; i < c + 4; i++) if (i < mylit) d[i] = src[i];
                     }
                 }
-                const uint32_t maxml = warp_max_u32((act && ml <= kLaneCopyMax) ? ml : 0u);
                 for (uint32_t lm = __ballot_sync(LZF_FULL_MASK, act && lit > kLaneCopyMax); lm; lm &= lm - 1) {
                     const uint32_t k = __ffs(lm) - 1;                           // a long run: the whole warp copies it
                     const uint32_t n = __shfl_sync(LZF_FULL_MASK, lit, k);

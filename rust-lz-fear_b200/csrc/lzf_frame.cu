@@ -31,6 +31,51 @@ struct __align__(16) RangeHashSmem {
     uint64_t bar[8][kHashDepth];
 };
 
+// The stripe phase of one range per lane group (j = group, a = accumulator of the lane) through the group's double-
+// buffered shared-memory windows; every lane of the warp calls it (nwin_max = the longest range of the warp).
+template <uint32_t kHashWin>
+__device__ __forceinline__ uint32_t hash_windows(RangeHashSmem<kHashWin>& sm, unsigned j, unsigned a, const uint8_t* p, uint64_t nstripes,
+                                                 uint64_t nwin, uint64_t nwin_max, uint32_t acc) {
+    if (a == 0) for (uint32_t d = 0; d < kHashDepth; d++) mbar_init(&sm.bar[j][d], 1);
+    __syncwarp();
+    auto issue = [&](uint64_t w) {                                                // leader lane of the range
+        const uint64_t o = w * kHashWin;
+        const uint64_t left = nstripes * 16 - o;
+        bulk_load(sm.buf[j][w % kHashDepth], p + o, (uint32_t)(left < kHashWin ? left : kHashWin), &sm.bar[j][w % kHashDepth]);
+    };
+    if (a == 0) for (uint64_t w = 0; w < kHashDepth && w < nwin; w++) issue(w);
+    __syncwarp();
+    for (uint64_t w = 0; w < nwin_max; w++) {
+        if (w < nwin) {
+#ifndef LZF_SIMT_EMU   // (the CPU test harness copies synchronously, and its wait is a warp collective)
+            mbar_wait(&sm.bar[j][w % kHashDepth], (uint32_t)((w / kHashDepth) & 1));
+#endif
+            const uint64_t left = nstripes - w * (kHashWin / 16);
+            const uint32_t ns = (uint32_t)(left < kHashWin / 16 ? left : kHashWin / 16);
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(sm.buf[j][w % kHashDepth]) + a;
+            // the four chains are serial (IMAD, SHF, IMAD per stripe): the words of the next 8 stripes are loaded
+            // while the current 8 are hashed, so the chain never waits for shared memory either
+            uint32_t s = 0;
+            if (ns >= 8) {
+                uint32_t x[8];                                                    // a rolling window: each word is reloaded right after its round
+#pragma unroll
+                for (int i = 0; i < 8; i++) x[i] = q[i * 4];
+                for (; s + 16 <= ns; s += 8) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) { acc = xxh_round(acc, x[i]); x[i] = q[(s + 8 + i) * 4]; }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; i++) acc = xxh_round(acc, x[i]);
+                s += 8;
+            }
+            for (; s < ns; s++) acc = xxh_round(acc, q[s * 4]);
+        }
+        __syncwarp();                                                             // the window is free again
+        if (a == 0 && w + kHashDepth < nwin) issue(w + kHashDepth);
+    }
+    return acc;
+}
+
 template <uint32_t kHashWin>
 #ifdef LZF_SIMT_EMU
 __global__ void
@@ -61,55 +106,34 @@ xxh32_ranges_kernel(const uint8_t* data, const uint64_t* off, const uint64_t* le
         const uint64_t o = __shfl_xor_sync(LZF_FULL_MASK, nwin_max, sft);
         nwin_max = o > nwin_max ? o : nwin_max;
     }
-    if (a == 0) for (uint32_t d = 0; d < kHashDepth; d++) mbar_init(&sm.bar[j][d], 1);
-    __syncwarp();
-    auto issue = [&](uint64_t w) {                                                // leader lane of the range
-        const uint64_t o = w * kHashWin;
-        const uint64_t left = nstripes * 16 - o;
-        bulk_load(sm.buf[j][w % kHashDepth], p + o, (uint32_t)(left < kHashWin ? left : kHashWin), &sm.bar[j][w % kHashDepth]);
-    };
-    if (a == 0) for (uint64_t w = 0; w < kHashDepth && w < nwin; w++) issue(w);
-    __syncwarp();
-    uint32_t acc = xxh32_seed_acc(a);
-    for (uint64_t w = 0; w < nwin_max; w++) {
-        if (w < nwin) {
-#ifndef LZF_SIMT_EMU   // (the CPU test harness copies synchronously, and its wait is a warp collective)
-            mbar_wait(&sm.bar[j][w % kHashDepth], (uint32_t)((w / kHashDepth) & 1));
-#endif
-            const uint64_t left = nstripes - w * (kHashWin / 16);
-            const uint32_t ns = (uint32_t)(left < kHashWin / 16 ? left : kHashWin / 16);
-            const uint32_t* q = reinterpret_cast<const uint32_t*>(sm.buf[j][w % kHashDepth]) + a;
-            // the four chains are serial (IMAD, SHF, IMAD per stripe): the words of the next 8 stripes are loaded
-            // while the current 8 are hashed, so the chain never waits for shared memory either
-            uint32_t s = 0;
-            if (ns >= 8) {
-                uint32_t x[8];                                                    // a rolling window: each word is reloaded right after its round
-#pragma unroll
-                for (int i = 0; i < 8; i++) x[i] = q[i * 4];
-                for (; s + 16 <= ns; s += 8) {
-#pragma unroll
-                    for (int i = 0; i < 8; i++) { acc = xxh_round(acc, x[i]); x[i] = q[(s + 8 + i) * 4]; }
-                }
-#pragma unroll
-                for (int i = 0; i < 8; i++) acc = xxh_round(acc, x[i]);
-                s += 8;
-            }
-            for (; s < ns; s++) acc = xxh_round(acc, q[s * 4]);
-        }
-        __syncwarp();                                                             // the window is free again
-        if (a == 0 && w + kHashDepth < nwin) issue(w + kHashDepth);
-    }
+    const uint32_t acc = hash_windows<kHashWin>(sm, j, a, p, nstripes, nwin, nwin_max, xxh32_seed_acc(a));
     const uint32_t h = warp_xxh32_x8_finish(acc, p, n);
     if (valid && a == 0) hash[r] = h;
 }
 
-// Stripe phase only, one warp, carrying a running state: acc[0..4) in/out (streaming content
-// checksums of the Read/Write-style host API, src/framed/compress.rs:233-235).
-__global__ void __launch_bounds__(32) xxh32_stripes_kernel(const uint8_t* data, uint64_t nstripes, uint32_t* acc) {
+// Stripe phase only, one warp, carrying a running state: acc[0..4) in/out (streaming content checksums of the
+// Read/Write-style host API, src/framed/compress.rs:233-235).  Long inputs stream through the same TMA windows as
+// xxh32_ranges_kernel (loading the stripes straight from global memory cost 5.2 ms per MiB).
+template <uint32_t kHashWin>
+#ifdef LZF_SIMT_EMU
+__global__ void
+#else
+__global__ void __maxnreg__(32)
+#endif
+xxh32_stream_kernel(const uint8_t* data, uint64_t nstripes, uint32_t* acc_io) {
+    LZF_DYN_SMEM(smem_raw);
+    RangeHashSmem<kHashWin>& sm = *reinterpret_cast<RangeHashSmem<kHashWin>*>(smem_raw);
     const unsigned lane = lane_id();
-    uint32_t a = lane < 4 ? acc[lane] : 0u;
-    a = warp_xxh32_stripes(data, nstripes, a);
-    if (lane < 4) acc[lane] = a;
+    const unsigned j = lane >> 2, a = lane & 3u;
+    uint32_t acc = lane < 4 ? acc_io[lane] : 0u;
+    if ((reinterpret_cast<uintptr_t>(data) & 15u) != 0 || nstripes * 16 < 4 * kHashWin) {
+        acc = warp_xxh32_stripes(data, nstripes, acc);
+    } else {
+        const uint64_t nwin = j == 0 ? (nstripes * 16 + kHashWin - 1) / kHashWin : 0;
+        const uint64_t nwin_max = (nstripes * 16 + kHashWin - 1) / kHashWin;
+        acc = hash_windows<kHashWin>(sm, j, a, data, j == 0 ? nstripes : 0, nwin, nwin_max, acc);
+    }
+    if (lane < 4) acc_io[lane] = acc;
 }
 
 constexpr uint32_t kSliceBytes = 64 * 1024;
@@ -448,7 +472,10 @@ extern "C" int lzf_launch_xxh32_ranges(const uint8_t* data, const uint64_t* off,
                        : lzf::launch_xxh32_ranges<2048>(data, off, len, nranges, hash, s);
 }
 extern "C" int lzf_launch_xxh32_stripes(const uint8_t* data, uint64_t nstripes, uint32_t* acc, cudaStream_t s) {
-    LZF_LAUNCH(lzf::xxh32_stripes_kernel, 1, 32, 0, s, data, nstripes, acc);
+    const size_t dyn = sizeof(lzf::RangeHashSmem<4096>);
+    const cudaError_t e = cudaFuncSetAttribute(lzf::xxh32_stream_kernel<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess) return (int)e;
+    LZF_LAUNCH(lzf::xxh32_stream_kernel<4096>, 1, 32, dyn, s, data, nstripes, acc);
     return (int)cudaGetLastError();
 }
 extern "C" int lzf_launch_stage_dict(const lzf::StageArgs* a, uint32_t max_block_len, cudaStream_t s) {
