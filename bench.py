@@ -270,7 +270,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a desynchronised collective should end the run in minutes, not after the default 10-minute watchdog
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
 
     def barrier():
         if world > 1:
@@ -283,6 +285,23 @@ def main():
         t = torch.tensor([x], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    def all_ranks_ok(ok):
+        """Collective AND: every rank calls it, every rank gets the same answer.  The exchange sections allocate large
+        buffers on rank 0 only; a rank that failed locally must not leave the others waiting inside a collective it never
+        joins (that is a 10-minute NCCL timeout), so every local step that can fail is followed by this agreement."""
+        if world == 1:
+            return bool(ok)
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    mem_log = {}
+
+    def log_mem(tag):
+        free, total = torch.cuda.mem_get_info()
+        mem_log[tag] = {"torch_allocated_gib": round(torch.cuda.memory_allocated() / GiB, 2),
+                        "torch_reserved_gib": round(torch.cuda.memory_reserved() / GiB, 2), "device_free_gib": round(free / GiB, 2)}
 
     def sum_over_ranks(x):
         if world == 1:
@@ -617,10 +636,13 @@ def main():
             comp_section["e2e"]["ceiling_note"] = "as for decompress: the step's pinned H2D + D2H bytes only, all %d ranks at once" % world
             del in_t, out_t
         if world > 1 and not args.no_gather:
+            # config-4 flavour: the one real exchange step — compressed frames of every rank travel to rank 0 over NCCL
+            # (all-gather of per-frame sizes, then ONE grouped batch of send/recv of the variable-length payloads).
+            # Every local step that can fail is agreed on by all ranks before the next collective (all_ranks_ok).
+            from lz_fear_b200 import sharding
+            log_mem("before_gather")
+            g_err, fr, packed, sizes, got = None, None, None, None, None
             try:
-                # config-4 flavour: the one real exchange step — compressed frames of every rank travel to rank 0 over
-                # NCCL (all-gather of per-frame sizes, then grouped send/recv of the variable-length payloads)
-                from lz_fear_b200 import sharding
                 gb = min(nb3, 1024)                                     # up to 4 GiB of plaintext per rank
                 nf = gb // BLOCKS_PER_FRAME3
                 fp = BLOCKS_PER_FRAME3 * BLOCK3
@@ -632,37 +654,50 @@ def main():
                                                     np.full(nf, bound, np.uint64), sset)
                 assert not fs.any()
                 packed = torch.cat([fr[int(o):int(o) + int(l)] for o, l in zip(g_off, fl)])
+                fr = None
                 sizes = torch.from_numpy(fl.astype(np.int64)).to(dev)
-                for _ in range(2):                                       # NCCL sets its point-to-point channels up on first use
-                    per_rank = sharding.all_gather_sizes(sizes)
-                    got = sharding.gather_bytes(packed, per_rank, dst=0)
-                barrier()
-                e0.record()
-                for _ in range(K):
-                    per_rank = sharding.all_gather_sizes(sizes)
-                    got = sharding.gather_bytes(packed, per_rank, dst=0)
-                e1.record()
-                barrier()
-                g_ms = max_over_ranks(e0.elapsed_time(e1)) / K
+            except Exception as e:
+                g_err = "%s: %s" % (type(e).__name__, str(e)[:200])
+            if not all_ranks_ok(g_err is None):
+                comp_section["gather"] = {"skipped": "a rank could not prepare its frames", "this_rank": g_err}
+            else:
+                per_rank = sharding.all_gather_sizes(sizes)
                 total_bytes = sum(int(x.sum().item()) for x in per_rank)
-                # every rank's payload is checked on rank 0: digests computed by the senders vs digests of the slices received
-                digs = [None] * world
-                dist.all_gather_object(digs, sharding.payload_digest(packed))
-                if rank == 0:
-                    assert got.numel() == total_bytes and torch.equal(got[: packed.numel()], packed)
-                    pos = 0
-                    for r in range(world):
-                        n_r = int(per_rank[r].sum().item())
-                        assert sharding.payload_digest(got[pos:pos + n_r]) == tuple(digs[r]), "gathered payload of rank %d differs" % r
-                        pos += n_r
-                comp_section["gather"] = {"ms": g_ms, "compressed_bytes_all_ranks": total_bytes,
-                                          "GiB_per_s_into_rank0": (total_bytes - int(packed.numel())) / GiB / (g_ms / 1e3),
-                                          "plaintext_GiB_per_rank": nf * fp / GiB,
-                                          "verified": "payload of every rank digested on rank 0",
-                                          "note": "NCCL all_gather(sizes) + one grouped batch of send/recv (ncclGroupStart/End) of whole frames to rank 0; not part of `value`"}
-                del fr, packed, got
-            except Exception as e:                                   # the exchange step is reported beside the value, never instead of it
-                comp_section["gather"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+                try:
+                    if rank == 0:
+                        got = torch.empty(total_bytes, dtype=torch.uint8, device=dev)
+                except Exception as e:
+                    g_err = "%s: %s" % (type(e).__name__, str(e)[:200])
+                if not all_ranks_ok(g_err is None):
+                    comp_section["gather"] = {"skipped": "rank 0 has no room for the gathered frames", "rank0": g_err}
+                else:
+                    for _ in range(2):                                   # NCCL sets its point-to-point channels up on first use
+                        sharding.gather_bytes(packed, per_rank, dst=0, out=got)
+                    barrier()
+                    e0.record()
+                    for _ in range(K):
+                        per_rank = sharding.all_gather_sizes(sizes)
+                        sharding.gather_bytes(packed, per_rank, dst=0, out=got)
+                    e1.record()
+                    barrier()
+                    g_ms = max_over_ranks(e0.elapsed_time(e1)) / K
+                    # every rank's payload is checked on rank 0: digests computed by the senders vs digests of the slices received
+                    digs = [None] * world
+                    dist.all_gather_object(digs, sharding.payload_digest(packed))
+                    verified = True
+                    if rank == 0:
+                        pos = 0
+                        for r in range(world):
+                            n_r = int(per_rank[r].sum().item())
+                            verified = verified and sharding.payload_digest(got[pos:pos + n_r]) == tuple(digs[r])
+                            pos += n_r
+                    comp_section["gather"] = {"ms": g_ms, "compressed_bytes_all_ranks": total_bytes,
+                                              "GiB_per_s_into_rank0": (total_bytes - int(packed.numel())) / GiB / (g_ms / 1e3),
+                                              "plaintext_GiB_per_rank": nf * fp / GiB,
+                                              "verified": "payload of every rank digested on rank 0: %s" % ("equal" if verified else "MISMATCH"),
+                                              "note": "NCCL all_gather(sizes) + one grouped batch of send/recv (ncclGroupStart/End) of whole frames to rank 0; not part of `value`"}
+            del fr, packed, got, sizes
+            torch.cuda.empty_cache()
         if rank == 0 and not args.no_cpu:
             cores = os.cpu_count() or 1
             ns = min(nb3, 256)
@@ -687,7 +722,10 @@ def main():
     if not args.no_compress:
         del data, cbuf, off3, len3, clen, cst, cxx
     ctx.trim()                              # the e2e pipelines left tens of GiB of staging scratch in the context
+    import gc
+    gc.collect()
     torch.cuda.empty_cache()
+    log_mem("before_extra_configs")
     if not args.no_extra:
         extra = {}
         torch.cuda.empty_cache()
@@ -739,58 +777,82 @@ def main():
         if world > 1 and not args.no_gather:
             # §8(e), the full exchange: every rank compresses its frames -> all-gather of sizes + grouped send/recv GATHER of
             # whole frames to rank 0 (the archive) -> rank 0 walks the frame boundaries and SCATTERS contiguous ranges of whole
-            # frames back -> every rank decompresses what it received -> bit-exact against its own plaintext
+            # frames back -> every rank decompresses what it received -> bit-exact against its own plaintext.
+            # Collective-safe: all ranks agree (all_ranks_ok) after every local step that can fail, and nothing raises
+            # between two collectives.
+            from lz_fear_b200 import sharding
+            x_err, packed4, sizes4, archive, recv4 = None, None, None, None, None
             try:
-                from lz_fear_b200 import sharding
                 packed4 = torch.cat([fr4[int(o):int(o) + int(l)] for o, l in zip(fo_off, fl4)])
                 sizes4 = torch.from_numpy(fl4.astype(np.int64)).to(dev)
+            except Exception as e:
+                x_err = "%s: %s" % (type(e).__name__, str(e)[:200])
+            del fr4                                               # the frames live on in packed4
+            torch.cuda.empty_cache()
+            log_mem("before_config4_exchange")
+            if not all_ranks_ok(x_err is None):
+                extra["config4"]["exchange"] = {"skipped": "a rank could not pack its frames", "this_rank": x_err}
+            else:
                 per_rank4 = sharding.all_gather_sizes(sizes4)
                 totals4 = [int(x.sum().item()) for x in per_rank4]
-                archive = torch.empty(sum(totals4), dtype=torch.uint8, device=dev) if rank == 0 else None
-                recv4 = torch.empty(totals4[rank], dtype=torch.uint8, device=dev)
-                for _ in range(2):
-                    sharding.gather_bytes(packed4, per_rank4, dst=0, out=archive)
-                    sharding.scatter_bytes(archive, totals4, src=0, out=recv4)
-                barrier()
-                e0.record()
-                for _ in range(K):
-                    per_rank4 = sharding.all_gather_sizes(sizes4)
-                    sharding.gather_bytes(packed4, per_rank4, dst=0, out=archive)
-                e1.record()
-                barrier()
-                g4_ms = max_over_ranks(e0.elapsed_time(e1)) / K
-                e0.record()
-                for _ in range(K):
-                    sharding.scatter_bytes(archive, totals4, src=0, out=recv4)
-                e1.record()
-                barrier()
-                s4_ms = max_over_ranks(e0.elapsed_time(e1)) / K
-                digs4 = [None] * world
-                dist.all_gather_object(digs4, sharding.payload_digest(packed4))
-                if rank == 0:
-                    pos = 0
-                    for r in range(world):
-                        assert sharding.payload_digest(archive[pos:pos + totals4[r]]) == tuple(digs4[r]), "archive slice of rank %d differs" % r
-                        pos += totals4[r]
-                assert torch.equal(recv4, packed4), "scattered frames differ from the frames this rank compressed"
-                # decode what came back over the wire (dense layout: frame f at the running sum of the frame lengths)
-                r_off = np.zeros(nf4, dtype=np.uint64); r_off[1:] = np.cumsum(fl4)[:-1]
-                back4.zero_()
-                ol4b, ds4b, _d = ctx.frames_decompress_device(recv4, r_off, fl4, back4, fi_off, fi_len)
-                assert not ds4b.any() and (ol4b == fp4).all() and torch.equal(back4, mixed), "config 4 round trip over the exchange failed"
-                remote = sum(totals4) - totals4[0]
-                comp_s4, dec_s4 = tc / K, td / K
-                extra["config4"]["exchange"] = {
-                    "gather_ms": g4_ms, "scatter_ms": s4_ms, "frame_bytes_all_ranks": sum(totals4),
-                    "gather_GiB_per_s_into_rank0": remote / GiB / (g4_ms / 1e3), "scatter_GiB_per_s_out_of_rank0": remote / GiB / (s4_ms / 1e3),
-                    "compress_GiB_per_s_with_gather": tot4 / GiB / (comp_s4 + g4_ms / 1e3),
-                    "decompress_GiB_per_s_with_scatter": tot4 / GiB / (dec_s4 + s4_ms / 1e3),
-                    "verified": "every rank's frames digested on rank 0 after the gather; scattered frames equal to the sender's; "
-                                "decoded plaintext of every rank bit-exact to its input",
-                    "how": "NCCL: all_gather(sizes) + one grouped batch of isend/irecv per direction (batch_isend_irecv), whole frames only"}
-                del packed4, archive, recv4
-            except Exception as e:
-                extra["config4"]["exchange"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+                try:
+                    if rank == 0:
+                        archive = torch.empty(sum(totals4), dtype=torch.uint8, device=dev)
+                    recv4 = torch.empty(totals4[rank], dtype=torch.uint8, device=dev)
+                except Exception as e:
+                    x_err = "%s: %s" % (type(e).__name__, str(e)[:300])
+                if not all_ranks_ok(x_err is None):
+                    extra["config4"]["exchange"] = {"skipped": "not enough device memory for the archive on rank 0 (%.1f GiB of frames)"
+                                                               % (sum(totals4) / GiB), "this_rank": x_err, "mem": mem_log.get("before_config4_exchange")}
+                else:
+                    for _ in range(2):
+                        sharding.gather_bytes(packed4, per_rank4, dst=0, out=archive)
+                        sharding.scatter_bytes(archive, totals4, src=0, out=recv4)
+                    barrier()
+                    e0.record()
+                    for _ in range(K):
+                        per_rank4 = sharding.all_gather_sizes(sizes4)
+                        sharding.gather_bytes(packed4, per_rank4, dst=0, out=archive)
+                    e1.record()
+                    barrier()
+                    g4_ms = max_over_ranks(e0.elapsed_time(e1)) / K
+                    e0.record()
+                    for _ in range(K):
+                        sharding.scatter_bytes(archive, totals4, src=0, out=recv4)
+                    e1.record()
+                    barrier()
+                    s4_ms = max_over_ranks(e0.elapsed_time(e1)) / K
+                    digs4 = [None] * world
+                    dist.all_gather_object(digs4, sharding.payload_digest(packed4))
+                    ok_archive = True
+                    if rank == 0:
+                        pos = 0
+                        for r in range(world):
+                            ok_archive = ok_archive and sharding.payload_digest(archive[pos:pos + totals4[r]]) == tuple(digs4[r])
+                            pos += totals4[r]
+                    ok_scatter = bool(torch.equal(recv4, packed4))
+                    # decode what came back over the wire (dense layout: frame f at the running sum of the frame lengths)
+                    ok_decode = False
+                    try:
+                        r_off = np.zeros(nf4, dtype=np.uint64); r_off[1:] = np.cumsum(fl4)[:-1]
+                        back4.zero_()
+                        ol4b, ds4b, _d = ctx.frames_decompress_device(recv4, r_off, fl4, back4, fi_off, fi_len)
+                        ok_decode = bool(not ds4b.any() and (ol4b == fp4).all() and torch.equal(back4, mixed))
+                    except Exception as e:
+                        x_err = "%s: %s" % (type(e).__name__, str(e)[:200])
+                    all_decoded = all_ranks_ok(ok_decode and ok_scatter)
+                    remote = sum(totals4) - totals4[0]
+                    comp_s4, dec_s4 = tc / K, td / K
+                    extra["config4"]["exchange"] = {
+                        "gather_ms": g4_ms, "scatter_ms": s4_ms, "frame_bytes_all_ranks": sum(totals4),
+                        "gather_GiB_per_s_into_rank0": remote / GiB / (g4_ms / 1e3), "scatter_GiB_per_s_out_of_rank0": remote / GiB / (s4_ms / 1e3),
+                        "compress_GiB_per_s_with_gather": tot4 / GiB / (comp_s4 + g4_ms / 1e3),
+                        "decompress_GiB_per_s_with_scatter": tot4 / GiB / (dec_s4 + s4_ms / 1e3),
+                        "verified": {"archive_slices_equal_senders_digests": ok_archive,
+                                     "scattered_frames_equal_on_every_rank_and_decode_bit_exact": all_decoded, "this_rank_error": x_err},
+                        "how": "NCCL: all_gather(sizes) + one grouped batch of isend/irecv per direction (batch_isend_irecv), whole frames only"}
+            del packed4, archive, recv4, sizes4
+            torch.cuda.empty_cache()
         if rank == 0 and not args.no_cpu:
             # CPU bar for config 4: the same block mix through the C port (blocks of the first frames; stored blocks included)
             cores = os.cpu_count() or 1
@@ -812,6 +874,7 @@ def main():
                                                 "kind": "port", "sample": "first %d blocks (%d MiB): block loops only, no frame assembly or checksums; "
                                                 "decompress over the %d blocks that compressed" % (ns4, ns4 * BLOCK3 >> 20, len(ok4))}
             del h4, cout4, d_out
+        fr4 = None
         del mixed, fr4, back4
         torch.cuda.empty_cache()
         # ---- config 5: low-entropy blocks, HASHLOG 12 (reference) / 14 / 16 (extension): sizes vs the oracle at the same HASHLOG
@@ -979,6 +1042,7 @@ def main():
             line["extra_configs"] = extra
         if single is not None:
             line["single_file"] = single
+        line["device_memory_log"] = mem_log
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

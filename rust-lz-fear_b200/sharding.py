@@ -100,11 +100,18 @@ def scatter_bytes(packed, totals, src=0, group=None, device=None, out=None):
     return out[: totals[rank]]
 
 
-def payload_digest(t):
+def payload_digest(t, chunk=32 << 20):
     """A cheap order-sensitive digest of a uint8 tensor computed where it lives (exchange verification: every rank
-    digests what it sent, the receiver digests each slice it got): sum of bytes and sum of byte * (index mod 65521 + 1)."""
+    digests what it sent, the receiver digests each slice it got): (sum of bytes, sum of byte * (index mod 65521 + 1)),
+    both modulo 2^61 - 1.  Works in chunks so that the int64 temporaries stay small next to multi-GiB payloads."""
     if t is None or t.numel() == 0:
         return (0, 0)
-    x = t.to(torch.int64)
-    w = torch.arange(t.numel(), device=t.device, dtype=torch.int64) % 65521 + 1
-    return (int(x.sum().item()), int((x * w).sum().item()))
+    m = (1 << 61) - 1
+    s0 = s1 = 0
+    for lo in range(0, t.numel(), chunk):
+        x = t[lo: lo + chunk].to(torch.int64)
+        w = (torch.arange(lo, lo + x.numel(), device=t.device, dtype=torch.int64) % 65521) + 1
+        s0 = (s0 + int(x.sum().item())) % m
+        s1 = (s1 + int((x * w).sum().item())) % m
+        del x, w
+    return (s0, s1)
