@@ -296,6 +296,20 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         return bool(t.item())
 
+    class EventTimer:
+        """CUDA events on the current stream (the exchange runs there): sharding.frames_exchange's timer on the GPU."""
+
+        def __init__(self):
+            self.a, self.b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def start(self):
+            self.a.record()
+
+        def stop_ms(self):
+            self.b.record()
+            self.b.synchronize()
+            return self.a.elapsed_time(self.b)
+
     mem_log = {}
 
     def log_mem(tag):
@@ -641,7 +655,7 @@ def main():
             # Every local step that can fail is agreed on by all ranks before the next collective (all_ranks_ok).
             from lz_fear_b200 import sharding
             log_mem("before_gather")
-            g_err, fr, packed, sizes, got = None, None, None, None, None
+            g_err, fr, packed, sizes = None, None, None, None
             try:
                 gb = min(nb3, 1024)                                     # up to 4 GiB of plaintext per rank
                 nf = gb // BLOCKS_PER_FRAME3
@@ -661,42 +675,22 @@ def main():
             if not all_ranks_ok(g_err is None):
                 comp_section["gather"] = {"skipped": "a rank could not prepare its frames", "this_rank": g_err}
             else:
-                per_rank = sharding.all_gather_sizes(sizes)
-                total_bytes = sum(int(x.sum().item()) for x in per_rank)
-                try:
-                    if rank == 0:
-                        got = torch.empty(total_bytes, dtype=torch.uint8, device=dev)
-                except Exception as e:
-                    g_err = "%s: %s" % (type(e).__name__, str(e)[:200])
-                if not all_ranks_ok(g_err is None):
-                    comp_section["gather"] = {"skipped": "rank 0 has no room for the gathered frames", "rank0": g_err}
+                res = sharding.frames_exchange(packed, sizes, dev, reps=K, timer=EventTimer(), barrier=barrier)
+                if "skipped" in res:
+                    comp_section["gather"] = res
                 else:
-                    for _ in range(2):                                   # NCCL sets its point-to-point channels up on first use
-                        sharding.gather_bytes(packed, per_rank, dst=0, out=got)
-                    barrier()
-                    e0.record()
-                    for _ in range(K):
-                        per_rank = sharding.all_gather_sizes(sizes)
-                        sharding.gather_bytes(packed, per_rank, dst=0, out=got)
-                    e1.record()
-                    barrier()
-                    g_ms = max_over_ranks(e0.elapsed_time(e1)) / K
-                    # every rank's payload is checked on rank 0: digests computed by the senders vs digests of the slices received
-                    digs = [None] * world
-                    dist.all_gather_object(digs, sharding.payload_digest(packed))
-                    verified = True
-                    if rank == 0:
-                        pos = 0
-                        for r in range(world):
-                            n_r = int(per_rank[r].sum().item())
-                            verified = verified and sharding.payload_digest(got[pos:pos + n_r]) == tuple(digs[r])
-                            pos += n_r
-                    comp_section["gather"] = {"ms": g_ms, "compressed_bytes_all_ranks": total_bytes,
-                                              "GiB_per_s_into_rank0": (total_bytes - int(packed.numel())) / GiB / (g_ms / 1e3),
+                    g_ms, s_ms = max_over_ranks(res["gather_ms"]), max_over_ranks(res["scatter_ms"])
+                    total_bytes = sum(res["totals"])
+                    remote = total_bytes - res["totals"][0]
+                    comp_section["gather"] = {"ms": g_ms, "scatter_ms": s_ms, "compressed_bytes_all_ranks": total_bytes,
+                                              "GiB_per_s_into_rank0": remote / GiB / (g_ms / 1e3),
+                                              "scatter_GiB_per_s_out_of_rank0": remote / GiB / (s_ms / 1e3),
                                               "plaintext_GiB_per_rank": nf * fp / GiB,
-                                              "verified": "payload of every rank digested on rank 0: %s" % ("equal" if verified else "MISMATCH"),
-                                              "note": "NCCL all_gather(sizes) + one grouped batch of send/recv (ncclGroupStart/End) of whole frames to rank 0; not part of `value`"}
-            del fr, packed, got, sizes
+                                              "verified": {"archive_slices_equal_senders_digests": res["archive_slices_equal_senders_digests"],
+                                                           "scattered_frames_equal_on_every_rank": res["scattered_frames_equal_on_every_rank_and_decoded"]},
+                                              "note": "sharding.frames_exchange: NCCL all_gather(sizes) + one grouped batch of send/recv "
+                                                      "(ncclGroupStart/End) of whole frames per direction; not part of `value`"}
+            del fr, packed, sizes
             torch.cuda.empty_cache()
         if rank == 0 and not args.no_cpu:
             cores = os.cpu_count() or 1
@@ -781,7 +775,7 @@ def main():
             # Collective-safe: all ranks agree (all_ranks_ok) after every local step that can fail, and nothing raises
             # between two collectives.
             from lz_fear_b200 import sharding
-            x_err, packed4, sizes4, archive, recv4 = None, None, None, None, None
+            x_err, packed4, sizes4 = None, None, None
             try:
                 packed4 = torch.cat([fr4[int(o):int(o) + int(l)] for o, l in zip(fo_off, fl4)])
                 sizes4 = torch.from_numpy(fl4.astype(np.int64)).to(dev)
@@ -793,54 +787,19 @@ def main():
             if not all_ranks_ok(x_err is None):
                 extra["config4"]["exchange"] = {"skipped": "a rank could not pack its frames", "this_rank": x_err}
             else:
-                per_rank4 = sharding.all_gather_sizes(sizes4)
-                totals4 = [int(x.sum().item()) for x in per_rank4]
-                try:
-                    if rank == 0:
-                        archive = torch.empty(sum(totals4), dtype=torch.uint8, device=dev)
-                    recv4 = torch.empty(totals4[rank], dtype=torch.uint8, device=dev)
-                except Exception as e:
-                    x_err = "%s: %s" % (type(e).__name__, str(e)[:300])
-                if not all_ranks_ok(x_err is None):
-                    extra["config4"]["exchange"] = {"skipped": "not enough device memory for the archive on rank 0 (%.1f GiB of frames)"
-                                                               % (sum(totals4) / GiB), "this_rank": x_err, "mem": mem_log.get("before_config4_exchange")}
-                else:
-                    for _ in range(2):
-                        sharding.gather_bytes(packed4, per_rank4, dst=0, out=archive)
-                        sharding.scatter_bytes(archive, totals4, src=0, out=recv4)
-                    barrier()
-                    e0.record()
-                    for _ in range(K):
-                        per_rank4 = sharding.all_gather_sizes(sizes4)
-                        sharding.gather_bytes(packed4, per_rank4, dst=0, out=archive)
-                    e1.record()
-                    barrier()
-                    g4_ms = max_over_ranks(e0.elapsed_time(e1)) / K
-                    e0.record()
-                    for _ in range(K):
-                        sharding.scatter_bytes(archive, totals4, src=0, out=recv4)
-                    e1.record()
-                    barrier()
-                    s4_ms = max_over_ranks(e0.elapsed_time(e1)) / K
-                    digs4 = [None] * world
-                    dist.all_gather_object(digs4, sharding.payload_digest(packed4))
-                    ok_archive = True
-                    if rank == 0:
-                        pos = 0
-                        for r in range(world):
-                            ok_archive = ok_archive and sharding.payload_digest(archive[pos:pos + totals4[r]]) == tuple(digs4[r])
-                            pos += totals4[r]
-                    ok_scatter = bool(torch.equal(recv4, packed4))
+                def decode_back(received):
                     # decode what came back over the wire (dense layout: frame f at the running sum of the frame lengths)
-                    ok_decode = False
-                    try:
-                        r_off = np.zeros(nf4, dtype=np.uint64); r_off[1:] = np.cumsum(fl4)[:-1]
-                        back4.zero_()
-                        ol4b, ds4b, _d = ctx.frames_decompress_device(recv4, r_off, fl4, back4, fi_off, fi_len)
-                        ok_decode = bool(not ds4b.any() and (ol4b == fp4).all() and torch.equal(back4, mixed))
-                    except Exception as e:
-                        x_err = "%s: %s" % (type(e).__name__, str(e)[:200])
-                    all_decoded = all_ranks_ok(ok_decode and ok_scatter)
+                    r_off = np.zeros(nf4, dtype=np.uint64); r_off[1:] = np.cumsum(fl4)[:-1]
+                    back4.zero_()
+                    ol4b, ds4b, _d = ctx.frames_decompress_device(received, r_off, fl4, back4, fi_off, fi_len)
+                    return bool(not ds4b.any() and (ol4b == fp4).all() and torch.equal(back4, mixed))
+                res = sharding.frames_exchange(packed4, sizes4, dev, reps=K, decode=decode_back, timer=EventTimer(), barrier=barrier)
+                if "skipped" in res:
+                    res["mem"] = mem_log.get("before_config4_exchange")
+                    extra["config4"]["exchange"] = res
+                else:
+                    g4_ms, s4_ms = max_over_ranks(res["gather_ms"]), max_over_ranks(res["scatter_ms"])
+                    totals4 = res["totals"]
                     remote = sum(totals4) - totals4[0]
                     comp_s4, dec_s4 = tc / K, td / K
                     extra["config4"]["exchange"] = {
@@ -848,10 +807,12 @@ def main():
                         "gather_GiB_per_s_into_rank0": remote / GiB / (g4_ms / 1e3), "scatter_GiB_per_s_out_of_rank0": remote / GiB / (s4_ms / 1e3),
                         "compress_GiB_per_s_with_gather": tot4 / GiB / (comp_s4 + g4_ms / 1e3),
                         "decompress_GiB_per_s_with_scatter": tot4 / GiB / (dec_s4 + s4_ms / 1e3),
-                        "verified": {"archive_slices_equal_senders_digests": ok_archive,
-                                     "scattered_frames_equal_on_every_rank_and_decode_bit_exact": all_decoded, "this_rank_error": x_err},
-                        "how": "NCCL: all_gather(sizes) + one grouped batch of isend/irecv per direction (batch_isend_irecv), whole frames only"}
-            del packed4, archive, recv4, sizes4
+                        "verified": {"archive_slices_equal_senders_digests": res["archive_slices_equal_senders_digests"],
+                                     "scattered_frames_equal_on_every_rank_and_decode_bit_exact": res["scattered_frames_equal_on_every_rank_and_decoded"],
+                                     "this_rank_error": res["this_rank_error"]},
+                        "how": "sharding.frames_exchange: NCCL all_gather(sizes) + one grouped batch of isend/irecv per direction "
+                               "(batch_isend_irecv), whole frames only"}
+            del packed4, sizes4
             torch.cuda.empty_cache()
         if rank == 0 and not args.no_cpu:
             # CPU bar for config 4: the same block mix through the C port (blocks of the first frames; stored blocks included)

@@ -291,8 +291,9 @@ class Context:
         del keep
         return st.value, out[: w.value].tobytes()
 
-    def frame_decompress(self, data, dictionary=b"", cap=None):
-        """decompress_frame over a host buffer -> (status, detail, plaintext, consumed)."""
+    def frame_decompress(self, data, dictionary=b"", cap=None, view=False):
+        """decompress_frame over a host buffer -> (status, detail, plaintext, consumed).  view=True: the plaintext comes
+        back as a uint8 numpy array over the call's own output buffer (no copy) instead of bytes."""
         a = _as_u8(data)
         d = _as_u8(dictionary)
         if cap is None:
@@ -302,7 +303,7 @@ class Context:
         st, det = C.c_int32(0), C.c_int32(0)
         self._check(self._lib.lzf_frame_decompress(self._h, _np_ptr(a), a.size, _np_ptr(d), d.size, out.ctypes.data,
                                                    int(cap), C.byref(w), C.byref(cons), C.byref(st), C.byref(det)))
-        return st.value, det.value, out[: w.value].tobytes(), cons.value
+        return st.value, det.value, (out[: w.value] if view else out[: w.value].tobytes()), cons.value
 
     def frames_compress(self, inp, in_off, in_len, out, out_off, out_cap, settings):
         """Batched host-buffer frame compress. numpy arrays; returns (out_len u64[], status i32[])."""

@@ -420,15 +420,15 @@ class _ReadAhead:
                     nblocks += self._count_blocks(carried)
                 carried = b""
                 if records:
-                    frame = self.header + records + (b"" if tail == "overflow" else (0).to_bytes(4, "little"))
+                    frame = b"".join((self.header, records, b"" if tail == "overflow" else (0).to_bytes(4, "little")))
                     status, detail, plain, consumed = self.ctx.frame_decompress(frame, dictionary=self.window,
-                                                                                cap=max(1, nblocks) * fr.block_maxsize)
-                    if plain:
+                                                                                cap=max(1, nblocks) * fr.block_maxsize, view=True)
+                    if len(plain):
                         if fr.content_hasher is not None:
                             self.ctx.xxh32_update(fr.content_hasher, plain)
                         if self.dependent:
-                            self.window = (self.window + plain)[-WINDOW_SIZE:]
-                        self.q.put(("data", plain))
+                            self.window = (self.window + plain[-WINDOW_SIZE:].tobytes())[-WINDOW_SIZE:]
+                        self.q.put(("data", memoryview(plain)))     # the batch's own output buffer: no copy on the way to the caller
                     if status != N.F_OK:
                         self.q.put(("status", (status, detail)))
                         return
@@ -443,13 +443,13 @@ class _ReadAhead:
                         while carried:
                             fr2 = self.header + carried + (0).to_bytes(4, "little")
                             status, detail, plain, consumed = self.ctx.frame_decompress(
-                                fr2, dictionary=self.window, cap=max(1, self._count_blocks(carried)) * fr.block_maxsize)
-                            if plain:
+                                fr2, dictionary=self.window, cap=max(1, self._count_blocks(carried)) * fr.block_maxsize, view=True)
+                            if len(plain):
                                 if fr.content_hasher is not None:
                                     self.ctx.xxh32_update(fr.content_hasher, plain)
                                 if self.dependent:
-                                    self.window = (self.window + plain)[-WINDOW_SIZE:]
-                                self.q.put(("data", plain))
+                                    self.window = (self.window + plain[-WINDOW_SIZE:].tobytes())[-WINDOW_SIZE:]
+                                self.q.put(("data", memoryview(plain)))
                             if status != N.F_OK:
                                 self.q.put(("status", (status, detail)))
                                 return
@@ -510,17 +510,18 @@ class LZ4FrameIoReader:
     def __init__(self, frame_reader, dictionary, read_ahead=None):
         self.frame_reader = frame_reader
         self.bytes_taken = 0
-        self.buffer = bytearray()
+        self.buffer = bytearray()           # (read-ahead: the current batch itself, a read-only view; else one decoded block)
         self.dictionary = dictionary
         self.read_ahead = self.READ_AHEAD_BYTES if read_ahead is None else int(read_ahead)
         self._ahead = None
         self._done = False
 
     def fill_buf(self):
+        """BufRead::fill_buf: the unconsumed part of the current buffer (a zero-copy view), refilled when it is empty."""
         if self.bytes_taken == len(self.buffer):
-            del self.buffer[:]
             self.bytes_taken = 0
             if self.read_ahead > 0 and self.frame_reader.block_maxsize in (64 << 10, 256 << 10, 1 << 20, 4 << 20):
+                self.buffer = b""
                 if self._done or self.frame_reader.finished:
                     return b""
                 if self._ahead is None:
@@ -532,10 +533,11 @@ class LZ4FrameIoReader:
                     raise
                 if finished:
                     self._done = True
-                self.buffer += chunk
+                self.buffer = chunk                      # bytes or a memoryview over the batch's output buffer
             else:
+                self.buffer = bytearray()
                 self.frame_reader.decode_block(self.buffer, self.dictionary)
-        return bytes(self.buffer[self.bytes_taken:])
+        return memoryview(self.buffer)[self.bytes_taken:]
 
     def consume(self, amt):
         self.bytes_taken += amt
@@ -547,7 +549,7 @@ class LZ4FrameIoReader:
         mybuf = self.fill_buf()
         take = min(len(mybuf), n)
         self.consume(take)
-        return mybuf[:take]
+        return bytes(mybuf[:take])
 
     def read_to_end(self):
         """std::io::Read::read_to_end: stops at the first read() that returns 0 bytes."""

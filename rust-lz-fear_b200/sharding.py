@@ -115,3 +115,84 @@ def payload_digest(t, chunk=32 << 20):
         s1 = (s1 + int((x * w).sum().item())) % m
         del x, w
     return (s0, s1)
+
+
+def all_ranks_ok(ok, device, group=None):
+    """Collective AND: every rank calls it and every rank gets the same answer.  The exchange steps allocate their large
+    buffers on the root only; a rank that fails locally must not leave the others waiting inside a collective it never
+    joins, so every local step that can fail is followed by this agreement before the next collective."""
+    t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return bool(t.item())
+
+
+class _WallTimer:
+    def __init__(self):
+        import time
+        self._t, self._time = 0.0, time
+
+    def start(self):
+        self._t = self._time.perf_counter()
+
+    def stop_ms(self):
+        return (self._time.perf_counter() - self._t) * 1e3
+
+
+def frames_exchange(packed, frame_sizes, device, reps=1, root=0, group=None, decode=None, timer=None, barrier=None,
+                    alloc=torch.empty):
+    """The full frame-granular exchange of SURVEY §8(e) with its verification, safe against rank-local failures:
+
+        all-gather of the per-frame sizes -> GATHER of every rank's packed frames into one archive on `root`
+        -> `root` cuts the archive at frame boundaries and SCATTERS every rank's range back -> decode(received) on every rank
+
+    `packed` = this rank's frames back to back (uint8, on `device`), `frame_sizes` = their lengths (int64 tensor).
+    `decode(received) -> bool` checks what came back (e.g. decompress and compare with the plaintext).  `alloc` is
+    torch.empty (tests inject a failing one).  Returns a dict on every rank; {"skipped": ...} when some rank could not
+    allocate — agreed on by all ranks, so nobody waits in a collective."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    timer = timer or _WallTimer()
+    sync = barrier or (lambda: dist.barrier(group=group))
+    per_rank = all_gather_sizes(frame_sizes, group=group)
+    totals = [int(x.sum().item()) for x in per_rank]
+    err, archive, recv = None, None, None
+    try:
+        if rank == root:
+            archive = alloc(sum(totals), dtype=torch.uint8, device=device)
+        recv = alloc(totals[rank], dtype=torch.uint8, device=device)
+    except Exception as e:          # noqa: BLE001 — reported, and agreed on below
+        err = "%s: %s" % (type(e).__name__, str(e)[:300])
+    if not all_ranks_ok(err is None, device, group):
+        return {"skipped": "a rank could not allocate its exchange buffers (root needs %d bytes)" % sum(totals), "this_rank_error": err}
+    for _ in range(2):                                          # NCCL sets its point-to-point channels up on first use
+        gather_bytes(packed, per_rank, dst=root, group=group, out=archive)
+        scatter_bytes(archive, totals, src=root, group=group, out=recv)
+    sync()
+    timer.start()
+    for _ in range(reps):
+        per_rank = all_gather_sizes(frame_sizes, group=group)
+        gather_bytes(packed, per_rank, dst=root, group=group, out=archive)
+    g_ms = timer.stop_ms() / reps
+    sync()
+    timer.start()
+    for _ in range(reps):
+        scatter_bytes(archive, totals, src=root, group=group, out=recv)
+    s_ms = timer.stop_ms() / reps
+    sync()
+    digs = [None] * world
+    dist.all_gather_object(digs, payload_digest(packed), group=group)
+    ok_archive = True
+    if rank == root:
+        pos = 0
+        for r in range(world):
+            ok_archive = ok_archive and payload_digest(archive[pos:pos + totals[r]]) == tuple(digs[r])
+            pos += totals[r]
+    ok_local = bool(torch.equal(recv, packed[: totals[rank]]))
+    if decode is not None:
+        try:
+            ok_local = ok_local and bool(decode(recv))
+        except Exception as e:      # noqa: BLE001
+            ok_local, err = False, "%s: %s" % (type(e).__name__, str(e)[:200])
+    ok_all = all_ranks_ok(ok_local, device, group)
+    ok_archive = all_ranks_ok(ok_archive, device, group)       # the root's verdict, known everywhere
+    return {"gather_ms": g_ms, "scatter_ms": s_ms, "totals": totals, "archive_slices_equal_senders_digests": ok_archive,
+            "scattered_frames_equal_on_every_rank_and_decoded": ok_all, "this_rank_error": err}

@@ -67,6 +67,29 @@ def main():
     if rank == 0:
         assert back.numpy().tobytes() == b"".join(datas), "scattered -> decoded -> gathered plaintext differs"
         print("MULTI-RANK-OK")
+    # the packaged exchange bench.py runs at N > 1 (gather -> scatter -> decode, verified), and its behaviour when ONE rank
+    # cannot allocate its buffers: every rank must come back with the same "skipped" verdict instead of waiting forever
+    def decode_ok(received):
+        p, ok = 0, True
+        for i in range(lo, hi):
+            st, det, plain, _c = ctx.frame_decompress(received[p: p + all_sizes[i]].numpy(), cap=len(datas[i]) + 16)
+            ok = ok and (st, plain) == (0, datas[i])
+            p += all_sizes[i]
+        return ok
+    res = sharding.frames_exchange(local[: totals[rank]], sizes, "cpu", reps=2, decode=decode_ok)
+    assert res.get("archive_slices_equal_senders_digests") and res.get("scattered_frames_equal_on_every_rank_and_decoded"), res
+
+    def failing_alloc(n, **kw):
+        if rank == 0 and n > totals[0]:
+            raise MemoryError("injected: no room for the archive")
+        return torch.empty(n, **kw)
+    res = sharding.frames_exchange(local[: totals[rank]], sizes, "cpu", alloc=failing_alloc)
+    assert "skipped" in res, res
+    # ... and the ranks are still in step afterwards
+    res = sharding.frames_exchange(local[: totals[rank]], sizes, "cpu", decode=lambda r: rank != 1)
+    assert res["scattered_frames_equal_on_every_rank_and_decoded"] is False and res["archive_slices_equal_senders_digests"], res
+    if rank == 0:
+        print("EXCHANGE-OK")
     dist.barrier()
     dist.destroy_process_group()
 

@@ -38,4 +38,4 @@ def test_sharded_compress_gather_matches_single_process(world, simt_lib_path):
                                       env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs = [p.communicate(timeout=600)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
-    assert "MULTI-RANK-OK" in outs[0]
+    assert "MULTI-RANK-OK" in outs[0] and "EXCHANGE-OK" in outs[0]
