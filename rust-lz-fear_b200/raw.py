@@ -59,18 +59,45 @@ class WriterFull(OSError):
 
 
 class EncoderTable:
-    """EncoderTable (src/raw/compress/mod.rs:19-25).  The table itself lives in shared memory on the
-    GPU for the duration of one block; host objects only select the flavour and carry `hashlog`."""
+    """EncoderTable (src/raw/compress/mod.rs:19-25).  While a table is fresh (Default::default(), never used with a
+    history) it only selects the flavour: the kernel zeroes its own copy.  The first call that carries state — cursor > 0,
+    offset(), or a second compress2 with the same table — makes it a device-resident object (lzf_table_*) that lives
+    across calls with the reference's replace / offset semantics."""
     kind = N.TABLE_U32
     _LIMIT = 0xFFFFFFFF
 
     def __init__(self, hashlog=12):
         self.hashlog = hashlog
         self._fresh = True
+        self._handle = None
+        self._ctx = None
+        self._pending_offset = 0
 
     @classmethod
     def payload_size_limit(cls):
         return cls._LIMIT
+
+    def offset(self, offset):
+        """EncoderTable::offset (:72-74,97-99): positions of later calls are shifted by `offset`."""
+        self._pending_offset += int(offset)
+        self._fresh = False
+
+    def _device(self, ctx):
+        if self._handle is None:
+            self._ctx = ctx
+            self._handle = ctx.table_new(self.kind, self.hashlog)
+        if self._pending_offset:
+            ctx.table_offset(self._handle, self._pending_offset)
+            self._pending_offset = 0
+        return self._handle
+
+    def __del__(self):
+        if getattr(self, "_handle", None) is not None and self._ctx is not None:
+            try:
+                self._ctx.table_free(self._handle)
+            except Exception:            # noqa: BLE001 — interpreter shutdown
+                pass
+            self._handle = None
 
 
 class U32Table(EncoderTable):          # src/raw/compress/mod.rs:27-36,63-76
@@ -83,26 +110,30 @@ class U16Table(EncoderTable):          # src/raw/compress/mod.rs:78-101
     _LIMIT = 0xFFFF
 
 
-def _compress(input, table, cap, ctx):
+def _compress(input, table, cap, ctx, cursor=0):
     ctx = ctx or default_context()
     table = table or U32Table()
     if len(input) > table.payload_size_limit():
         raise AssertionError("assertion failed: input.len() <= T::payload_size_limit()")   # mod.rs:167
-    status, out = ctx.raw_compress_into(input, cap=cap, table=table.kind, hashlog=table.hashlog)
+    if cursor == 0 and table._fresh:
+        status, out = ctx.raw_compress_into(input, cap=cap, table=table.kind, hashlog=table.hashlog)
+    else:
+        status, out = ctx.raw_compress2(input, cursor, table._device(ctx), cap=cap)
     if status == N.PANIC:
         raise AssertionError("EncoderTable contract violated")
     return status, out
 
 
 def compress2(input, cursor, table, writer, ctx=None):
-    """raw::compress2 with cursor 0 and a fresh table (the independent-block call of the framed path,
-    src/framed/compress.rs:242-243,265-270).  `writer` needs a .write(bytes) method."""
-    if cursor != 0 or (table is not None and not table._fresh):
-        raise NotImplementedError("prefix / carried-over table state (dependent blocks) is not on the GPU path yet")
-    status, out = _compress(input, table, None, ctx)
-    assert status == N.OK
-    if table is not None and len(input):
+    """raw::compress2(input, cursor, &mut table, writer) (src/raw/compress/mod.rs:165-238): input[..cursor] is match-only
+    history, the table keeps its entries from call to call (dependent blocks, src/framed/compress.rs:220,270-275).
+    `writer` needs a .write(bytes) method; an unbounded writer never refuses."""
+    if table is not None and table._fresh and cursor == 0 and len(input):
+        # first use of a fresh table at cursor 0: the kernel's own zeroed table would do, but the caller may come back
+        # with the same table, so the state has to be kept from the start
         table._fresh = False
+    status, out = _compress(input, table, None, ctx, cursor)
+    assert status == N.OK
     writer.write(out)
 
 

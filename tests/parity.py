@@ -395,3 +395,33 @@ def check_streaming_host_mirror(backend, oracle, scale=1):
             assert out.getvalue() == oracle.frame_compress(data, content_size=len(data), **kw)[1], kw
     finally:
         L.raw.set_default_context(None)
+
+
+def check_raw_mirror_with_history(backend, oracle):
+    """lz_fear_b200.raw.compress2 with cursor > 0 / a table used twice / table.offset(): the Python mirror of
+    src/raw/compress/mod.rs:165-170 over lzf_raw_compress2 (was NotImplementedError in round 1)."""
+    import io
+    import lz_fear_b200 as L
+    L.raw.set_default_context(backend.ctx)
+    try:
+        data = W.text(200000, 3).numpy().tobytes()
+        for mk, omk, n0, n1 in ((L.raw.U32Table, lambda: oracle.Table(), 70000, 150000),
+                                (L.raw.U16Table, lambda: oracle.Table(N.TABLE_U16), 20000, 60000)):
+            t, ot = mk(), omk()
+            w = io.BytesIO(); L.raw.compress2(data[:n0], 0, t, w)
+            assert (0, w.getvalue()) == oracle.compress2(data[:n0], 0, ot)
+            w = io.BytesIO(); L.raw.compress2(data[:n1], n0, t, w)
+            assert (0, w.getvalue()) == oracle.compress2(data[:n1], n0, ot)
+        t, ot = L.raw.U32Table(), oracle.Table()
+        L.raw.compress2(data[:100000], 0, t, io.BytesIO()); oracle.compress2(data[:100000], 0, ot)
+        t.offset(40000); ot.offset(40000)                               # the frame writer's window slide
+        w = io.BytesIO(); L.raw.compress2(data[40000:], 60000, t, w)
+        assert (0, w.getvalue()) == oracle.compress2(data[40000:], 60000, ot)
+        out = bytearray(100000)
+        n = L.raw.compress_into(data[:100000], out)
+        assert bytes(out[:n]) == oracle.compress_block(data[:100000])[1]
+        import pytest
+        with pytest.raises(L.raw.WriterFull):
+            L.raw.compress_into(W.random_bytes(5000, 1).numpy().tobytes(), bytearray(5000))
+    finally:
+        L.raw.set_default_context(None)

@@ -363,3 +363,7 @@ def test_batched_calls_on_two_streams_do_not_race(gpu, oracle):       # ADVICE r
     torch.cuda.synchronize()
     for k in range(2):
         assert int(sts[k].abs().sum()) == 0 and torch.equal(backs[k], datas[k])
+
+
+def test_raw_mirror_compress2_with_history(gpu, oracle):
+    parity.check_raw_mirror_with_history(gpu, oracle)

@@ -377,3 +377,7 @@ def test_segmented_parse_is_valid_lz4_of_reference_size(emu, oracle):
 
 def test_streaming_reader_and_writer(emu, oracle):               # src/framed/decompress.rs:46-77, examples/delz4.rs
     parity.check_streaming_host_mirror(emu, oracle)
+
+
+def test_raw_mirror_compress2_with_history(emu, oracle):
+    parity.check_raw_mirror_with_history(emu, oracle)
