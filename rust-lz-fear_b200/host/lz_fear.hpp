@@ -54,11 +54,34 @@ struct DecodeError : std::runtime_error {
 // io::ErrorKind::ConnectionAborted out of NoPartialWrites — src/framed/compress.rs:298-301
 struct WriterFull : std::runtime_error { WriterFull() : std::runtime_error("ConnectionAborted") {} };
 
-// EncoderTable flavours — src/raw/compress/mod.rs:27-36,78-101.  The table lives in shared memory on the GPU.
-struct U32Table { static constexpr uint32_t kind = LZF_TABLE_U32; static size_t payload_size_limit() { return 0xffffffffull; } bool fresh = true; };
-struct U16Table { static constexpr uint32_t kind = LZF_TABLE_U16; static size_t payload_size_limit() { return 0xffffull; } bool fresh = true; };
+// EncoderTable flavours — src/raw/compress/mod.rs:19-101.  A fresh table only selects the flavour (the kernel zeroes
+// its own copy); the first call that carries state — cursor > 0, offset(), a second compress2 — makes it a
+// device-resident object (lzf_table_*) with the reference's replace / offset semantics.
+template <uint32_t kKind, uint64_t kLimit>
+struct DeviceTable {
+    static constexpr uint32_t kind = kKind;
+    static size_t payload_size_limit() { return (size_t)kLimit; }
+    bool fresh = true;
+    DeviceTable() = default;
+    DeviceTable(const DeviceTable&) = delete;
+    DeviceTable& operator=(const DeviceTable&) = delete;
+    ~DeviceTable() { if (h_) lzf_table_destroy(ctx_ ? ctx_->get() : nullptr, h_); }
+    void offset(size_t by) { pending_ += by; fresh = false; }                  // EncoderTable::offset :72-74,97-99
+    lzf_table* device(Context& ctx) {
+        if (!h_) { ctx_ = &ctx; ctx.check(lzf_table_create(ctx.get(), kKind, 12, &h_)); }
+        if (pending_) { ctx.check(lzf_table_offset(ctx.get(), h_, pending_)); pending_ = 0; }
+        return h_;
+    }
+  private:
+    lzf_table* h_ = nullptr;
+    Context* ctx_ = nullptr;
+    uint64_t pending_ = 0;
+};
+using U32Table = DeviceTable<LZF_TABLE_U32, 0xffffffffull>;
+using U16Table = DeviceTable<LZF_TABLE_U16, 0xffffull>;
 
-// compress2 through NoPartialWrites(out[..cap]) — src/raw/compress/mod.rs:165-238, src/framed/compress.rs:242
+// compress2 through NoPartialWrites(out[..cap]) from a fresh table at cursor 0 — src/raw/compress/mod.rs:165-238,
+// src/framed/compress.rs:242
 template <class Table = U32Table>
 inline size_t compress_into(const uint8_t* input, size_t n, uint8_t* out, size_t cap, Context& ctx = Context::default_context()) {
     if (n > Table::payload_size_limit()) throw std::logic_error("assertion failed: input.len() <= T::payload_size_limit()");
@@ -70,14 +93,20 @@ inline size_t compress_into(const uint8_t* input, size_t n, uint8_t* out, size_t
     return written;
 }
 
-// raw::compress2 (cursor 0, fresh table) into any writer with write(const char*, std::streamsize)
+// raw::compress2(input, cursor, &mut table, writer) — src/raw/compress/mod.rs:165-170: input[..cursor] is match-only
+// history, the table keeps its entries from call to call (src/framed/compress.rs:220,270-275).  Any writer with
+// write(const char*, std::streamsize); an unbounded writer never refuses.
 template <class Writer, class Table>
 inline void compress2(const uint8_t* input, size_t n, size_t cursor, Table& table, Writer& writer, Context& ctx = Context::default_context()) {
-    if (cursor != 0 || !table.fresh) throw std::logic_error("prefix / carried-over table state is not on the GPU path yet");
+    if (n > Table::payload_size_limit()) throw std::logic_error("assertion failed: input.len() <= T::payload_size_limit()");
     std::vector<uint8_t> buf(lzf_compress_bound(n));
-    const size_t w = compress_into<Table>(input, n, buf.data(), buf.size(), ctx);
+    size_t written = 0;
+    int32_t status = 0;
     if (n) table.fresh = false;
-    writer.write(reinterpret_cast<const char*>(buf.data()), (std::streamsize)w);
+    ctx.check(lzf_raw_compress2(ctx.get(), input, n, cursor, table.device(ctx), buf.data(), buf.size(), &written, &status));
+    if (status == LZF_WRITER_FULL) throw WriterFull();
+    if (status != LZF_OK) throw std::logic_error("EncoderTable contract violated");
+    writer.write(reinterpret_cast<const char*>(buf.data()), (std::streamsize)written);
 }
 
 // raw::decompress_raw — src/raw/decompress.rs:58-78: appends to `output`; bytes already in it are history
