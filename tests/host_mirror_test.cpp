@@ -50,24 +50,26 @@ int main() {
         try { raw::compress_into((const uint8_t*)s.data(), s.size(), small, sizeof(small)); } catch (const raw::WriterFull&) { threw = true; }
         CHECK(threw);
     }
-    {   // compress2 with history and a table that lives across calls (src/raw/compress/mod.rs:165-170): the second call's
-        // matches reach into the first part, so it only decodes with that part as the prefix
-        std::string text;
-        for (int i = 0; i < 6000; i++) text += "the quick brown fox " + std::to_string(i % 97) + " jumps over the lazy dog; ";
-        const size_t cut = text.size() / 2;
+    {   // compress2 with history and a table that lives across calls (src/raw/compress/mod.rs:165-170): the second half
+        // repeats the first (pseudo-random bytes), so it compresses only through matches that reach into the history
+        std::string half;
+        uint32_t x = 12345;
+        for (int i = 0; i < 40000; i++) { x = x * 1664525u + 1013904223u; half += (char)(x >> 24); }
+        const std::string both = half + half;
         raw::U32Table t;
         std::ostringstream w1, w2;
-        raw::compress2((const uint8_t*)text.data(), cut, 0, t, w1);
-        raw::compress2((const uint8_t*)text.data(), text.size(), cut, t, w2);
+        raw::compress2((const uint8_t*)both.data(), half.size(), 0, t, w1);
+        raw::compress2((const uint8_t*)both.data(), both.size(), half.size(), t, w2);
         const std::string c1 = w1.str(), c2 = w2.str();
+        CHECK(c1.size() > half.size() && c2.size() < half.size() / 20);
         std::vector<uint8_t> first, second;
         raw::decompress_raw((const uint8_t*)c1.data(), c1.size(), nullptr, 0, first, size_t(1) << 30);
-        CHECK(std::string(first.begin(), first.end()) == text.substr(0, cut));
-        raw::decompress_raw((const uint8_t*)c2.data(), c2.size(), (const uint8_t*)text.data(), cut, second, size_t(1) << 30);
-        CHECK(std::string(second.begin(), second.end()) == text.substr(cut));
-        bool threw = false;                                       // ... and without the prefix its first far match is invalid
+        CHECK(std::string(first.begin(), first.end()) == half);
+        raw::decompress_raw((const uint8_t*)c2.data(), c2.size(), (const uint8_t*)both.data(), half.size(), second, size_t(1) << 30);
+        CHECK(std::string(second.begin(), second.end()) == half);
+        bool threw = false;                                       // without the history its matches point nowhere
         try { std::vector<uint8_t> o3; raw::decompress_raw((const uint8_t*)c2.data(), c2.size(), nullptr, 0, o3, size_t(1) << 30); }
-        catch (const raw::DecodeError&) { threw = true; }
+        catch (const raw::DecodeError& e) { threw = e.kind == raw::DecodeError::InvalidDeduplicationOffset; }
         CHECK(threw);
     }
     {   // frames: CompressionSettings -> LZ4FrameReader, block by block and all at once
