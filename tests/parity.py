@@ -425,3 +425,121 @@ def check_raw_mirror_with_history(backend, oracle):
             L.raw.compress_into(W.random_bytes(5000, 1).numpy().tobytes(), bytearray(5000))
     finally:
         L.raw.set_default_context(None)
+
+
+# ---------------------------------------------------------------------------------------------
+# seeded structural fuzz: many small inputs of the shapes LZ4 parsers get wrong (runs, periods, repeats around the 64 KiB
+# window, tails shorter than the end-of-block rules), every case compared with the oracle byte for byte
+# ---------------------------------------------------------------------------------------------
+def fuzz_input(rng, max_len=200000, depth=0):
+    kind = int(rng.integers(0, 8))
+    if depth and kind == 6:
+        kind = 2
+    n = int(rng.integers(1, max_len)) if rng.integers(0, 4) else int(rng.integers(1, 400))
+    if kind == 0:                                           # incompressible
+        return rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+    if kind == 1:                                           # runs over a tiny alphabet
+        a = rng.integers(0, int(rng.integers(2, 6)), n, dtype=np.uint8)
+        return np.repeat(a, rng.integers(1, int(rng.integers(2, 80)), n))[:n].astype(np.uint8).tobytes()
+    if kind == 2:                                           # words from a vocabulary
+        vocab = [bytes(rng.integers(97, 123, int(rng.integers(1, 12)), dtype=np.uint8)) for _ in range(int(rng.integers(2, 400)))]
+        out = bytearray()
+        while len(out) < n:
+            out += vocab[int(rng.integers(0, len(vocab)))] + b" "
+        return bytes(out[:n])
+    if kind == 3:                                           # one repeat at a chosen distance (window edges included)
+        base = rng.integers(0, 256, int(rng.integers(8, 3000)), dtype=np.uint8).tobytes()
+        d = int(rng.choice([1, 2, 3, 4, 7, 8, 15, 16, 31, 32, 33, 63, 64, 65, 255, 4096, 65534, 65535, 65536, 65537, 70000, 131072]))
+        d = min(d, max_len)
+        filler = rng.integers(0, 256, max(0, d - len(base)), dtype=np.uint8).tobytes()
+        return (base + filler + base + rng.integers(0, 4, int(rng.integers(0, 3000)), dtype=np.uint8).tobytes())[:max(n, 13)]
+    if kind == 4:                                           # periodic with point noise
+        p = int(rng.integers(1, 200))
+        a = np.tile(rng.integers(0, 256, p, dtype=np.uint8), n // p + 1)[:n].copy()
+        k = int(rng.integers(0, max(1, n // 50)))
+        if k:
+            a[rng.integers(0, n, k)] = rng.integers(0, 256, k, dtype=np.uint8)
+        return a.tobytes()
+    if kind == 5:                                           # zeros with islands of noise
+        a = np.zeros(n, dtype=np.uint8)
+        for _ in range(int(rng.integers(0, 20))):
+            s = int(rng.integers(0, n))
+            a[s:s + 300] = rng.integers(0, 256, len(a[s:s + 300]), dtype=np.uint8)
+        return a.tobytes()
+    if kind == 6:                                           # a mixture of short pieces of the above
+        parts, tot = [], 0
+        while tot < n:
+            parts.append(fuzz_input(np.random.default_rng(int(rng.integers(0, 1 << 30))), max_len, 1)[:int(rng.integers(1, 5000))])
+            tot += len(parts[-1])
+        return b"".join(parts)[:n]
+    m = int(rng.choice([12, 13, 16, 17, 31, 32, 33, 64, 65, 66, 67, 68, 69, 99, 100, 128]))   # lengths around the tail rules
+    return bytes(rng.integers(97, 100, m, dtype=np.uint8))
+
+
+def check_fuzz_blocks(backend, oracle, seed, count, max_len=200000):
+    """raw compress (both table kinds, bounded and unbounded writers) and raw decompress (valid, truncated and mutated
+    streams, several output limits) on `count` seeded inputs: status, bytes and lengths equal to the oracle's."""
+    ctx = backend.ctx
+    for i in range(count):
+        rng = np.random.default_rng(seed * 1000003 + i)
+        data = fuzz_input(rng, max_len)
+        tk = N.TABLE_U16 if (len(data) <= 0xFFFF and rng.integers(0, 3) == 0) else N.TABLE_U32
+        capsel = int(rng.integers(0, 3))
+        cap = None if capsel == 0 else (len(data) if capsel == 1 else int(rng.integers(0, len(data) + 20)))
+        got = ctx.raw_compress_into(data, cap=cap, table=tk)
+        want = oracle.compress_block(data, table=tk, cap=cap)
+        assert got[0] == want[0] and (got[0] != 0 or got[1] == want[1]), ("compress", seed, i, len(data), tk, cap, got[0], want[0])
+        if got[0] != 0 or rng.integers(0, 3):
+            continue
+        for blob in (got[1], got[1][: max(1, int(rng.integers(1, len(got[1]) + 1)))]):
+            a = bytearray(blob)
+            if len(a) and rng.integers(0, 2):
+                a[int(rng.integers(0, len(a)))] = int(rng.integers(0, 256))
+            lim = int(rng.choice([len(data), max(0, len(data) - 1), len(data) + 5, 1 << 30]))
+            capd = len(data) + len(a) + 64
+            d1 = ctx.raw_decompress(bytes(a), out_limit=lim, cap=capd)
+            d2 = oracle.decompress_raw(bytes(a), out_limit=lim, cap=capd)
+            assert d1 == d2, ("decompress", seed, i, len(a), lim, d1[0], d2[0], d1[2], d2[2])
+
+
+def check_fuzz_frames(backend, oracle, seed, count, max_len=200000):
+    """CompressionSettings over random flag / block size / dictionary / content size combinations: frames equal to the
+    oracle's; then the valid, a truncated and a mutated copy of every frame decode to the oracle's status, detail, bytes
+    and consumed count."""
+    ctx = backend.ctx
+    for i in range(count):
+        rng = np.random.default_rng(seed * 7919 + i)
+        data = fuzz_input(rng, max_len)
+        if rng.integers(0, 3) == 0:
+            data = data * int(rng.integers(1, 4))
+        kw = dict(independent_blocks=bool(rng.integers(0, 2)), block_checksums=bool(rng.integers(0, 2)),
+                  content_checksum=bool(rng.integers(0, 2)), block_size=int(rng.choice([65536, 262144, 1 << 20, 4 << 20])))
+        dic = None
+        if rng.integers(0, 3) == 0:
+            dn = int(rng.choice([0, 1, 5, 100, 4000, 65536, 70000]))
+            dic = (data[: dn // 2] + bytes(rng.integers(0, 256, dn, dtype=np.uint8)))[:dn] if dn else b""
+            kw["dictionary"] = dic
+            if rng.integers(0, 2):
+                kw["dictionary_id"] = int(rng.integers(0, 1 << 32))
+        if rng.integers(0, 3) == 0:
+            kw["content_size"] = len(data)
+        shown = {k: v for k, v in kw.items() if k != "dictionary"}
+        st, fr = ctx.frame_compress(data, **kw)
+        orc, ofr = oracle.frame_compress(data, **kw)
+        assert st == orc and (orc != 0 or fr == ofr), ("frame compress", seed, i, len(data), shown, st, orc)
+        if orc != 0:
+            continue
+        for t in range(3):
+            a = bytearray(ofr)
+            if t == 1 and len(a):
+                a = a[: int(rng.integers(0, len(a) + 1))]
+            if t == 2 and len(a):
+                for _ in range(int(rng.integers(1, 4))):          # half of the hits land in the header / first block header
+                    pos = int(rng.integers(0, min(len(a), 32))) if rng.integers(0, 2) else int(rng.integers(0, len(a)))
+                    a[pos] = int(rng.integers(0, 256))
+            a = bytes(a) + (b"xyz" if rng.integers(0, 4) == 0 else b"")
+            cap = len(data) + int(rng.choice([0, 16, 1 << 16]))
+            g = ctx.frame_decompress(a, dictionary=dic or b"", cap=cap)
+            w = oracle.frame_decompress(a, dictionary=dic or b"", cap=cap)
+            assert g[0] == w[0] and g[1] == w[1] and (g[0] != 0 or (g[2] == w[2] and g[3] == w[3])), \
+                ("frame decompress", seed, i, t, len(a), cap, shown, g[0], g[1], len(g[2]), g[3], w[0], w[1], len(w[2]), w[3])

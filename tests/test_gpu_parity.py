@@ -367,3 +367,8 @@ def test_batched_calls_on_two_streams_do_not_race(gpu, oracle):       # ADVICE r
 
 def test_raw_mirror_compress2_with_history(gpu, oracle):
     parity.check_raw_mirror_with_history(gpu, oracle)
+
+
+def test_seeded_structural_fuzz(gpu, oracle):
+    parity.check_fuzz_blocks(gpu, oracle, seed=21, count=600)
+    parity.check_fuzz_frames(gpu, oracle, seed=21, count=300)

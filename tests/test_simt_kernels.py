@@ -381,3 +381,8 @@ def test_streaming_reader_and_writer(emu, oracle):               # src/framed/de
 
 def test_raw_mirror_compress2_with_history(emu, oracle):
     parity.check_raw_mirror_with_history(emu, oracle)
+
+
+def test_seeded_structural_fuzz(emu, oracle):                   # 3900 more cases of the same generator were run once by hand
+    parity.check_fuzz_blocks(emu, oracle, seed=11, count=90, max_len=60000)
+    parity.check_fuzz_frames(emu, oracle, seed=11, count=50, max_len=60000)
