@@ -543,3 +543,88 @@ def check_fuzz_frames(backend, oracle, seed, count, max_len=200000):
             w = oracle.frame_decompress(a, dictionary=dic or b"", cap=cap)
             assert g[0] == w[0] and g[1] == w[1] and (g[0] != 0 or (g[2] == w[2] and g[3] == w[3])), \
                 ("frame decompress", seed, i, t, len(a), cap, shown, g[0], g[1], len(g[2]), g[3], w[0], w[1], len(w[2]), w[3])
+
+
+def check_fuzz_frame_batches(backend, oracle, seed, count, max_len=120000):
+    """lzf_frames_compress / lzf_frames_decompress over batches of 1..13 frames laid out with gaps: random settings, empty
+    frames, capacities that fit exactly / miss by a few bytes / are random, truncated and mutated frames among valid ones.
+    Every frame must come out exactly as the oracle produces it on its own, a frame that does not fit must fail, and
+    nothing outside a frame's [offset, offset + capacity) may be written."""
+    ctx = backend.ctx
+
+    def layout(sizes, rng, gap):
+        off, p = np.zeros(len(sizes), dtype=np.uint64), 0
+        for k, n in enumerate(sizes):
+            p += int(rng.integers(0, gap))
+            off[k] = p
+            p += int(n)
+        return off, p
+
+    def untouched(buf, off, caps, fill):
+        mask = np.ones(buf.size, bool)
+        for o, c in zip(off, caps):
+            mask[int(o):int(o) + int(c)] = False
+        return bool((buf[mask] == fill).all())
+
+    for i in range(count):
+        rng = np.random.default_rng(seed * 49979687 + i)
+        nf = int(rng.integers(1, 14))
+        datas = [fuzz_input(rng, max_len) if rng.integers(0, 8) else b"" for _ in range(nf)]
+        kw = dict(independent_blocks=bool(rng.integers(0, 2)), block_checksums=bool(rng.integers(0, 2)),
+                  content_checksum=bool(rng.integers(0, 2)), block_size=int(rng.choice([65536, 262144])))
+        dic = None
+        if rng.integers(0, 4) == 0:
+            dic = fuzz_input(rng, 70000)
+            kw["dictionary"] = dic
+        s, _keep = N.make_settings(**kw)
+        in_len = np.array([len(d) for d in datas], dtype=np.uint64)
+        in_off, total = layout(in_len, rng, 40)
+        src = np.full(total + 8, 0x55, dtype=np.uint8)
+        for f in range(nf):
+            src[int(in_off[f]):int(in_off[f]) + len(datas[f])] = np.frombuffer(datas[f], dtype=np.uint8)
+        wants = [oracle.frame_compress(d, **kw) for d in datas]
+        caps = np.zeros(nf, dtype=np.uint64)
+        for f in range(nf):
+            b = ctx.frame_bound(s, len(datas[f]))
+            sel = int(rng.integers(0, 5))
+            caps[f] = b if sel < 2 else (len(wants[f][1]) if sel == 2 else
+                                         (max(0, len(wants[f][1]) - int(rng.integers(1, 9))) if sel == 3 else int(rng.integers(0, b + 1))))
+        out_off, total = layout(caps, rng, 40)
+        out = np.full(total + 8, 0xEE, dtype=np.uint8)
+        fl, fs = ctx.frames_compress(src, in_off, in_len, out, out_off, caps, s)
+        good = []
+        for f in range(nf):
+            w, o = wants[f], int(out_off[f])
+            if w[0] == 0 and len(w[1]) <= int(caps[f]):
+                assert int(fs[f]) == 0 and out[o:o + int(fl[f])].tobytes() == w[1], ("batched compress", seed, i, f, nf, int(fs[f]), int(fl[f]), len(w[1]))
+                good.append(f)
+            else:
+                assert int(fs[f]) != 0, ("frame must not fit", seed, i, f, int(caps[f]), len(w[1]), w[0])
+        assert untouched(out, out_off, caps, 0xEE), ("compress wrote outside a frame's capacity", seed, i)
+        if not good or dic is not None:               # the batched host decode takes no dictionary
+            continue
+        frames = []
+        for f in good:
+            a = bytearray(wants[f][1])
+            m = int(rng.integers(0, 4))
+            if m == 1 and len(a):
+                a = a[: int(rng.integers(0, len(a) + 1))]
+            if m == 2 and len(a):
+                pos = int(rng.integers(0, min(len(a), 32))) if rng.integers(0, 2) else int(rng.integers(0, len(a)))
+                a[pos] = int(rng.integers(0, 256))
+            frames.append(bytes(a))
+        dl = np.array([len(x) for x in frames], dtype=np.uint64)
+        do, total = layout(dl, rng, 30)
+        packed = np.full(total + 8, 0x77, dtype=np.uint8)
+        for k, fr in enumerate(frames):
+            packed[int(do[k]):int(do[k]) + len(fr)] = np.frombuffer(fr, dtype=np.uint8)
+        ocap = np.array([len(datas[f]) + int(rng.choice([0, 0, 16, 100])) for f in good], dtype=np.uint64)
+        oo, total = layout(ocap, rng, 30)
+        pout = np.full(total + 8, 0xDD, dtype=np.uint8)
+        ol, st, det = ctx.frames_decompress(packed, do, dl, pout, oo, ocap)
+        for k in range(len(frames)):
+            w = oracle.frame_decompress(frames[k], cap=int(ocap[k]))
+            assert (int(st[k]), int(det[k])) == (w[0], w[1]) and \
+                (w[0] != 0 or pout[int(oo[k]):int(oo[k]) + int(ol[k])].tobytes() == w[2]), \
+                ("batched decode", seed, i, k, len(frames[k]), int(ocap[k]), int(st[k]), int(det[k]), int(ol[k]), w[0], w[1], len(w[2]))
+        assert untouched(pout, oo, ocap, 0xDD), ("decode wrote outside a frame's capacity", seed, i)

@@ -386,3 +386,4 @@ def test_raw_mirror_compress2_with_history(emu, oracle):
 def test_seeded_structural_fuzz(emu, oracle):                   # 3900 more cases of the same generator were run once by hand
     parity.check_fuzz_blocks(emu, oracle, seed=11, count=90, max_len=60000)
     parity.check_fuzz_frames(emu, oracle, seed=11, count=50, max_len=60000)
+    parity.check_fuzz_frame_batches(emu, oracle, seed=11, count=20, max_len=50000)
