@@ -16,4 +16,7 @@ from . import raw, framed  # noqa: E402,F401
 from .framed import (  # noqa: E402,F401
     CompressionSettings, CompressionError, LZ4FrameReader, LZ4FrameIoReader, DecompressionError,
     decompress_frame, MAGIC, WINDOW_SIZE,
+    # CompressionError / DecompressionError variants (src/framed/compress.rs:33-42, decompress.rs:20-44)
+    ReadError, WriteError, InvalidBlockSize, InputError, CodecError, HeaderParseError, WrongMagic, HeaderChecksumFail,
+    BlockChecksumFail, FrameChecksumFail, BlockLengthOverflow, BlockSizeOverflow,
 )

@@ -164,11 +164,12 @@ class CompressionSettings:
         ctx = self._ctx or _raw.default_context()
         s, keep = self._settings(content_size)
         streamable = self._independent_blocks and not self._dictionary and self._block_size in (64 << 10, 256 << 10, 1 << 20, 4 << 20)
+        chunk_bytes = max(self._block_size, self.STREAM_CHUNK_BYTES // self._block_size * self._block_size) if streamable else -1
         try:
-            first = reader.read(self.STREAM_CHUNK_BYTES if streamable else -1)
+            first = _read_up_to(reader, chunk_bytes)
         except OSError as e:
             raise ReadError(str(e)) from e
-        if not streamable or len(first) < self.STREAM_CHUNK_BYTES:
+        if not streamable or len(first) < chunk_bytes:
             status, frame = ctx.frame_compress(first, settings=s)       # everything fits one call
             del keep
             _raise_frame_status(status)
@@ -177,9 +178,9 @@ class CompressionSettings:
             except OSError as e:
                 raise WriteError(str(e)) from e
             return
-        self._compress_streaming(ctx, reader, writer, first, content_size)
+        self._compress_streaming(ctx, reader, writer, first, content_size, chunk_bytes)
 
-    def _compress_streaming(self, ctx, reader, writer, first, content_size):
+    def _compress_streaming(self, ctx, reader, writer, first, content_size, chunk_bytes):
         import threading
         import queue
         # the header as compress_internal writes it (:163-200): taken from an empty frame with the same settings
@@ -194,7 +195,17 @@ class CompressionSettings:
         chunk_hlen = 7
         hasher = ctx.xxh32_new() if self._content_checksum else None
         q = queue.Queue(maxsize=2)
+        stop = threading.Event()            # set when the consumer gives up (a failing writer): the producer must not block
         worker_ctx = N.Context(ctx.device) if hasattr(ctx, "device") else ctx
+
+        def put(item):
+            while not stop.is_set():
+                try:
+                    q.put(item, timeout=0.05)
+                    return True
+                except queue.Full:
+                    pass
+            return False
 
         def produce():
             try:
@@ -203,15 +214,15 @@ class CompressionSettings:
                     st, fr = worker_ctx.frame_compress(chunk, settings=s_chunk)
                     if hasher is not None and st == N.F_OK:
                         worker_ctx.xxh32_update(hasher, chunk)
-                    q.put((st, fr))
-                    if st != N.F_OK:
+                    if not put((st, fr)) or st != N.F_OK:
                         return
-                    chunk = reader.read(self.STREAM_CHUNK_BYTES)
-                q.put(None)
+                    # a reader may return short counts (pipes, sockets): a chunk is cut at EOF only, never inside a block
+                    chunk = _read_up_to(reader, chunk_bytes)
+                put(None)
             except OSError as e:
-                q.put(ReadError(str(e)))
+                put(ReadError(str(e)))
             except Exception as e:          # noqa: BLE001 — handed to the consumer
-                q.put(e)
+                put(e)
 
         t = threading.Thread(target=produce, daemon=True)
         t.start()
@@ -232,6 +243,7 @@ class CompressionSettings:
         except OSError as e:
             raise WriteError(str(e)) from e
         finally:
+            stop.set()
             t.join()
             if worker_ctx is not ctx:
                 worker_ctx.close()
@@ -241,6 +253,24 @@ class CompressionSettings:
         out = io.BytesIO()
         self.compress(io.BytesIO(bytes(data)), out)
         return out.getvalue()
+
+
+def _read_up_to(reader, n):
+    """Read::read until `n` bytes are there or the stream ends (n < 0: everything) — what the reference's block loop does
+    with its own buffer (compress.rs:222-231: read until the block is full or read() returns 0)."""
+    if n < 0:
+        return reader.read()
+    first = reader.read(n)
+    if len(first) == n or not first:
+        return first
+    parts, total = [first], len(first)
+    while total < n:
+        more = reader.read(n - total)
+        if not more:
+            break
+        parts.append(more)
+        total += len(more)
+    return b"".join(parts)
 
 
 def _read_exact(reader, n):
@@ -365,6 +395,8 @@ class _ReadAhead:
         import threading
         self.fr = fr
         self.q = queue.Queue(maxsize=2)
+        self._queue_full = queue.Full
+        self.stop = threading.Event()                        # set by close(): a reader dropped mid-frame must not strand the thread
         self.batch_bytes = batch_bytes
         base = fr._context()
         self.ctx = N.Context(base.device) if hasattr(base, "device") else base
@@ -378,6 +410,15 @@ class _ReadAhead:
         self.dependent = not (fr.flags & 0x20)
         self.thread = threading.Thread(target=self._produce, daemon=True)
         self.thread.start()
+
+    def _put(self, item):
+        while not self.stop.is_set():
+            try:
+                self.q.put(item, timeout=0.05)
+                return True
+            except self._queue_full:
+                pass
+        return False
 
     def _read_batch(self, carried):
         """Whole block records up to batch_bytes -> (records, number of blocks, tail); tail = "more" | ("end", content
@@ -414,7 +455,7 @@ class _ReadAhead:
         fr = self.fr
         carried = b""
         try:
-            while True:
+            while not self.stop.is_set():
                 records, nblocks, tail = self._read_batch(carried)
                 if carried:
                     nblocks += self._count_blocks(carried)
@@ -428,14 +469,14 @@ class _ReadAhead:
                             self.ctx.xxh32_update(fr.content_hasher, plain)
                         if self.dependent:
                             self.window = (self.window + plain[-WINDOW_SIZE:].tobytes())[-WINDOW_SIZE:]
-                        self.q.put(("data", memoryview(plain)))     # the batch's own output buffer: no copy on the way to the caller
+                        self._put(("data", memoryview(plain)))     # the batch's own output buffer: no copy on the way to the caller
                     if status != N.F_OK:
-                        self.q.put(("status", (status, detail)))
+                        self._put(("status", (status, detail)))
                         return
                     if consumed < len(frame) - 4:
                         # a block that decoded to nothing: the reader hands an empty buffer to its caller (read_to_end
                         # stops there, decompress.rs:54-61) and goes on with the next block if it is asked again
-                        self.q.put(("empty", None))
+                        self._put(("empty", None))
                         carried = frame[consumed:len(frame) - 4]
                         if tail == "more":
                             continue
@@ -449,33 +490,33 @@ class _ReadAhead:
                                     self.ctx.xxh32_update(fr.content_hasher, plain)
                                 if self.dependent:
                                     self.window = (self.window + plain[-WINDOW_SIZE:].tobytes())[-WINDOW_SIZE:]
-                                self.q.put(("data", memoryview(plain)))
+                                self._put(("data", memoryview(plain)))
                             if status != N.F_OK:
-                                self.q.put(("status", (status, detail)))
+                                self._put(("status", (status, detail)))
                                 return
                             if consumed < len(fr2) - 4:
-                                self.q.put(("empty", None))
+                                self._put(("empty", None))
                                 carried = fr2[consumed:len(fr2) - 4]
                             else:
                                 carried = b""
                 if tail == "more":
                     continue
                 if tail == "overflow":
-                    self.q.put(("error", BlockSizeOverflow()))
+                    self._put(("error", BlockSizeOverflow()))
                     return
                 if tail[0] == "error":
-                    self.q.put(("error", tail[1]))
+                    self._put(("error", tail[1]))
                     return
                 cks = tail[1]                                # EndMark: verify the content checksum (:206-215)
                 if fr.content_hasher is not None and cks is not None:
                     hasher, fr.content_hasher = fr.content_hasher, None
                     if self.ctx.xxh32_finish(hasher) != cks:
-                        self.q.put(("error", FrameChecksumFail()))
+                        self._put(("error", FrameChecksumFail()))
                         return
-                self.q.put(("end", None))
+                self._put(("end", None))
                 return
         except Exception as e:           # noqa: BLE001 — handed to the consumer
-            self.q.put(("error", e))
+            self._put(("error", e))
 
     def next(self):
         """-> (plaintext of the next batch, frame finished?).  (b"", False) = a block that decoded to nothing; raises what
@@ -494,8 +535,9 @@ class _ReadAhead:
         raise val
 
     def close(self):
+        self.stop.set()
         self.thread.join(timeout=60)
-        if self.own_ctx:
+        if self.own_ctx and not self.thread.is_alive():
             self.ctx.close()
             self.own_ctx = False
 
@@ -538,6 +580,25 @@ class LZ4FrameIoReader:
                 self.buffer = bytearray()
                 self.frame_reader.decode_block(self.buffer, self.dictionary)
         return memoryview(self.buffer)[self.bytes_taken:]
+
+    def close(self):
+        """Stops the read-ahead thread of a reader that is dropped before the end of its frame (idempotent; also run by
+        `with` and on garbage collection)."""
+        if self._ahead is not None:
+            self._ahead.close()
+        self._done = True
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:                # noqa: BLE001 — interpreter shutdown
+            pass
 
     def consume(self, amt):
         self.bytes_taken += amt

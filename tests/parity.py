@@ -393,6 +393,46 @@ def check_streaming_host_mirror(backend, oracle, scale=1):
             out = io.BytesIO()
             cs.compress_with_size(io.BytesIO(data), out)
             assert out.getvalue() == oracle.frame_compress(data, content_size=len(data), **kw)[1], kw
+        # a reader that returns short counts (a pipe): chunks are still cut at block boundaries -> the one-shot frame
+        class Dribble(io.RawIOBase):
+            def __init__(self, data, step):
+                self.d, self.p, self.step = data, 0, step
+            def read(self, n=-1):
+                n = self.step if n is None or n < 0 else min(n, self.step)
+                out = self.d[self.p:self.p + n]
+                self.p += len(out)
+                return out
+        cs = L.CompressionSettings.default().block_size(64 << 10)
+        cs.STREAM_CHUNK_BYTES = 128 << 10
+        out = io.BytesIO()
+        cs.compress(Dribble(data, 50001), out)
+        assert out.getvalue() == oracle.frame_compress(data, block_size=64 << 10)[1]
+        # a writer that fails while the producer thread is ahead: WriteError, and the call returns (no thread left waiting)
+        class Full(io.RawIOBase):
+            def __init__(self):
+                self.n = 0
+            def write(self, b):
+                self.n += 1
+                if self.n >= 2:
+                    raise OSError("disk full")
+                return len(b)
+        cs = L.CompressionSettings.default().block_size(64 << 10)
+        cs.STREAM_CHUNK_BYTES = 64 << 10
+        import threading
+        before = threading.active_count()
+        try:
+            cs.compress(io.BytesIO(data), Full())
+            raise AssertionError("the writer's error was swallowed")
+        except L.WriteError:
+            pass
+        assert threading.active_count() == before
+        # a reader dropped in the middle of its frame: close() (or `with`, or garbage collection) stops the read-ahead thread
+        rc, frame = oracle.frame_compress(data, block_size=64 << 10)
+        with L.LZ4FrameIoReader(L.LZ4FrameReader(io.BytesIO(frame)), b"", read_ahead=64 << 10) as rd:
+            assert bytes(rd.fill_buf()[:100]) == data[:100]
+        assert threading.active_count() == before
+        rd.consume(len(rd.fill_buf()))                   # what was handed out stays valid; nothing comes after it
+        assert rd.fill_buf() == b""
     finally:
         L.raw.set_default_context(None)
 
@@ -628,3 +668,56 @@ def check_fuzz_frame_batches(backend, oracle, seed, count, max_len=120000):
                 (w[0] != 0 or pout[int(oo[k]):int(oo[k]) + int(ol[k])].tobytes() == w[2]), \
                 ("batched decode", seed, i, k, len(frames[k]), int(ocap[k]), int(st[k]), int(det[k]), int(ol[k]), w[0], w[1], len(w[2]))
         assert untouched(pout, oo, ocap, 0xDD), ("decode wrote outside a frame's capacity", seed, i)
+
+
+def check_fuzz_block_batches(backend, oracle, seed, count, use_torch_device=None, max_len=100000):
+    """lzf_compress_blocks / lzf_decompress_blocks on ragged batches of fuzz inputs (check_batched_blocks), then one
+    decode launch over valid, truncated and mutated streams with per-block limits: status and — for blocks that decode —
+    length, bytes and XXH32 equal to the oracle's block by block; a failing block never disturbs its neighbours."""
+    import torch
+    dev = use_torch_device or "cpu"
+    T = lambda a: torch.from_numpy(a.view(np.int64) if a.dtype == np.uint64 else a.view(np.int32) if a.dtype == np.uint32 else a).to(dev)
+    for i in range(count):
+        rng = np.random.default_rng(seed * 86028121 + i)
+        nb = int(rng.integers(1, 40))
+        inputs = [fuzz_input(rng, max_len) for _ in range(nb)]
+        check_batched_blocks(backend, oracle, inputs, use_torch_device=use_torch_device)
+        streams, limits, caps = [], [], []
+        for b in inputs:
+            st, c = oracle.compress_block(b)
+            a = bytearray(c)
+            m = int(rng.integers(0, 4))
+            if m == 1:
+                a = a[: int(rng.integers(1, len(a) + 1))]
+            if m >= 2 and len(a):
+                a[int(rng.integers(0, len(a)))] = int(rng.integers(0, 256))
+            streams.append(bytes(a))
+            limits.append(int(rng.choice([len(b), max(0, len(b) - 1), len(b) + 7])))
+            caps.append(len(b) + 16)
+        lens = np.array([len(s) for s in streams], dtype=np.uint32)
+        in_off = np.zeros(nb, dtype=np.uint64); in_off[1:] = np.cumsum((lens.astype(np.uint64) + 63) // 64 * 64)[:-1]
+        flat = np.zeros(int(in_off[-1]) + len(streams[-1]) + 64, dtype=np.uint8)
+        for k, s in enumerate(streams):
+            flat[int(in_off[k]):int(in_off[k]) + len(s)] = np.frombuffer(s, dtype=np.uint8)
+        capa = np.array(caps, dtype=np.uint32)
+        out_off = np.zeros(nb, dtype=np.uint64); out_off[1:] = np.cumsum((capa.astype(np.uint64) + 63) // 64 * 64)[:-1]
+        d_plain = torch.full((int(out_off[-1]) + caps[-1] + 64,), 0xAB, dtype=torch.uint8, device=dev)
+        d_olen = torch.zeros(nb, dtype=torch.int32, device=dev)
+        d_st = torch.zeros(nb, dtype=torch.int32, device=dev)
+        d_xx = torch.zeros(nb, dtype=torch.int32, device=dev)
+        backend.ctx.decompress_blocks(T(flat), T(in_off), T(lens), nb, d_plain, T(out_off), T(capa), T(np.array(limits, dtype=np.uint32)),
+                                      d_olen, d_st, d_xx)
+        if dev != "cpu":
+            torch.cuda.synchronize()
+        plain = d_plain.cpu().numpy(); olen = d_olen.cpu().numpy().view(np.uint32); st = d_st.cpu().numpy()
+        xx = d_xx.cpu().numpy().view(np.uint32)
+        for k in range(nb):
+            wst, wout, wn = oracle.decompress_raw(streams[k], out_limit=limits[k], cap=caps[k])
+            assert st[k] == wst, ("batched decode status", seed, i, k, len(streams[k]), limits[k], int(st[k]), wst)
+            if wst == 0:
+                o = int(out_off[k])
+                assert olen[k] == wn and plain[o:o + wn].tobytes() == wout and xx[k] == oracle.xxh32(wout), ("batched decode bytes", seed, i, k)
+        mask = np.ones(plain.size, bool)
+        for k in range(nb):
+            mask[int(out_off[k]):int(out_off[k]) + caps[k]] = False
+        assert (plain[mask] == 0xAB).all(), ("decode wrote outside a block's capacity", seed, i)

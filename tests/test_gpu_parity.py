@@ -373,3 +373,4 @@ def test_seeded_structural_fuzz(gpu, oracle):
     parity.check_fuzz_blocks(gpu, oracle, seed=21, count=600)
     parity.check_fuzz_frames(gpu, oracle, seed=21, count=300)
     parity.check_fuzz_frame_batches(gpu, oracle, seed=21, count=150)
+    parity.check_fuzz_block_batches(gpu, oracle, seed=21, count=60, use_torch_device="cuda")

@@ -387,3 +387,4 @@ def test_seeded_structural_fuzz(emu, oracle):                   # 3900 more case
     parity.check_fuzz_blocks(emu, oracle, seed=11, count=90, max_len=60000)
     parity.check_fuzz_frames(emu, oracle, seed=11, count=50, max_len=60000)
     parity.check_fuzz_frame_batches(emu, oracle, seed=11, count=20, max_len=50000)
+    parity.check_fuzz_block_batches(emu, oracle, seed=11, count=6, max_len=40000)
