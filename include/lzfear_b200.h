@@ -228,8 +228,11 @@ int lzf_raw_decompress(lzf_ctx* ctx, const uint8_t* in, size_t n, const uint8_t*
  *   lzf_table_create   U32Table::default() / U16Table::default()  (:32-36,83-87); hashlog 0/12 = reference
  *   lzf_table_reset    *table = T::default()
  *   lzf_table_offset   EncoderTable::offset(by)  (:72-74): positions of later calls are shifted by `by`
- * *status: LZF_OK, LZF_WRITER_FULL, or LZF_PANIC where the reference would panic (:67 "EncoderTable contract
- * violated", :167).  A refused write leaves the table as the reference leaves it (updated up to that point). */
+ * *status: LZF_OK, LZF_WRITER_FULL, or LZF_PANIC where the reference would panic (:167 the size assert; :67,92
+ * "EncoderTable contract violated" — raised for a position that is actually INSERTED beyond the slot width, i.e. never
+ * for the last 7 bytes of the input, and not when the writer refused an earlier sequence first: both orders are
+ * reproduced).  A refused write leaves the table as the reference leaves it (updated up to that point); after
+ * LZF_PANIC the table is unspecified, as it is behind a Rust panic. */
 typedef struct lzf_table lzf_table;
 int lzf_table_create(lzf_ctx* ctx, uint32_t table_kind, uint32_t hashlog, lzf_table** table);
 void lzf_table_destroy(lzf_ctx* ctx, lzf_table* table);

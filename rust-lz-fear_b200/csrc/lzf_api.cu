@@ -389,6 +389,7 @@ int compress_blocks_impl(lzf_ctx* c, const uint8_t* d_in, const uint64_t* d_in_o
         a.chain_first = chains->chain_first; a.chain_count = chains->chain_count; a.nchains = chains->nchains;
         a.max_pos = chains->max_pos; a.table_io = chains->table_io;
         a.fin_pos = chains->fin_pos; a.fin_lit = chains->fin_lit;
+        a.allow_slot_wrap = chains->allow_slot_wrap;
     }
     a.in = d_in; a.in_off = d_in_off; a.in_len = d_in_len; a.nblocks = nblocks;
     a.hashlog = hashlog; a.table_kind = table_kind;
@@ -632,6 +633,48 @@ extern "C" int lzf_table_offset(lzf_ctx* c, lzf_table* t, uint64_t by) {      //
     return LZF_SUCCESS;
 }
 
+namespace {
+// What compress2 returns for a call whose table comes within reach of its slot limit, from the sequence stream `seq` the
+// same parse writes into an unbounded writer.  The reference runs front to back: sequence j's positions are inserted
+// (its probes, then cursor - 2 behind its match, :196,218) BEFORE its bytes are written (:235-236), so it panics in the
+// first sequence that inserts a position p with offset + p > slot_limit unless the writer refused an earlier sequence.
+// The largest position sequence j inserts is c_j - 2 (c_j = end of its match; its probes lie at least 4 bytes in front);
+// the closing literal run probes literal_start, +step, ... while 12 bytes remain (:177-178,225-231).
+int32_t settle_panic_zone(const uint8_t* seq, size_t len, size_t n, size_t cursor, uint64_t offset, uint64_t slot_limit, size_t cap) {
+    auto violates = [&](uint64_t pos) { return offset + pos > slot_limit; };
+    size_t i = 0, pos = cursor;
+    while (i < len) {
+        const size_t seq_start = i;
+        const uint8_t token = seq[i++];
+        size_t lit = token >> 4;
+        if (lit == 15) { uint8_t b; do { b = seq[i++]; lit += b; } while (b == 255 && i < len); }
+        i += lit;
+        if (i >= len) {
+            // the closing run: literals only (:178-190)
+            size_t cur = pos, step_counter = (size_t)1 << 6, step = 1;
+            bool panics = false;
+            while (cur < n && n - cur >= 12) {
+                if (violates(cur)) { panics = true; break; }
+                cur += step;
+                step = step_counter >> 6;
+                if (pos + 1 != cur) step_counter += 1;
+            }
+            if (seq_start > cap) return LZF_WRITER_FULL;          // an earlier sequence did not fit
+            if (panics) return LZF_PANIC;
+            return len > cap ? LZF_WRITER_FULL : LZF_OK;
+        }
+        i += 2;
+        size_t ml = (token & 15);
+        if (ml == 15) { uint8_t b; do { b = seq[i++]; ml += b; } while (b == 255 && i < len); }
+        ml += 4;
+        const size_t match_end = pos + lit + ml;
+        if (violates(match_end - 2)) return seq_start > cap ? LZF_WRITER_FULL : LZF_PANIC;
+        pos = match_end;
+    }
+    return len > cap ? LZF_WRITER_FULL : LZF_OK;
+}
+}  // namespace
+
 extern "C" int lzf_raw_compress2(lzf_ctx* c, const uint8_t* in, size_t n, size_t cursor, lzf_table* t,
                                  uint8_t* out, size_t cap, size_t* written, int32_t* status) {
     if (!c || !t || !written || !status || (n && !in) || (cap && !out) || cursor > n) return LZF_ERR_INVALID_ARG;
@@ -640,10 +683,16 @@ extern "C" int lzf_raw_compress2(lzf_ctx* c, const uint8_t* in, size_t n, size_t
     // assert!(input.len() <= T::payload_size_limit())   :167
     if (n > 0xffffffffull || (t->kind == LZF_TABLE_U16 && n > 0xffffull)) { *status = LZF_PANIC; return LZF_SUCCESS; }
     if (cursor == n) return LZF_SUCCESS;                               // while cursor < input.len() :171 never runs
-    // "EncoderTable contract violated" (:67,92): every position this call can insert must fit the slot
-    if (t->offset + n > (t->kind == LZF_TABLE_U16 ? 0xffffull : 0xffffffffull)) { *status = LZF_PANIC; return LZF_SUCCESS; }
+    // "EncoderTable contract violated" (:67,92) fires when a position that is INSERTED leaves the slot width.  compress2
+    // inserts probe positions <= n - 12 (:178,196) and cursor - 2 <= n - 7 behind a match (:218): a call whose positions
+    // up to n - 7 all fit can not panic.  Beyond that it depends on where the parse actually inserts, and on whether the
+    // writer ran full first: that rare zone (a table within a few bytes of its 64 KiB / 4 GiB limit) is settled below
+    // from the sequence stream of an unbounded run.
+    const uint64_t slot_limit = t->kind == LZF_TABLE_U16 ? 0xffffull : 0xffffffffull;
+    const bool panic_zone = t->offset + n > slot_limit + 7;
     LZF_CU(c, cudaSetDevice(c->device));
-    const size_t capc = cap > 0xffffffffull ? 0xffffffffull : cap;
+    const size_t want_cap = panic_zone ? lzf_compress_bound(n - cursor) : cap;
+    const size_t capc = want_cap > 0xffffffffull ? 0xffffffffull : want_cap;
     int rc;
     if ((rc = ensure_dev(c, cur_slot(c)->d_io_in, n + 64))) return rc;
     if ((rc = ensure_dev(c, cur_slot(c)->d_io_out, capc + 64))) return rc;
@@ -669,6 +718,7 @@ extern "C" int lzf_raw_compress2(lzf_ctx* c, const uint8_t* in, size_t n, size_t
     ch.prefix_len = (const uint32_t*)(d + 24); ch.abs_base = (const uint32_t*)(d + 28);
     ch.chain_first = (const uint32_t*)(d + 32); ch.chain_count = (const uint32_t*)(d + 36); ch.nchains = 1;
     ch.table_io = t->d_slots;
+    ch.allow_slot_wrap = panic_zone ? 1u : 0u;
     // max_block_len 0 ("unknown") keeps plain slots: the carried dict is the reference's, value for value
     rc = compress_blocks_impl(c, (const uint8_t*)cur_slot(c)->d_io_in.p, (const uint64_t*)d, (const uint32_t*)(d + 16), 1, t->hashlog,
                               t->kind, 0, (uint8_t*)cur_slot(c)->d_io_out.p, (const uint64_t*)(d + 8),
@@ -678,6 +728,18 @@ extern "C" int lzf_raw_compress2(lzf_ctx* c, const uint8_t* in, size_t n, size_t
     LZF_CU(c, cudaStreamSynchronize(s));
     const uint32_t olen = *(uint32_t*)(h + 64);
     *status = *(int32_t*)(h + 68);
+    if (panic_zone) {
+        if (*status != LZF_OK) return fail(c, LZF_ERR_CUDA, "unbounded run refused");
+        std::vector<uint8_t> seqs;
+        try { seqs.resize(olen); } catch (...) { return fail(c, LZF_ERR_OOM, "host memory"); }
+        if (olen) {
+            LZF_CU(c, cudaMemcpyAsync(seqs.data(), cur_slot(c)->d_io_out.p, olen, cudaMemcpyDeviceToHost, s));
+            LZF_CU(c, cudaStreamSynchronize(s));
+        }
+        *status = settle_panic_zone(seqs.data(), olen, n, cursor, t->offset, slot_limit, cap);
+        if (*status == LZF_OK) { memcpy(out, seqs.data(), olen); *written = olen; }
+        return LZF_SUCCESS;
+    }
     if (*status == LZF_OK && olen) {
         LZF_CU(c, cudaMemcpyAsync(out, cur_slot(c)->d_io_out.p, olen, cudaMemcpyDeviceToHost, s));
         LZF_CU(c, cudaStreamSynchronize(s));

@@ -259,10 +259,13 @@ encode_blocks_kernel(EncodeArgs a, uint32_t nslots, int n_smem_warps) {
         const bool gated = a.progress != nullptr && cursor0 == 0;
         uint32_t arrived = gated ? 0u : 0xffffffffu;
 
-        // assert!(input.len() <= T::payload_size_limit())  :167 / "EncoderTable contract violated" :67,92;
-        // the slot width must hold every stream position
-        const bool too_big = len64 + ab > 0xffffffffull || (kHash4 && len64 + ab > 0xffffull) ||
-                             (kTab == 1 && len64 + ab > 0x10000ull) || (kPacked && own_len > kPacked17MaxLen) ||
+        // assert!(input.len() <= T::payload_size_limit())  :167 / "EncoderTable contract violated" :67,92: the slot
+        // width must hold every stream position that is INSERTED — probes stop 12 bytes and cursor - 2 lies 7 bytes in
+        // front of the end (:178,218), so a block may reach 7 positions past the limit
+        const uint64_t reach = len64 + ab - (len64 + ab > 7 ? 7 : 0);
+        const bool too_big = len64 > 0xffffffffull || (kHash4 && len64 > 0xffffull) ||
+                             (!a.allow_slot_wrap && (reach > 0xffffffffull || (kHash4 && reach > 0xffffull))) ||
+                             (kTab == 1 && !kHash4 && len64 + ab > 0x10000ull) || (kPacked && own_len > kPacked17MaxLen) ||
                              (a.max_block_len && own_len > a.max_block_len);
         if (too_big) {
             status = LZF_PANIC;

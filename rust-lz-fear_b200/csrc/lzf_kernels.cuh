@@ -35,6 +35,9 @@ struct EncodeArgs {
     // internal (segmented parse): where the closing literal-only sequence of block b starts in its output, and how
     // many literals it holds (null = not wanted)
     uint32_t* fin_pos; uint32_t* fin_lit;
+    // internal (lzf_raw_compress2 next to the table's position limit): parse on even though stream positions leave the
+    // slot width (they wrap); the host decides from the sequence stream where the reference's expect() fires
+    uint32_t allow_slot_wrap;
 };
 // Segmented parse (lzf_set_option LZF_OPT_SEGMENT_BYTES): a launch with too few blocks to fill the GPU cuts every block
 // into S segments that are parsed side by side, each from a table primed with the 64 KiB in front of it, and stitches

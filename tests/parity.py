@@ -272,6 +272,34 @@ def check_raw_compress2_with_history(backend, oracle, table_kind=N.TABLE_U32):
     ctx.table_offset(tab, (1 << 32) - 1000)
     assert ctx.raw_compress2(stream[:70000], 0, tab)[0] == N.PANIC
     ctx.table_free(tab)
+    check_table_limit_zone(backend, oracle, seed=3, count=60)
+
+
+def check_table_limit_zone(backend, oracle, seed, count):
+    """A table within a few bytes of its position limit: the reference's expect() ("EncoderTable contract violated",
+    src/raw/compress/mod.rs:67,92) fires only when a position that leaves the slot width is actually INSERTED (probes end
+    12 bytes, cursor - 2 lies 7 bytes in front of the end), and only if the writer has not refused an earlier sequence.
+    Same status and bytes as the oracle for offsets that end -3..+40 (sometimes +3000) bytes around the limit."""
+    ctx = backend.ctx
+    rng = np.random.default_rng(seed)
+    seen = set()
+    for _ in range(count):
+        kind = N.TABLE_U16 if rng.integers(0, 2) else N.TABLE_U32
+        lim = 0xFFFF if kind == N.TABLE_U16 else 0xFFFFFFFF
+        data = fuzz_input(rng, 60000)[:65535]
+        e = int(rng.integers(-3, 40)) if rng.integers(0, 5) else int(rng.integers(-3, 3000))      # offset + len - limit
+        off = lim - len(data) + e
+        if off < 0:
+            continue
+        cursor = 0 if rng.integers(0, 3) else int(rng.integers(0, len(data) + 1))
+        cap = None if rng.integers(0, 3) == 0 else int(rng.integers(0, len(data) + 20))
+        tab, otab = ctx.table_new(kind), oracle.Table(kind)
+        ctx.table_offset(tab, off); otab.offset(off)
+        got, want = ctx.raw_compress2(data, cursor, tab, cap=cap), oracle.compress2(data, cursor, otab, cap=cap)
+        ctx.table_free(tab)
+        assert got[0] == want[0] and (got[0] != 0 or got[1] == want[1]), (kind, len(data), e, cursor, cap, got[0], want[0])
+        seen.add((want[0], e > 7))
+    return seen
 
 
 def check_segmented_parse(backend, oracle, sizes=(70001, 300000), scale=1):
