@@ -613,12 +613,29 @@ def check_fuzz_frames(backend, oracle, seed, count, max_len=200000):
                 ("frame decompress", seed, i, t, len(a), cap, shown, g[0], g[1], len(g[2]), g[3], w[0], w[1], len(w[2]), w[3])
 
 
-def check_fuzz_frame_batches(backend, oracle, seed, count, max_len=120000):
+def check_fuzz_frame_batches(backend, oracle, seed, count, max_len=120000, device_api=None):
     """lzf_frames_compress / lzf_frames_decompress over batches of 1..13 frames laid out with gaps: random settings, empty
     frames, capacities that fit exactly / miss by a few bytes / are random, truncated and mutated frames among valid ones.
     Every frame must come out exactly as the oracle produces it on its own, a frame that does not fit must fail, and
-    nothing outside a frame's [offset, offset + capacity) may be written."""
+    nothing outside a frame's [offset, offset + capacity) may be written.  device_api = a torch device name: the same
+    batches through lzf_frames_compress_device / lzf_frames_decompress_device with buffers that live there."""
     ctx = backend.ctx
+    if device_api is not None:
+        import torch
+
+        def compress_call(src, in_off, in_len, out, out_off, caps, s):
+            d_out = torch.from_numpy(out).to(device_api)
+            r = ctx.frames_compress_device(torch.from_numpy(src).to(device_api), in_off, in_len, d_out, out_off, caps, s)
+            out[:] = d_out.cpu().numpy()
+            return r
+
+        def decompress_call(packed, do, dl, pout, oo, ocap):
+            d_out = torch.from_numpy(pout).to(device_api)
+            r = ctx.frames_decompress_device(torch.from_numpy(packed).to(device_api), do, dl, d_out, oo, ocap)
+            pout[:] = d_out.cpu().numpy()
+            return r
+    else:
+        compress_call, decompress_call = ctx.frames_compress, ctx.frames_decompress
 
     def layout(sizes, rng, gap):
         off, p = np.zeros(len(sizes), dtype=np.uint64), 0
@@ -659,7 +676,7 @@ def check_fuzz_frame_batches(backend, oracle, seed, count, max_len=120000):
                                          (max(0, len(wants[f][1]) - int(rng.integers(1, 9))) if sel == 3 else int(rng.integers(0, b + 1))))
         out_off, total = layout(caps, rng, 40)
         out = np.full(total + 8, 0xEE, dtype=np.uint8)
-        fl, fs = ctx.frames_compress(src, in_off, in_len, out, out_off, caps, s)
+        fl, fs = compress_call(src, in_off, in_len, out, out_off, caps, s)
         good = []
         for f in range(nf):
             w, o = wants[f], int(out_off[f])
@@ -689,7 +706,7 @@ def check_fuzz_frame_batches(backend, oracle, seed, count, max_len=120000):
         ocap = np.array([len(datas[f]) + int(rng.choice([0, 0, 16, 100])) for f in good], dtype=np.uint64)
         oo, total = layout(ocap, rng, 30)
         pout = np.full(total + 8, 0xDD, dtype=np.uint8)
-        ol, st, det = ctx.frames_decompress(packed, do, dl, pout, oo, ocap)
+        ol, st, det = decompress_call(packed, do, dl, pout, oo, ocap)
         for k in range(len(frames)):
             w = oracle.frame_decompress(frames[k], cap=int(ocap[k]))
             assert (int(st[k]), int(det[k])) == (w[0], w[1]) and \
@@ -749,3 +766,29 @@ def check_fuzz_block_batches(backend, oracle, seed, count, use_torch_device=None
         for k in range(nb):
             mask[int(out_off[k]):int(out_off[k]) + caps[k]] = False
         assert (plain[mask] == 0xAB).all(), ("decode wrote outside a block's capacity", seed, i)
+
+
+def check_examples(oracle, tmp_path, lib_path, scale=1):
+    """examples/dolz4.py and examples/delz4.py in processes of their own; lib_path = the build of the C ABI to load
+    (None: the shipped CUDA library)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    if lib_path:
+        env["LZF_B200_LIB"] = str(lib_path)
+    data = (W.text(300000 * scale, 41).numpy().tobytes() + W.random_bytes(70000, 42).numpy().tobytes() + bytes(100000) +
+            W.lowent(200000 * scale, 43).numpy().tobytes())
+    plain, packed, back = tmp_path / "file.bin", tmp_path / "file.lz4", tmp_path / "file.out"
+    plain.write_bytes(data)
+    subprocess.check_call([sys.executable, os.path.join(root, "examples", "dolz4.py"), str(plain), str(packed)], env=env, timeout=600)
+    assert packed.read_bytes() == oracle.frame_compress(data, content_size=len(data))[1]
+    subprocess.check_call([sys.executable, os.path.join(root, "examples", "delz4.py"), str(packed), str(back)], env=env, timeout=600)
+    assert back.read_bytes() == data
+    # a damaged file: delz4 fails (non-zero exit), it does not write garbage silently
+    bad = bytearray(packed.read_bytes()); bad[len(bad) // 2] ^= 0x10
+    (tmp_path / "bad.lz4").write_bytes(bytes(bad))
+    r = subprocess.run([sys.executable, os.path.join(root, "examples", "delz4.py"), str(tmp_path / "bad.lz4"), str(back)], env=env,
+                       timeout=600, capture_output=True)
+    assert r.returncode != 0 and (b"ChecksumFail" in r.stderr or b"Error" in r.stderr), r.stderr[-300:]

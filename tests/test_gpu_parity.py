@@ -373,4 +373,9 @@ def test_seeded_structural_fuzz(gpu, oracle):
     parity.check_fuzz_blocks(gpu, oracle, seed=21, count=600)
     parity.check_fuzz_frames(gpu, oracle, seed=21, count=300)
     parity.check_fuzz_frame_batches(gpu, oracle, seed=21, count=150)
+    parity.check_fuzz_frame_batches(gpu, oracle, seed=22, count=100, device_api="cuda")
     parity.check_fuzz_block_batches(gpu, oracle, seed=21, count=60, use_torch_device="cuda")
+
+
+def test_examples_dolz4_delz4(gpu, oracle, tmp_path):                       # examples/dolz4.rs, examples/delz4.rs
+    parity.check_examples(oracle, tmp_path, None, scale=16)
