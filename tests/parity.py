@@ -750,8 +750,8 @@ def check_fuzz_block_batches(backend, oracle, seed, count, use_torch_device=None
         d_olen = torch.zeros(nb, dtype=torch.int32, device=dev)
         d_st = torch.zeros(nb, dtype=torch.int32, device=dev)
         d_xx = torch.zeros(nb, dtype=torch.int32, device=dev)
-        backend.ctx.decompress_blocks(T(flat), T(in_off), T(lens), nb, d_plain, T(out_off), T(capa), T(np.array(limits, dtype=np.uint32)),
-                                      d_olen, d_st, d_xx)
+        d_flat, d_ioff, d_lens, d_ooff, d_capa, d_lim = T(flat), T(in_off), T(lens), T(out_off), T(capa), T(np.array(limits, dtype=np.uint32))
+        backend.ctx.decompress_blocks(d_flat, d_ioff, d_lens, nb, d_plain, d_ooff, d_capa, d_lim, d_olen, d_st, d_xx)
         if dev != "cpu":
             torch.cuda.synchronize()
         plain = d_plain.cpu().numpy(); olen = d_olen.cpu().numpy().view(np.uint32); st = d_st.cpu().numpy()
