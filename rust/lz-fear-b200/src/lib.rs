@@ -277,6 +277,181 @@ pub mod framed {
         }
     }
 
+    pub const WINDOW_SIZE: usize = 64 * 1024;
+    const FLAG_INDEPENDENT_BLOCKS: u8 = 0x20;
+    const FLAG_BLOCK_CHECKSUMS: u8 = 0x10;
+    const FLAG_CONTENT_CHECKSUM: u8 = 0x04;
+
+    fn hash_update(st: &mut sys::lzf_xxh32_state, data: &[u8]) -> io::Result<()> {
+        let rc = with_ctx(|c| unsafe { sys::lzf_xxh32_update(c, st, data.as_ptr(), data.len()) })?;
+        if rc != sys::LZF_SUCCESS { return Err(io::Error::new(io::ErrorKind::Other, "lzf_xxh32_update failed")); }
+        Ok(())
+    }
+    fn hash_new() -> sys::lzf_xxh32_state {
+        let mut st: sys::lzf_xxh32_state = unsafe { std::mem::zeroed() };
+        unsafe { sys::lzf_xxh32_init(&mut st) };
+        st
+    }
+    fn read_u32_le<R: Read>(reader: &mut R) -> io::Result<u32> {
+        let mut w = [0u8; 4];
+        reader.read_exact(&mut w)?;
+        Ok(u32::from_le_bytes(w))
+    }
+
+    /// `LZ4FrameReader` (src/framed/decompress.rs:81-279): the header is parsed by `new`, every `decode_block` reads one
+    /// block record and hands its payload to the GPU block decoder.  (The batched, read-ahead form of this loop is
+    /// `lzf_frames_decompress`; this type keeps the reference's block-at-a-time contract for callers that rely on it.)
+    pub struct LZ4FrameReader<R: Read> {
+        reader: R,
+        flags: u8,
+        block_maxsize: usize,
+        content_size: Option<u64>,
+        dictionary_id: Option<u32>,
+        content_hasher: Option<sys::lzf_xxh32_state>,
+        carryover_window: Option<Vec<u8>>,
+        read_buf: Vec<u8>,
+        finished: bool,
+    }
+
+    impl<R: Read> LZ4FrameReader<R> {
+        /// `LZ4FrameReader::new` (:101-161).  The header parser is fed one more byte at a time until it has the whole
+        /// descriptor, so nothing behind the header is taken from `reader`.
+        pub fn new(mut reader: R) -> Result<Self, DecompressionError> {
+            let mut hdr = vec![0u8; 4];
+            reader.read_exact(&mut hdr)?;
+            let info = loop {
+                let mut info: sys::lzf_frame_info = unsafe { std::mem::zeroed() };
+                let mut detail = 0i32;
+                let status = unsafe { sys::lzf_frame_parse_header(hdr.as_ptr(), hdr.len(), &mut info, &mut detail) };
+                match status {
+                    sys::LZF_F_OK => break info,
+                    sys::LZF_F_INPUT_ERROR => {
+                        let mut one = [0u8; 1];
+                        reader.read_exact(&mut one)?;
+                        hdr.push(one[0]);
+                    }
+                    sys::LZF_F_WRONG_MAGIC => return Err(DecompressionError::WrongMagic(u32::from_le_bytes([hdr[0], hdr[1], hdr[2], hdr[3]]))),
+                    sys::LZF_F_HEADER_CHECKSUM_FAIL => return Err(DecompressionError::HeaderChecksumFail),
+                    _ => return Err(DecompressionError::HeaderParseError(detail)),
+                }
+            };
+            let flags = info.flags;
+            Ok(LZ4FrameReader {
+                reader,
+                flags,
+                block_maxsize: info.block_maxsize as usize,
+                content_size: if info.has_content_size != 0 { Some(info.content_size) } else { None },
+                dictionary_id: if info.has_dictionary_id != 0 { Some(info.dictionary_id) } else { None },
+                content_hasher: if flags & FLAG_CONTENT_CHECKSUM != 0 { Some(hash_new()) } else { None },
+                carryover_window: if flags & FLAG_INDEPENDENT_BLOCKS != 0 { None } else { Some(Vec::with_capacity(WINDOW_SIZE)) },
+                read_buf: Vec::new(),
+                finished: false,
+            })
+        }
+
+        pub fn block_size(&self) -> usize { self.block_maxsize }
+        pub fn frame_size(&self) -> Option<u64> { self.content_size }
+        pub fn dictionary_id(&self) -> Option<u32> { self.dictionary_id }
+
+        pub fn into_read(self) -> LZ4FrameIoReader<'static, R> { self.into_read_with_dictionary(&[]) }
+        pub fn into_read_with_dictionary<'a>(self, dictionary: &'a [u8]) -> LZ4FrameIoReader<'a, R> {
+            LZ4FrameIoReader { frame_reader: self, bytes_taken: 0, buffer: Vec::new(), dictionary }
+        }
+
+        /// `decode_block` (:197-279): `output` must be empty; it stays empty once the EndMark has been read.
+        pub fn decode_block(&mut self, output: &mut Vec<u8>, dictionary: &[u8]) -> Result<(), DecompressionError> {
+            assert!(output.is_empty(), "You must pass an empty buffer to this interface.");
+            if self.finished { return Ok(()); }
+            let word = read_u32_le(&mut self.reader)?;
+            if word == 0 {
+                // EndMark, then the content checksum if the header promised one (:206-215)
+                if let Some(hasher) = self.content_hasher.take() {
+                    let expected = read_u32_le(&mut self.reader)?;
+                    if unsafe { sys::lzf_xxh32_finish(&hasher) } != expected { return Err(DecompressionError::FrameChecksumFail); }
+                }
+                self.finished = true;
+                return Ok(());
+            }
+            let is_compressed = word & sys::LZF_INCOMPRESSIBLE == 0;
+            let block_length = (word & !sys::LZF_INCOMPRESSIBLE) as usize;
+            if block_length > self.block_maxsize { return Err(DecompressionError::BlockSizeOverflow); }      // :220-222
+            let mut buf = std::mem::take(&mut self.read_buf);
+            buf.resize(block_length, 0);
+            self.reader.read_exact(&mut buf[..])?;
+            if self.flags & FLAG_BLOCK_CHECKSUMS != 0 {                                                      // :229-234
+                let expected = read_u32_le(&mut self.reader)?;
+                let mut st = hash_new();
+                hash_update(&mut st, &buf)?;
+                if unsafe { sys::lzf_xxh32_finish(&st) } != expected { return Err(DecompressionError::BlockChecksumFail); }
+            }
+            {
+                // dependent blocks: the last 64 KiB of plaintext (or, in front of the first block, the dictionary) are the
+                // decoder's prefix (:238-246)
+                let dec_prefix: &[u8] = match self.carryover_window.as_mut() {
+                    Some(window) => {
+                        if window.is_empty() { window.extend_from_slice(dictionary); }
+                        &window[..]
+                    }
+                    None => dictionary,
+                };
+                if is_compressed {
+                    raw::decompress_raw(&buf, dec_prefix, output, self.block_maxsize).map_err(DecompressionError::CodecError)?;   // :248
+                } else {
+                    output.extend_from_slice(&buf);
+                }
+            }
+            if let Some(window) = self.carryover_window.as_mut() {                                           // :253-269
+                let outlen = output.len();
+                if outlen < WINDOW_SIZE {
+                    let total = window.len() + outlen;
+                    if total > WINDOW_SIZE { window.drain(..total - WINDOW_SIZE); }
+                    window.extend_from_slice(&output[..]);
+                } else {
+                    window.clear();
+                    window.extend_from_slice(&output[outlen - WINDOW_SIZE..]);
+                }
+            }
+            self.read_buf = buf;
+            if output.len() > self.block_maxsize { return Err(DecompressionError::BlockSizeOverflow); }      // :272-274
+            if let Some(hasher) = self.content_hasher.as_mut() { hash_update(hasher, &output[..])?; }              // :276-278
+            Ok(())
+        }
+    }
+
+    /// `LZ4FrameIoReader` (src/framed/decompress.rs:46-77): `Read` + `BufRead` over a frame, one block per refill —
+    /// `LZ4FrameReader::new(file)?.into_read()` of examples/delz4.rs:13.
+    pub struct LZ4FrameIoReader<'a, R: Read> {
+        frame_reader: LZ4FrameReader<R>,
+        bytes_taken: usize,
+        buffer: Vec<u8>,
+        dictionary: &'a [u8],
+    }
+    impl<R: Read> io::BufRead for LZ4FrameIoReader<'_, R> {
+        fn fill_buf(&mut self) -> io::Result<&[u8]> {
+            if self.bytes_taken == self.buffer.len() {
+                self.buffer.clear();
+                self.bytes_taken = 0;
+                self.frame_reader.decode_block(&mut self.buffer, self.dictionary)
+                    .map_err(|e| match e { DecompressionError::InputError(err) => err, other => io::Error::new(io::ErrorKind::Other, other) })?;
+            }
+            Ok(&self.buffer[self.bytes_taken..])
+        }
+        fn consume(&mut self, amt: usize) {
+            self.bytes_taken += amt;
+            assert!(self.bytes_taken <= self.buffer.len(), "You consumed more bytes than I even gave you!");
+        }
+    }
+    impl<R: Read> Read for LZ4FrameIoReader<'_, R> {
+        fn read(&mut self, buf: &mut [u8]) -> io::Result<usize> {
+            use io::BufRead;
+            let mybuf = self.fill_buf()?;
+            let n = std::cmp::min(mybuf.len(), buf.len());
+            buf[..n].copy_from_slice(&mybuf[..n]);
+            self.consume(n);
+            Ok(n)
+        }
+    }
+
     /// `decompress_frame` (src/framed/decompress.rs:283-288): reads one frame from `reader`, returns its plaintext.
     pub fn decompress_frame<R: Read>(mut reader: R) -> Result<Vec<u8>, DecompressionError> {
         let mut input = Vec::new();
