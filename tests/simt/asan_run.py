@@ -35,6 +35,10 @@ def main():
         rc, frame = oracle.frame_compress(inputs[6] + inputs[5], **kw)
         frames += [parity.mutate(frame, 7 * k, k=2) for k in range(10)]
     parity.check_frame_decode_errors(b, oracle, frames)
+    # a slice of the seeded structural fuzz (the whole campaign ran clean under this build once)
+    parity.check_fuzz_blocks(b, oracle, seed=301, count=16, max_len=40000)
+    parity.check_fuzz_frame_batches(b, oracle, seed=303, count=4, max_len=30000)
+    parity.check_table_limit_zone(b, oracle, seed=9, count=16)
     print("ASAN-RUN-OK")
 
 
