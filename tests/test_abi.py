@@ -140,3 +140,16 @@ def test_rust_struct_layouts_match_the_header():
     assert [f[1] for f in cs["lzf_settings"]] == [f[0] for f in _native.Settings._fields_]
     assert [f[1] for f in cs["lzf_frame_info"]] == [f[0] for f in _native.FrameInfo._fields_]
     assert [f[1] for f in cs["lzf_xxh32_state"]] == [f[0] for f in _native.Xxh32State._fields_]
+
+
+def test_feature_patch_applies_to_the_reference_snapshot():
+    """rust/patches/lz-fear-b200-feature.patch is a real unified diff: `patch --dry-run` accepts every hunk against the
+    reference snapshot (skipped where the snapshot is absent, e.g. on the GPU box; a dry run writes nothing)."""
+    import shutil
+    ref = "/root/reference"
+    if not os.path.isdir(os.path.join(ref, "src", "framed")) or shutil.which("patch") is None:
+        pytest.skip("reference snapshot or patch(1) not available")
+    p = subprocess.run(["patch", "--dry-run", "-p1", "-d", ref, "-i", os.path.join(ROOT, "rust", "patches", "lz-fear-b200-feature.patch")],
+                       capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert p.stdout.count("checking file") == 3
