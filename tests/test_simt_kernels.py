@@ -384,11 +384,11 @@ def test_raw_mirror_compress2_with_history(emu, oracle):
 
 
 def test_seeded_structural_fuzz(emu, oracle):                   # 3900 more cases of the same generator were run once by hand
-    parity.check_fuzz_blocks(emu, oracle, seed=11, count=90, max_len=60000)
-    parity.check_fuzz_frames(emu, oracle, seed=11, count=50, max_len=60000)
-    parity.check_fuzz_frame_batches(emu, oracle, seed=11, count=20, max_len=50000)
-    parity.check_fuzz_frame_batches(emu, oracle, seed=12, count=12, max_len=50000, device_api="cpu")
-    parity.check_fuzz_block_batches(emu, oracle, seed=11, count=6, max_len=40000)
+    parity.check_fuzz_blocks(emu, oracle, seed=11, count=60, max_len=60000)
+    parity.check_fuzz_frames(emu, oracle, seed=11, count=35, max_len=60000)
+    parity.check_fuzz_frame_batches(emu, oracle, seed=11, count=12, max_len=50000)
+    parity.check_fuzz_frame_batches(emu, oracle, seed=12, count=8, max_len=50000, device_api="cpu")
+    parity.check_fuzz_block_batches(emu, oracle, seed=11, count=4, max_len=40000)
 
 
 def test_examples_dolz4_delz4(emu, oracle, simt_lib_path, tmp_path):        # examples/dolz4.rs, examples/delz4.rs
