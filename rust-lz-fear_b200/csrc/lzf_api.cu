@@ -100,6 +100,7 @@ struct lzf_ctx {
         uint32_t enc_u32_slots = 0;             // LZF_B200_ENC_U32
         uint32_t enc_smem_warps_p1 = 0;         // LZF_B200_ENC_SMEM_WARPS + 1
         uint32_t dec_ctas_per_sm = 0;           // LZF_B200_DEC_CTAS_PER_SM
+        uint64_t pos_limit = 0xffffffffull;     // LZF_B200_TEST_POS_LIMIT (tests only): last stream position a u32 slot holds
     } tune;
 };
 
@@ -197,6 +198,7 @@ extern "C" int lzf_create(int device, lzf_ctx** out) {
     c->tune.enc_u32_slots = getenv("LZF_B200_ENC_U32") != nullptr;
     if (const char* e = getenv("LZF_B200_ENC_SMEM_WARPS")) { const int v = atoi(e); if (v >= 0) c->tune.enc_smem_warps_p1 = (uint32_t)v + 1; }
     if (const char* e = getenv("LZF_B200_DEC_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1) c->tune.dec_ctas_per_sm = (uint32_t)v; }
+    if (const char* e = getenv("LZF_B200_TEST_POS_LIMIT")) { const unsigned long long v = strtoull(e, nullptr, 10); if (v && v < 0xffffffffull) c->tune.pos_limit = v; }
     if (!ok) { lzf_destroy(c); return LZF_ERR_CUDA; }
     *out = c;
     return LZF_SUCCESS;
@@ -880,8 +882,14 @@ int frames_compress_core(lzf_ctx* c, const lzf_settings* s, const uint8_t* d_in,
     const uint64_t bs = s->block_size;
 
     // ---- plan
+    // A dependent-block stream that leaves the u32 slot width makes the reference panic inside THAT frame ("EncoderTable
+    // contract violated", src/raw/compress/mod.rs:67; the last 7 positions of the stream are never inserted): the frame is
+    // answered with LZF_F_PANIC and takes no part in the launch (planned as empty), the other frames are unaffected.
+    std::vector<uint8_t> frame_panics(nframes, 0);
+    for (uint32_t f = 0; f < nframes; f++) frame_panics[f] = dependent && dlen + in_len[f] > c->tune.pos_limit + 7;
+    auto planned_len = [&](uint32_t f) -> uint64_t { return frame_panics[f] ? 0 : in_len[f]; };
     uint64_t nblocks64 = 0;
-    for (uint32_t f = 0; f < nframes; f++) nblocks64 += (in_len[f] + bs - 1) / bs;
+    for (uint32_t f = 0; f < nframes; f++) nblocks64 += (planned_len(f) + bs - 1) / bs;
     if (nblocks64 > 0x7fffffffull) return fail(c, LZF_ERR_UNSUPPORTED, "too many blocks in one call");
     const uint32_t nblocks = (uint32_t)nblocks64;
 
@@ -925,13 +933,12 @@ int frames_compress_core(lzf_ctx* c, const lzf_settings* s, const uint8_t* d_in,
     uint64_t* ssrc = (uint64_t*)(h + o_ssrc); uint64_t* sdst = (uint64_t*)(h + o_sdst); uint32_t* slen = (uint32_t*)(h + o_slen);
     uint32_t nchains = 0, nstaged = 0;
     uint64_t stage_total = 0, max_pos = 0;
-    bool positions_overflow = false;
     uint32_t b = 0;
     uint64_t comp_total = 0;
     uint32_t max_block_len = 0;
     for (uint32_t f = 0; f < nframes; f++) {
         first[f] = b;
-        const uint64_t n = in_len[f];
+        const uint64_t n = planned_len(f);
         const uint32_t nb = (uint32_t)((n + bs - 1) / bs);
         nblk[f] = nb;
         uint32_t hl = 0;
@@ -959,7 +966,6 @@ int frames_compress_core(lzf_ctx* c, const lzf_settings* s, const uint8_t* d_in,
                 pfx[b] = (uint32_t)hist;
                 absb[b] = (uint32_t)base;
                 prime[b] = dict_history ? (uint32_t)dlen : 0;
-                if (base + hist + l > 0xffffffffull) positions_overflow = true;   // "EncoderTable contract violated" :67
                 if (base + hist + l > max_pos) max_pos = base + hist + l;
                 if (!dependent || i == 0) { cfirst[nchains] = b; ccount[nchains] = 1; nchains++; }
                 else ccount[nchains - 1]++;
@@ -971,7 +977,6 @@ int frames_compress_core(lzf_ctx* c, const lzf_settings* s, const uint8_t* d_in,
             }
         }
     }
-    if (positions_overflow) { for (uint32_t f = 0; f < nframes; f++) status[f] = LZF_F_PANIC; return LZF_SUCCESS; }
     if ((rc = ensure_dev(c, cur_slot(c)->d_comp, comp_total + 64))) return rc;
     // with a dictionary every block address becomes absolute: staged blocks live in their own buffer
     const uint8_t* enc_base = d_in;
@@ -1059,7 +1064,10 @@ int frames_compress_core(lzf_ctx* c, const lzf_settings* s, const uint8_t* d_in,
     LZF_CU(c, cudaStreamSynchronize(st));
     const uint64_t* flen = (const uint64_t*)(hr + r_flen);
     const int32_t* fst = (const int32_t*)(hr + r_fst);
-    for (uint32_t f = 0; f < nframes; f++) { out_len[f] = flen[f]; status[f] = fst[f]; }
+    for (uint32_t f = 0; f < nframes; f++) {
+        out_len[f] = frame_panics[f] ? 0 : flen[f];
+        status[f] = frame_panics[f] ? LZF_F_PANIC : fst[f];
+    }
     return LZF_SUCCESS;
 }
 

@@ -795,3 +795,30 @@ def check_examples(oracle, tmp_path, lib_path, scale=1):
     r = subprocess.run([sys.executable, os.path.join(root, "examples", "delz4.py"), str(tmp_path / "bad.lz4"), str(back)], env=env,
                        timeout=600, capture_output=True)
     assert r.returncode != 0 and (b"ChecksumFail" in r.stderr or b"Error" in r.stderr), r.stderr[-300:]
+
+
+def check_dependent_frame_position_limit(backend, oracle):
+    """A dependent-block stream that leaves the u32 slot width panics in the reference ("EncoderTable contract violated",
+    src/raw/compress/mod.rs:67) — inside that frame only.  With the limit lowered to 200 000 positions for the test
+    (LZF_B200_TEST_POS_LIMIT, read by lzf_create): the two long dependent frames of a batch answer LZF_F_PANIC, the other
+    frames of the same call are the oracle's bytes, and independent frames never care.  The caller sets the environment
+    variable (monkeypatch) and passes a backend created afterwards (backend.fresh())."""
+    ctx = backend.ctx
+    datas = [W.text(n, n).numpy().tobytes() for n in (150000, 200007, 200008, 300000, 70000)]
+    for indep in (False, True):
+        s, _keep = N.make_settings(independent_blocks=indep, block_size=65536)
+        in_len = np.array([len(d) for d in datas], dtype=np.uint64)
+        in_off = np.zeros(len(datas), dtype=np.uint64); in_off[1:] = np.cumsum(in_len)[:-1]
+        src = np.frombuffer(b"".join(datas), dtype=np.uint8).copy()
+        caps = np.array([ctx.frame_bound(s, len(d)) for d in datas], dtype=np.uint64)
+        out_off = np.zeros(len(datas), dtype=np.uint64); out_off[1:] = np.cumsum(caps)[:-1]
+        out = np.zeros(int(caps.sum()), dtype=np.uint8)
+        fl, fs = ctx.frames_compress(src, in_off, in_len, out, out_off, caps, s)
+        assert [int(x) for x in fs] == ([0, 0, N.F_PANIC, N.F_PANIC, 0] if not indep else [0] * 5), list(fs)
+        for f, d in enumerate(datas):
+            if fs[f] == 0:
+                want = oracle.frame_compress(d, independent_blocks=indep, block_size=65536)
+                assert (0, out[int(out_off[f]):int(out_off[f]) + int(fl[f])].tobytes()) == want, f
+            else:
+                assert fl[f] == 0
+        assert ctx.frame_compress(datas[3], independent_blocks=indep, block_size=65536)[0] == (0 if indep else N.F_PANIC)

@@ -379,3 +379,9 @@ def test_seeded_structural_fuzz(gpu, oracle):
 
 def test_examples_dolz4_delz4(gpu, oracle, tmp_path):                       # examples/dolz4.rs, examples/delz4.rs
     parity.check_examples(oracle, tmp_path, None, scale=16)
+
+
+def test_dependent_frame_beyond_the_position_limit_panics_alone(gpu, oracle, monkeypatch):   # src/raw/compress/mod.rs:67
+    monkeypatch.setenv("LZF_B200_TEST_POS_LIMIT", "200000")
+    with gpu.fresh() as b:
+        parity.check_dependent_frame_position_limit(b, oracle)

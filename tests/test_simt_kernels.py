@@ -395,3 +395,9 @@ def test_examples_dolz4_delz4(emu, oracle, simt_lib_path, tmp_path):        # ex
     """The two example programs as a user runs them (separate processes, files in and out): dolz4 writes the frame the
     reference writes (compress_with_size: content size in the header), delz4 restores the file."""
     parity.check_examples(oracle, tmp_path, simt_lib_path)
+
+
+def test_dependent_frame_beyond_the_position_limit_panics_alone(emu, oracle, monkeypatch):   # src/raw/compress/mod.rs:67
+    monkeypatch.setenv("LZF_B200_TEST_POS_LIMIT", "200000")
+    with emu.fresh() as b:
+        parity.check_dependent_frame_position_limit(b, oracle)
