@@ -41,6 +41,8 @@
  * Environment (read ONCE, by lzf_create; tuning and test knobs, never needed for correct results)
  *     LZF_B200_CHUNK_BYTES, LZF_B200_FEED_SLICE, LZF_B200_FEED_MIN_BLOCKS, LZF_B200_ENC_U32,
  *     LZF_B200_ENC_SMEM_WARPS, LZF_B200_DEC_CTAS_PER_SM, LZF_B200_TRACE
+ *     LZF_B200_TEST_POS_LIMIT (tests only): lowers the stream position at which a dependent-block frame answers
+ *     LZF_F_PANIC ("EncoderTable contract violated") from 2^32 - 1, so that the rule can be tested with small frames
  */
 #ifndef LZFEAR_B200_H
 #define LZFEAR_B200_H
