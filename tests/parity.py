@@ -315,6 +315,12 @@ def check_segmented_parse(backend, oracle, sizes=(70001, 300000), scale=1):
         n *= scale
         inputs += [t(n, n), lo(n, n + 1), bytes(n), rnd(n // 3, n) + t(n - n // 3, n + 2), t(n // 2, n + 3) + rnd(n - n // 2, n + 4)]
     inputs += [rnd(200000 * scale, 9), t(65536 * 2 * scale, 5)[:-1], (t(1000, 6) * 400)[: 262144 * scale + 13], t(600000 * scale, 12)]
+    try:                                             # C lz4 as a second, independent decoder of the stitched streams
+        import ctypes
+        c_lz4 = ctypes.CDLL("liblz4.so.1")
+        c_lz4.LZ4_decompress_safe.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
+    except OSError:
+        c_lz4 = None
     ctx.set_option(N.OPT_SEGMENT_BYTES, 65536)
     try:
         worst = 0.0
@@ -328,6 +334,10 @@ def check_segmented_parse(backend, oracle, sizes=(70001, 300000), scale=1):
                 if st == 0:
                     dst, plain, dlen = oracle.decompress_raw(out, out_limit=len(data), cap=len(data) + 64)
                     assert (dst, plain) == (0, data), "segmented stream does not decode to the input (len %d)" % len(data)
+                    if c_lz4 is not None:
+                        buf = ctypes.create_string_buffer(max(len(data), 1))
+                        assert c_lz4.LZ4_decompress_safe(out, buf, len(out), len(data)) == len(data) and buf.raw[:len(data)] == data, \
+                            "C lz4 does not accept the stitched stream (len %d)" % len(data)
                     if ost == 0:
                         # a segment boundary costs up to ~16 bytes (the closing 12-byte / 5-literal rule applies at every
                         # segment end); beyond that fixed cost the size must be within 1 % of the reference's
