@@ -202,6 +202,14 @@ pub mod framed {
         BlockSizeOverflow,
     }
 
+    /// Plaintext handed to the GPU per launch of the streaming `compress` (whole blocks; at least one block).
+    pub const STREAM_CHUNK_BYTES: usize = 1 << 30;
+
+    /// Read until `n` bytes are there or the stream ends — the reference's `take(block_size).read_to_end(..)` (:227).
+    fn read_up_to<R: Read>(reader: &mut R, n: usize, buf: &mut Vec<u8>) -> io::Result<usize> {
+        reader.by_ref().take(n as u64).read_to_end(buf)
+    }
+
     /// `CompressionSettings` (src/framed/compress.rs:36-133): same builder, same defaults (:44-55).
     #[derive(Clone)]
     pub struct CompressionSettings<'a> {
@@ -238,17 +246,54 @@ pub mod framed {
             s
         }
 
-        /// `compress` (:137-140).  The whole input goes through ONE batched launch, so the reader is read to its end first.
-        pub fn compress<R: Read, W: Write>(&self, mut reader: R, writer: W) -> Result<(), CompressionError> {
-            let mut input = Vec::new();
-            reader.read_to_end(&mut input).map_err(CompressionError::ReadError)?;
-            self.compress_buffer(&input, writer, None)
+        /// `compress` (:137-140)
+        pub fn compress<R: Read, W: Write>(&self, reader: R, writer: W) -> Result<(), CompressionError> {
+            self.compress_stream(reader, writer, None)
         }
         /// `compress_with_size_unchecked` (:142-145)
-        pub fn compress_with_size_unchecked<R: Read, W: Write>(&self, mut reader: R, writer: W, content_size: u64) -> Result<(), CompressionError> {
-            let mut input = Vec::new();
-            reader.read_to_end(&mut input).map_err(CompressionError::ReadError)?;
-            self.compress_buffer(&input, writer, Some(content_size))
+        pub fn compress_with_size_unchecked<R: Read, W: Write>(&self, reader: R, writer: W, content_size: u64) -> Result<(), CompressionError> {
+            self.compress_stream(reader, writer, Some(content_size))
+        }
+
+        /// `compress_internal` (:159-282).  Independent blocks without a dictionary are STREAMED: the reader is consumed in
+        /// chunks of whole blocks (`STREAM_CHUNK_BYTES`), every chunk is one batched launch, and its block records are
+        /// spliced into the frame — the records of a chunk compressed on its own are the records the whole frame would hold
+        /// (independent blocks share nothing, :265-270); the content checksum runs over the plaintext as it streams by
+        /// (:172,233-235).  Dependent blocks and dictionaries carry a table from block to block: one call for the whole input.
+        /// (Same scheme as `CompressionSettings._compress_streaming` of the Python mirror, which the test tiers execute.)
+        fn compress_stream<R: Read, W: Write>(&self, mut reader: R, mut writer: W, content_size: Option<u64>) -> Result<(), CompressionError> {
+            let streamable = self.independent_blocks && self.dictionary.is_none()
+                && [64usize << 10, 256 << 10, 1 << 20, 4 << 20].contains(&self.block_size);
+            let chunk_bytes = if streamable { std::cmp::max(self.block_size, STREAM_CHUNK_BYTES / self.block_size * self.block_size) } else { usize::MAX };
+            let mut chunk = Vec::new();
+            read_up_to(&mut reader, chunk_bytes, &mut chunk).map_err(CompressionError::ReadError)?;
+            if !streamable || chunk.len() < chunk_bytes {
+                return self.compress_buffer(&chunk, writer, content_size);          // everything fits one call
+            }
+            // the header as compress_internal writes it (:163-200): taken from an empty frame with the same settings
+            let mut empty = Vec::new();
+            self.compress_buffer(&[], &mut empty, content_size)?;
+            let trailer = 4 + if self.content_checksum { 4 } else { 0 };
+            writer.write_all(&empty[..empty.len() - trailer])?;
+            // a chunk travels as a frame of its own without a content checksum: 7 header bytes | block records | EndMark
+            let mut chunk_settings = self.clone();
+            chunk_settings.content_checksum = false;
+            chunk_settings.dictionary_id = None;
+            let mut hasher = if self.content_checksum { Some(hash_new()) } else { None };
+            let mut framed = Vec::new();
+            while !chunk.is_empty() {
+                framed.clear();
+                chunk_settings.compress_buffer(&chunk, &mut framed, None)?;
+                if let Some(h) = hasher.as_mut() { hash_update(h, &chunk)?; }
+                writer.write_all(&framed[7..framed.len() - 4])?;
+                chunk.clear();
+                read_up_to(&mut reader, chunk_bytes, &mut chunk).map_err(CompressionError::ReadError)?;
+            }
+            writer.write_all(&0u32.to_le_bytes())?;                                  // EndMark :277
+            if let Some(h) = hasher {
+                writer.write_all(&unsafe { sys::lzf_xxh32_finish(&h) }.to_le_bytes())?;   // :279-281
+            }
+            Ok(())
         }
         /// `compress_with_size` (:147-157): the length comes from seeking, as in the reference
         pub fn compress_with_size<R: Read + io::Seek, W: Write>(&self, mut reader: R, writer: W) -> Result<(), CompressionError> {
