@@ -153,3 +153,21 @@ def test_feature_patch_applies_to_the_reference_snapshot():
                        capture_output=True, text=True)
     assert p.returncode == 0, p.stdout + p.stderr
     assert p.stdout.count("checking file") == 3
+
+
+def test_rust_sources_are_lexically_balanced():
+    """No Rust toolchain here: at least brackets, braces and parentheses of the hand-written crate balance outside
+    strings, chars, lifetimes and comments (catches truncated edits; it is not a compile check)."""
+    for rel in ("rust/lz-fear-b200/src/lib.rs", "rust/lz-fear-b200-sys/src/lib.rs", "rust/lz-fear-b200-sys/build.rs"):
+        src = open(os.path.join(ROOT, rel)).read()
+        src = re.sub(r"//[^\n]*", "", src)
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        src = re.sub(r'"(?:\\.|[^"\\])*"', '""', src)
+        src = re.sub(r"'(?:\\.|[^'\\])'", "' '", src)           # char literals; lifetimes ('a) have no closing quote
+        stack, pairs = [], {")": "(", "]": "[", "}": "{"}
+        for i, ch in enumerate(src):
+            if ch in "([{":
+                stack.append(ch)
+            elif ch in pairs:
+                assert stack and stack.pop() == pairs[ch], (rel, src[max(0, i - 80):i + 20])
+        assert not stack, (rel, stack[-3:])
